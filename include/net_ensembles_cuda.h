@@ -1,0 +1,143 @@
+/*
+ * net_ensembles_cuda — C ABI of the B200-native `vertex_load` hot path.
+ *
+ * This header is the drop-in boundary: the entry points below are exactly what a
+ * Rust `extern "C"` block (rust/net_ensembles_cuda.rs), a ctypes stub
+ * (net_ensembles_b200/_lib.py) or the C++ mirror (include/net_ensembles_cuda.hpp)
+ * bind.  Plain pointers and sizes only; no torch / C++ types cross this line.
+ *
+ * Reference interface replaced (all paths relative to the reference repo):
+ *   GenericGraph::vertex_load(&self, include_endpoints: bool) -> Vec<f64>
+ *       src/generic_graph/generic_graph.rs:1310-1385
+ *   MeasurableGraphQuantities::vertex_load + blanket impl for every ensemble
+ *       src/traits/graph_traits.rs:267, :272-331 (method at :328-330)
+ * Input side (what the exporter flattens, once per sampled graph):
+ *   container_iter()/neighbors()/degree()   generic_graph.rs:222, graph_traits.rs:72,75
+ *   NodeContainer.adj: Vec<usize>           src/graph.rs:33-37, neighbors :62-64
+ *   SwContainer.adj: Vec<SwEdge>            src/sw_graph.rs:158-162, neighbors :195-199
+ *
+ * Semantics (identical to the reference): *load* centrality — a vertex's accumulated
+ * value is split EQUALLY among its BFS predecessors (generic_graph.rs:1377-1380); it
+ * is not sigma-weighted Brandes betweenness.  Path counts (sigma) are available from
+ * nec_bfs_debug only and never enter the load value.
+ *
+ * Conventions
+ *   - every function returning int returns NEC_OK (0) on success, a negative NEC_E*
+ *     code otherwise; nec_last_error(ctx) then describes the failure.
+ *   - there is NO CPU fallback: without a usable CUDA device nec_init fails.
+ *   - host pointers passed in are never retained past the call.
+ *   - a context is not thread-safe; use one context per host thread.
+ *   - graphs are simple undirected graphs given as an order-preserving CSR:
+ *     row_ptr[n+1] (u64, row_ptr[0]==0, row_ptr[n]==nnz), col_idx[nnz] (u32 < n),
+ *     every edge stored in both endpoint rows (as the crate's adjacency lists do).
+ */
+#ifndef NET_ENSEMBLES_CUDA_H
+#define NET_ENSEMBLES_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEC_OK 0
+#define NEC_EINVAL (-1)   /* bad argument (null pointer, col_idx out of range, ...) */
+#define NEC_ECUDA (-2)    /* CUDA runtime error (message in nec_last_error) */
+#define NEC_ENOMEM (-3)   /* device or host allocation failed */
+#define NEC_ENODEVICE (-4)/* no CUDA device / wrong architecture: no CPU fallback exists */
+#define NEC_EINTERNAL (-5)/* kernel reported an inconsistency (queue overflow, ...) */
+
+typedef struct nec_ctx nec_ctx;     /* opaque: device, stream, workspace arenas */
+typedef struct nec_graph nec_graph; /* opaque: device-resident CSR of one sampled graph */
+
+/* Library / build identification ("net_ensembles_cuda <version> sm_100a"). */
+const char *nec_version(void);
+
+/* Create a context on CUDA device `devices[0]` (n_devices must be 1 in this
+ * revision; multi-GPU runs use one process + one context per GPU and combine the
+ * per-GPU vectors with an NCCL all-reduce).  devices == NULL
+ * selects the current device. */
+int nec_init(nec_ctx **out, const int *devices, int n_devices);
+void nec_destroy(nec_ctx *ctx);
+
+/* Message for the last failing call on this context ("" if none).  ctx may be NULL:
+ * then the message of the last failing nec_init on this thread is returned. */
+const char *nec_last_error(const nec_ctx *ctx);
+
+/* Run all work of this context on the given cudaStream_t (passed as void*); NULL
+ * restores the context's own stream.  Lets a host framework (e.g. torch) time and
+ * order the kernels on its current stream. */
+int nec_set_stream(nec_ctx *ctx, void *cuda_stream);
+
+/* Cap the scratch arena (bytes of HBM the engine may use for per-batch state);
+ * 0 restores the default (60 % of free device memory at first use). */
+int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
+
+/* Upload one graph (H2D copy of the CSR; validates row_ptr monotonicity and
+ * col_idx < n).  Replaces the per-call traversal of the crate's adjacency lists. */
+int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr,
+                     const uint32_t *col_idx, nec_graph **out);
+void nec_graph_free(nec_ctx *ctx, nec_graph *g);
+
+/* vertex_load(include_endpoints) over all sources: out[n] (host) is overwritten.
+ * Synchronous: returns after the result is in `out`.
+ * Replaces generic_graph.rs:1310 / graph_traits.rs:328-330. */
+int nec_vertex_load(nec_ctx *ctx, const nec_graph *g, int include_endpoints, double *out);
+
+/* Partial load: only the contributions of the listed sources (the `for i in ...` loop
+ * body of generic_graph.rs:1321-1383 restricted to i in sources).  This is the
+ * multi-GPU sharding primitive and the sampled-parity primitive.  sources are vertex
+ * ids < n; duplicates count twice. */
+int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources,
+                            uint32_t n_sources, int include_endpoints, double *out);
+
+/* Same, but the result stays on the device: d_out is a device pointer to n doubles
+ * (overwritten) and the call only enqueues work on the context's stream (no host
+ * synchronisation, no D2H) — the caller may hand d_out straight to ncclAllReduce.
+ * sources is a HOST pointer (copied during the call). */
+int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources,
+                                   uint32_t n_sources, int include_endpoints, double *d_out);
+
+/* Many small graphs in one launch (one CTA per graph, all state in shared memory):
+ * the shape of a Markov chain that measures after every step
+ * (benches/common/mod.rs:79-90).  Graph i has n_per_graph[i] vertices
+ * (1..NEC_BATCH_MAX_N); its row pointers are
+ * row_ptr_concat[row_ptr_offsets[i] .. row_ptr_offsets[i]+n_i] (inclusive end, i.e.
+ * n_i+1 entries, LOCAL: starting at 0) and its neighbour ids (local, < n_i) are
+ * col_idx_concat[col_offsets[i] + row_ptr_local[...]].  out_concat receives the load
+ * vectors back to back (sum n_i doubles).  Results are bit-identical to calling
+ * nec_vertex_load on each graph. */
+#define NEC_BATCH_MAX_N 512u
+int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph,
+                          const uint64_t *row_ptr_offsets, const uint32_t *row_ptr_concat,
+                          const uint64_t *col_offsets, const uint32_t *col_idx_concat,
+                          int include_endpoints, double *out_concat);
+
+/* Intermediate state of one source, for exactness checks: dist[n] (UINT32_MAX =
+ * unreached), npred[n] (number of BFS predecessors), sigma[n] (f64 shortest-path
+ * counts; NOT used by the load), bk[n] (accumulated value b_k after the backward
+ * sweep; 1.0 for unreached).  Any output pointer may be NULL. */
+int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *dist,
+                  uint32_t *npred, double *sigma, double *bk);
+
+/* Counters of the last nec_vertex_load* call on this context. */
+typedef struct nec_stats {
+    uint64_t n_sources;       /* sources processed */
+    uint64_t n_batches;       /* 32-source batches */
+    uint64_t reached_pairs;   /* sum_s |R_s|  (vertices reached, source included) */
+    uint64_t edge_pairs;      /* sum_s E_s    (directed adjacency entries in s's component) */
+    uint64_t vertex_visits;   /* (vertex, level, batch) queue entries expanded, forward pass */
+    uint32_t max_depth;       /* largest BFS depth seen */
+    uint32_t kernel_launches; /* kernels of this library launched by the call */
+    uint32_t wide_batches;    /* batches re-run with 32-bit distances (depth >= 255) */
+    uint32_t n_slots;         /* resident batch slots (CTAs) used */
+    float kernel_ms;          /* CUDA-event time of the traversal kernels (0 for the
+                                 *_device entry point, which does not synchronise) */
+    uint64_t workspace_bytes; /* scratch arena in use */
+} nec_stats;
+int nec_get_stats(const nec_ctx *ctx, nec_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NET_ENSEMBLES_CUDA_H */

@@ -1,0 +1,69 @@
+"""Builds the native artefacts in-tree (no JIT cache): the CUDA library with the C ABI and,
+for tests/bench only, the CPU oracle.  Called by __graft_entry__.build(); nvcc cross-compiles
+sm_100a without a GPU."""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libnet_ensembles_cuda.so")
+ORACLE_PATH = os.path.join(ROOT, "oracle", "build", "liboracle.so")
+
+CUDA_SOURCES = [os.path.join(PKG, "csrc", "nec_api.cu"), os.path.join(PKG, "csrc", "host", "host_api.cpp")]
+CUDA_DEPS = CUDA_SOURCES + [
+    os.path.join(PKG, "csrc", "nec_kernels.cuh"), os.path.join(PKG, "csrc", "nec_small.cuh"),
+    os.path.join(PKG, "csrc", "host", "nec_graphs.hpp"), os.path.join(PKG, "csrc", "host", "nec_rand.hpp"),
+    os.path.join(ROOT, "include", "net_ensembles_cuda.h"),
+]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; net_ensembles_b200 cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_cuda(force=False, verbose=False):
+    if not force and not _stale(LIB_PATH, CUDA_DEPS):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + CUDA_SOURCES + ["-o", LIB_PATH]
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)   # the image's $CC wrapper is not a valid nvcc host compiler
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def build_oracle(force=False):
+    src = os.path.join(ROOT, "oracle", "ref_vertex_load.c")
+    if not force and not _stale(ORACLE_PATH, [src, os.path.join(ROOT, "oracle", "Makefile")]):
+        return ORACLE_PATH
+    res = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")] + (["-B"] if force else []),
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return ORACLE_PATH
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_oracle(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force=True, verbose=True))

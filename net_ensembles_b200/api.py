@@ -1,0 +1,266 @@
+"""Python host side of the vertex_load path: mirrors the reference's operator interface
+(`vertex_load(include_endpoints)` on graphs and ensembles — /root/reference
+src/generic_graph/generic_graph.rs:1310, src/traits/graph_traits.rs:267,272-331) over the
+C ABI.  Everything numeric happens in the CUDA library; this file only moves buffers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import NecStats, c_int, c_u32, c_u64, c_vp
+
+
+class NecError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("net_ensembles_cuda error %d: %s" % (code, message))
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data_as(c_vp) if a is not None else None
+
+
+class Context:
+    """One GPU, one stream, one workspace (nec_ctx).  Not thread-safe."""
+
+    def __init__(self, device=None):
+        self._lib = _lib.load()
+        h = c_vp()
+        dev = (c_int * 1)(device) if device is not None else None
+        rc = self._lib.nec_init(ctypes.byref(h), dev, 1)
+        if rc != 0:
+            raise NecError(rc, self._lib.nec_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nec_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NecError(rc, self._lib.nec_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._check(self._lib.nec_set_stream(self._h, c_vp(cuda_stream) if cuda_stream else None))
+
+    def set_workspace_limit(self, nbytes):
+        self._check(self._lib.nec_set_workspace_limit(self._h, int(nbytes)))
+
+    def stats(self):
+        s = NecStats()
+        self._check(self._lib.nec_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def upload(self, row_ptr, col_idx):
+        return DeviceGraph(self, row_ptr, col_idx)
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class DeviceGraph:
+    """Device-resident CSR of one sampled graph (nec_graph): export once, measure many times."""
+
+    def __init__(self, ctx, row_ptr, col_idx):
+        self.ctx = ctx
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        self.n = int(row_ptr.shape[0]) - 1
+        self.nnz = int(col_idx.shape[0])
+        h = c_vp()
+        ctx._check(ctx._lib.nec_graph_upload(ctx._h, self.n, self.nnz, _ptr(row_ptr), _ptr(col_idx), ctypes.byref(h)))
+        self._h = h
+
+    def free(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.nec_graph_free(self.ctx._h, self._h)
+        self._h = None
+
+    __del__ = free
+
+    def vertex_load(self, include_endpoints):
+        out = np.empty(self.n, dtype=np.float64)
+        self.ctx._check(self.ctx._lib.nec_vertex_load(self.ctx._h, self._h, int(bool(include_endpoints)), _ptr(out)))
+        return out
+
+    def vertex_load_sources(self, sources, include_endpoints):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.empty(self.n, dtype=np.float64)
+        self.ctx._check(self.ctx._lib.nec_vertex_load_sources(self.ctx._h, self._h, _ptr(src), src.shape[0],
+                                                              int(bool(include_endpoints)), _ptr(out)))
+        return out
+
+    def vertex_load_sources_device(self, sources, include_endpoints, d_out_ptr):
+        """Partial load into a caller-owned device buffer of n doubles (integer device pointer)."""
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        self.ctx._check(self.ctx._lib.nec_vertex_load_sources_device(self.ctx._h, self._h, _ptr(src), src.shape[0],
+                                                                     int(bool(include_endpoints)), c_vp(d_out_ptr)))
+
+    def bfs_debug(self, source):
+        n = self.n
+        dist, npred = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        sigma, bk = np.empty(n, np.float64), np.empty(n, np.float64)
+        self.ctx._check(self.ctx._lib.nec_bfs_debug(self.ctx._h, self._h, int(source), _ptr(dist), _ptr(npred), _ptr(sigma), _ptr(bk)))
+        return dist, npred, sigma, bk
+
+
+def vertex_load_batch(ctx, graphs, include_endpoints):
+    """graphs: list of (row_ptr, col_idx) with LOCAL ids, each n <= NEC_BATCH_MAX_N.
+    One launch, one CTA per graph.  Returns a list of load vectors."""
+    ns = np.array([len(rp) - 1 for rp, _ in graphs], dtype=np.uint32)
+    rp_off = np.zeros(len(graphs), dtype=np.uint64)
+    col_off = np.zeros(len(graphs), dtype=np.uint64)
+    if len(graphs):
+        rp_off[1:] = np.cumsum(ns[:-1].astype(np.uint64) + 1)
+        col_off[1:] = np.cumsum([len(c) for _, c in graphs][:-1])
+    rp_cat = np.concatenate([np.asarray(rp, dtype=np.uint32) for rp, _ in graphs]) if len(graphs) else np.zeros(0, np.uint32)
+    col_cat = np.concatenate([np.asarray(c, dtype=np.uint32) for _, c in graphs] + [np.zeros(0, np.uint32)])
+    out = np.empty(int(ns.sum()), dtype=np.float64)
+    ctx._check(ctx._lib.nec_vertex_load_batch(ctx._h, len(graphs), _ptr(ns), _ptr(rp_off), _ptr(np.ascontiguousarray(rp_cat)),
+                                              _ptr(col_off), _ptr(np.ascontiguousarray(col_cat)),
+                                              int(bool(include_endpoints)), _ptr(out)))
+    return np.split(out, np.cumsum(ns)[:-1]) if len(graphs) else []
+
+
+class _HostGraph:
+    """Base of the host-side mirrors: owns a nech handle (adjacency lists live in C++)."""
+
+    def __init__(self, handle):
+        self._lib = _lib.load()
+        if not handle:
+            raise ValueError(self._lib.nech_last_error().decode())
+        self._h = c_vp(handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.nech_free(self._h)
+            self._h = None
+
+    def vertex_count(self):
+        return int(self._lib.nech_vertex_count(self._h))
+
+    def edge_count(self):
+        return int(self._lib.nech_edge_count(self._h))
+
+    def add_edge(self, a, b):
+        """True if added, False if the edge exists (GraphErrors::EdgeExists)."""
+        rc = self._lib.nech_add_edge(self._h, a, b)
+        if rc < 0:
+            raise ValueError(self._lib.nech_last_error().decode())
+        return bool(rc)
+
+    def remove_edge(self, a, b):
+        rc = self._lib.nech_remove_edge(self._h, a, b)
+        if rc < 0:
+            raise ValueError(self._lib.nech_last_error().decode())
+        return bool(rc)
+
+    def export_csr(self):
+        """Order-preserving CSR (row_ptr u64[n+1], col_idx u32[nnz]) of the adjacency lists."""
+        n, nnz = self.vertex_count(), int(self._lib.nech_nnz(self._h))
+        row_ptr, col = np.empty(n + 1, np.uint64), np.empty(nnz, np.uint32)
+        self._lib.nech_export_csr(self._h, _ptr(row_ptr), _ptr(col))
+        return row_ptr, col
+
+    def adjacency(self):
+        rp, col = self.export_csr()
+        return [col[int(rp[i]):int(rp[i + 1])].tolist() for i in range(len(rp) - 1)]
+
+    def vertex_load(self, include_endpoints, ctx=None):
+        """Drop-in for `vertex_load(include_endpoints)`: export to CSR, run on the GPU, return
+        a fresh f64 vector.  Raises NecError on any device failure (no CPU fallback)."""
+        ctx = ctx or default_context()
+        out = np.empty(self.vertex_count(), dtype=np.float64)
+        rc = self._lib.nech_vertex_load_cuda(self._h, ctx._h, int(bool(include_endpoints)), _ptr(out))
+        if rc != 0:
+            raise NecError(rc, self._lib.nech_last_error().decode())
+        return out
+
+    def to_device(self, ctx=None):
+        ctx = ctx or default_context()
+        return DeviceGraph(ctx, *self.export_csr())
+
+
+class Graph(_HostGraph):
+    """`Graph<T>` = GenericGraph with plain adjacency lists (src/graph.rs:309)."""
+
+    def __init__(self, n, _handle=None):
+        lib = _lib.load()
+        super().__init__(_handle if _handle is not None else lib.nech_graph_new(n))
+
+
+class _Ensemble(_HostGraph):
+    def graph(self):
+        return self
+
+    def randomize(self):
+        if self._lib.nech_randomize(self._h) != 0:
+            raise ValueError(self._lib.nech_last_error().decode())
+
+    def m_steps(self, count):
+        if self._lib.nech_m_steps(self._h, count) != 0:
+            raise ValueError(self._lib.nech_last_error().decode())
+
+    def m_step(self):
+        self.m_steps(1)
+
+    def rng_state(self):
+        """(state, increment) of the Pcg64 as Python ints."""
+        s = np.zeros(4, dtype=np.uint64)
+        self._lib.nech_rng_state(self._h, _ptr(s))
+        return int(s[0]) | (int(s[1]) << 64), int(s[2]) | (int(s[3]) << 64)
+
+
+class ErEnsembleC(_Ensemble):
+    """ErEnsembleC::new(n, c_target, Pcg64::seed_from_u64(seed)) (src/er_c.rs:239)."""
+
+    def __init__(self, n, c_target, seed):
+        super().__init__(_lib.load().nech_erc_new(n, c_target, seed))
+
+
+class ErEnsembleM(_Ensemble):
+    """ErEnsembleM::new(n, m, rng) (src/er_m.rs:245); O(n^2) memory like the crate."""
+
+    def __init__(self, n, m, seed):
+        super().__init__(_lib.load().nech_erm_new(n, m, seed))
+
+
+class SwEnsemble(_Ensemble):
+    """SwEnsemble::new(n, r_prob, rng) / new_with_distance (src/sw.rs:214,234)."""
+
+    def __init__(self, n, r_prob, seed, ring_distance=2):
+        super().__init__(_lib.load().nech_sw_new(n, r_prob, seed, ring_distance))
+
+    def root_targets(self):
+        out = np.empty(int(self._lib.nech_nnz(self._h)), np.uint32)
+        self._lib.nech_sw_root_targets(self._h, _ptr(out))
+        return out
+
+
+class BAensemble(_Ensemble):
+    """BAensemble::new(n, rng, m, source_n) (src/barabasi_albert.rs:89); O(n^2) like the crate."""
+
+    def __init__(self, n, seed, m, source_n):
+        super().__init__(_lib.load().nech_ba_new(n, m, source_n, seed))
+
+
+def gnm_scalable(n, m, seed):
+    """G(n,m) for sizes the crate's ErEnsembleM cannot reach; not seed-identical to the crate."""
+    return Graph(n, _handle=_lib.load().nech_gnm_scalable(n, m, seed))
+
+
+def ba_scalable(n, m, source_n, seed):
+    """Barabasi-Albert for sizes the crate's BAensemble cannot reach; not seed-identical."""
+    return Graph(n, _handle=_lib.load().nech_ba_scalable(n, m, source_n, seed))

@@ -1,0 +1,190 @@
+// C entry points over the host-side graph/ensemble mirror (nec_graphs.hpp) for the Python
+// harness (ctypes).  `nech_` = net_ensembles_cuda host.  These build the INPUT graphs of the
+// hot path and call it through the public C ABI; they contain no load arithmetic and no CPU
+// implementation of vertex_load.
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+
+#include "../../../include/net_ensembles_cuda.h"
+#include "nec_graphs.hpp"
+
+using namespace nec_host;
+
+namespace {
+thread_local std::string g_err;
+
+enum class Kind { Plain, ErC, ErM, Sw, BA };
+
+struct Handle {
+    Kind kind;
+    std::unique_ptr<Graph> plain;
+    std::unique_ptr<ErEnsembleC> erc;
+    std::unique_ptr<ErEnsembleM> erm;
+    std::unique_ptr<SwEnsemble> sw;
+    std::unique_ptr<BAensemble> ba;
+
+    const Graph *plain_graph() const {
+        switch (kind) {
+            case Kind::Plain: return plain.get();
+            case Kind::ErC: return &erc->graph;
+            case Kind::ErM: return &erm->graph;
+            case Kind::BA: return &ba->graph;
+            default: return nullptr;
+        }
+    }
+    Pcg64 *rng() {
+        switch (kind) {
+            case Kind::ErC: return &erc->rng;
+            case Kind::ErM: return &erm->rng;
+            case Kind::Sw: return &sw->rng;
+            case Kind::BA: return &ba->rng;
+            default: return nullptr;
+        }
+    }
+};
+
+template <class F>
+auto guarded(F &&f, decltype(f()) on_error) -> decltype(f()) {
+    try {
+        return f();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return on_error;
+    }
+}
+
+template <class F>
+auto with_graph(const Handle *h, F &&f) {
+    if (h->kind == Kind::Sw) return f(h->sw->graph);
+    return f(*h->plain_graph());
+}
+}  // namespace
+
+extern "C" {
+
+const char *nech_last_error(void) { return g_err.c_str(); }
+
+void *nech_graph_new(uint64_t n) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::Plain}; h->plain.reset(new Graph(n)); return h; }, nullptr);
+}
+void *nech_erc_new(uint64_t n, double c, uint64_t seed) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::ErC}; h->erc.reset(new ErEnsembleC(n, c, Pcg64::seed_from_u64(seed))); return h; }, nullptr);
+}
+void *nech_erm_new(uint64_t n, uint64_t m, uint64_t seed) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::ErM}; h->erm.reset(new ErEnsembleM(n, m, Pcg64::seed_from_u64(seed))); return h; }, nullptr);
+}
+void *nech_sw_new(uint64_t n, double r_prob, uint64_t seed, uint64_t ring_distance) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::Sw}; h->sw.reset(new SwEnsemble(n, r_prob, Pcg64::seed_from_u64(seed), ring_distance)); return h; }, nullptr);
+}
+void *nech_ba_new(uint64_t n, uint64_t m, uint64_t source_n, uint64_t seed) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::BA}; h->ba.reset(new BAensemble(n, Pcg64::seed_from_u64(seed), m, source_n)); return h; }, nullptr);
+}
+// scalable, distribution-equivalent producers for the large benchmark shapes (plain Graph)
+void *nech_gnm_scalable(uint64_t n, uint64_t m, uint64_t seed) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::Plain}; h->plain.reset(new Graph(gnm_scalable(n, m, Pcg64::seed_from_u64(seed)))); return h; }, nullptr);
+}
+void *nech_ba_scalable(uint64_t n, uint64_t m, uint64_t source_n, uint64_t seed) {
+    return guarded([&]() -> void * { auto h = new Handle{Kind::Plain}; h->plain.reset(new Graph(ba_scalable(n, m, source_n, Pcg64::seed_from_u64(seed)))); return h; }, nullptr);
+}
+void nech_free(void *p) { delete static_cast<Handle *>(p); }
+
+uint64_t nech_vertex_count(const void *p) {
+    return with_graph(static_cast<const Handle *>(p), [](auto &g) { return (uint64_t)g.vertex_count(); });
+}
+uint64_t nech_edge_count(const void *p) {
+    return with_graph(static_cast<const Handle *>(p), [](auto &g) { return (uint64_t)g.edge_count; });
+}
+uint64_t nech_nnz(const void *p) {
+    return with_graph(static_cast<const Handle *>(p), [](auto &g) { return (uint64_t)g.nnz(); });
+}
+
+// 1 = done, 0 = GraphErrors::EdgeExists / EdgeDoesNotExist, -1 = invalid indices
+int nech_add_edge(void *p, uint32_t a, uint32_t b) {
+    auto h = static_cast<Handle *>(p);
+    return guarded([&]() -> int {
+        if (h->kind == Kind::Sw) return h->sw->graph.add_edge(a, b) ? 1 : 0;
+        return const_cast<Graph *>(h->plain_graph())->add_edge(a, b) ? 1 : 0; }, -1);
+}
+int nech_remove_edge(void *p, uint32_t a, uint32_t b) {
+    auto h = static_cast<Handle *>(p);
+    return guarded([&]() -> int {
+        if (h->kind == Kind::Sw) return h->sw->graph.remove_edge(a, b) ? 1 : 0;
+        return const_cast<Graph *>(h->plain_graph())->remove_edge(a, b) ? 1 : 0; }, -1);
+}
+
+// SimpleSample::randomize
+int nech_randomize(void *p) {
+    auto h = static_cast<Handle *>(p);
+    return guarded([&]() -> int {
+        switch (h->kind) {
+            case Kind::ErC: h->erc->randomize(); return 0;
+            case Kind::ErM: h->erm->randomize(); return 0;
+            case Kind::Sw: h->sw->randomize(); return 0;
+            case Kind::BA: h->ba->randomize(); return 0;
+            default: g_err = "randomize: not an ensemble"; return -1;
+        } }, -1);
+}
+// `count` Markov steps (MarkovChain::m_steps_quiet of the external `sampling` crate is a
+// plain loop over m_step; BAensemble has no Markov chain in the reference)
+int nech_m_steps(void *p, uint64_t count) {
+    auto h = static_cast<Handle *>(p);
+    return guarded([&]() -> int {
+        for (uint64_t k = 0; k < count; ++k) switch (h->kind) {
+            case Kind::ErC: h->erc->m_step(); break;
+            case Kind::ErM: h->erm->m_step(); break;
+            case Kind::Sw: h->sw->m_step(); break;
+            default: g_err = "m_steps: ensemble has no Markov chain"; return -1;
+        }
+        return 0; }, -1);
+}
+
+int nech_export_csr(const void *p, uint64_t *row_ptr, uint32_t *col_idx) {
+    return guarded([&]() -> int {
+        with_graph(static_cast<const Handle *>(p), [&](auto &g) { g.export_csr(row_ptr, col_idx); return 0; });
+        return 0; }, -1);
+}
+// per adjacency entry (CSR order): pristine ring target of a root edge, 0xFFFFFFFF otherwise
+int nech_sw_root_targets(const void *p, uint32_t *out) {
+    auto h = static_cast<const Handle *>(p);
+    if (h->kind != Kind::Sw) { g_err = "not a small-world ensemble"; return -1; }
+    size_t at = 0;
+    for (auto &c : h->sw->graph.vertices)
+        for (auto &e : c.adj) out[at++] = e.root_target;
+    return 0;
+}
+// generator state as 4 x u64: state lo, state hi, increment lo, increment hi
+int nech_rng_state(void *p, uint64_t *out4) {
+    Pcg64 *r = static_cast<Handle *>(p)->rng();
+    if (!r) { g_err = "no rng"; return -1; }
+    out4[0] = (uint64_t)r->state; out4[1] = (uint64_t)(r->state >> 64);
+    out4[2] = (uint64_t)r->increment; out4[3] = (uint64_t)(r->increment >> 64);
+    return 0;
+}
+
+// The drop-in call: <ensemble or graph>.vertex_load(include_endpoints) — export the
+// adjacency lists to CSR once, upload, run the CUDA path, free.  out: n doubles.
+int nech_vertex_load_cuda(const void *p, nec_ctx *ctx, int include_endpoints, double *out) {
+    return guarded([&]() -> int {
+        return with_graph(static_cast<const Handle *>(p), [&](auto &g) -> int {
+            std::vector<uint64_t> row_ptr(g.vertex_count() + 1);
+            std::vector<uint32_t> col(g.nnz());
+            g.export_csr(row_ptr.data(), col.data());
+            nec_graph *dg = nullptr;
+            int rc = nec_graph_upload(ctx, (uint32_t)g.vertex_count(), col.size(), row_ptr.data(), col.data(), &dg);
+            if (rc != NEC_OK) { g_err = nec_last_error(ctx); return rc; }
+            rc = nec_vertex_load(ctx, dg, include_endpoints, out);
+            if (rc != NEC_OK) g_err = nec_last_error(ctx);
+            nec_graph_free(ctx, dg);
+            return rc;
+        }); }, NEC_EINVAL);
+}
+
+// raw generator access, for the known-answer tests of the rand restatement
+void nech_pcg64_draws(uint64_t seed, uint64_t count, uint64_t *out_u64) {
+    Pcg64 r = Pcg64::seed_from_u64(seed);
+    for (uint64_t k = 0; k < count; ++k) out_u64[k] = r.next_u64();
+}
+
+}  // extern "C"

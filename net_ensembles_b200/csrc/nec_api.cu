@@ -1,0 +1,504 @@
+// C ABI of net_ensembles_cuda (include/net_ensembles_cuda.h): context, device CSR, the
+// vertex_load entry points and their workspace management.  All compute happens in the
+// kernels of nec_kernels.cuh / nec_small.cuh; there is no host implementation of the
+// algorithm here and no fallback when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/net_ensembles_cuda.h"
+#include "nec_kernels.cuh"
+#include "nec_small.cuh"
+
+namespace {
+
+thread_local std::string g_init_error;
+
+struct Arena {                       // per-slot scratch of the batched engine
+    void *base = nullptr;
+    size_t bytes = 0;
+    // layout parameters the arena was built for
+    uint32_t n = 0, n_slots = 0, dist_bytes = 0, max_levels = 0;
+    size_t qcap = 0;
+    // carved pointers
+    uint8_t *dist = nullptr; size_t dist_stride = 0;
+    double *q = nullptr;     size_t q_stride = 0;
+    uint32_t *mask = nullptr; size_t mask_stride = 0;
+    double *bslot = nullptr; size_t bslot_stride = 0;
+    uint2 *queue = nullptr;  size_t queue_stride = 0;
+    uint32_t *lvl = nullptr; size_t lvl_stride = 0;
+};
+
+}  // namespace
+
+struct nec_graph {
+    uint32_t n = 0;
+    uint64_t nnz = 0;
+    uint32_t *d_row_ptr = nullptr;   // n+1
+    uint32_t *d_col_idx = nullptr;   // nnz
+    uint32_t max_degree = 0;
+};
+
+struct nec_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t ws_limit = 0;
+    Arena arena;
+    // small device buffers reused across calls
+    uint32_t *d_sources = nullptr; size_t d_sources_cap = 0;
+    uint8_t *d_status = nullptr;   size_t d_status_cap = 0;
+    uint32_t *d_worklist = nullptr; size_t d_worklist_cap = 0;
+    unsigned long long *d_counters = nullptr;       // 4
+    double *d_out = nullptr; size_t d_out_cap = 0;  // result staging for host-pointer calls
+    int occ_u8 = 0, occ_u32 = 0;
+    nec::SmallWorkspace small;
+    nec_stats stats{};
+};
+
+namespace {
+
+int fail(nec_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+    return code;
+}
+
+#define NEC_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? NEC_ENOMEM : NEC_ECUDA,          \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                        \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <class T>
+int grow(nec_ctx *ctx, T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return NEC_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    NEC_CUDA(ctx, cudaMalloc((void **)&ptr, need * sizeof(T)));
+    cap = need;
+    return NEC_OK;
+}
+
+size_t per_slot_bytes(uint32_t n, uint32_t dist_bytes, size_t qcap, uint32_t max_levels) {
+    size_t b = 0;
+    b += align_up((size_t)n * nec::kLanes * dist_bytes, 256);
+    b += align_up((size_t)n * nec::kLanes * sizeof(double), 256);
+    b += align_up((size_t)n * 2 * sizeof(uint32_t), 256);
+    b += align_up((size_t)n * sizeof(double), 256);
+    b += align_up(qcap * sizeof(uint2), 256);
+    b += align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);
+    return b;
+}
+
+// Build (or reuse) the arena for (n, distance width, wanted slots).
+int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots) {
+    Arena &a = ctx->arena;
+    const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
+    size_t free_b = 0, total_b = 0;
+    NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + a.bytes) * 0.6);
+    // queue capacity: every vertex can sit on at most 32 distinct levels of one batch
+    size_t qcap = (size_t)n * nec::kLanes + nec::kLanes;
+    uint32_t slots = want_slots;
+    size_t ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
+    if (ps * slots > budget) {
+        // prefer keeping one slot per SM; shrink the queue bound (overflow is detected) first
+        const uint32_t floor_slots = std::min<uint32_t>(slots, (uint32_t)ctx->prop.multiProcessorCount);
+        while (ps * floor_slots > budget && qcap > (size_t)n * 4 + nec::kLanes) {
+            qcap = std::max((size_t)n * 4 + nec::kLanes, qcap / 2);
+            ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
+        }
+        slots = (uint32_t)std::min<size_t>(slots, budget / ps);
+        if (slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one batch slot (%zu B) for n=%u", budget, ps, n);
+    }
+    const bool reuse = a.base && a.n == n && a.dist_bytes == dist_bytes && a.n_slots >= slots && a.qcap == qcap;
+    if (!reuse) {
+        if (a.base) cudaFree(a.base);
+        a = Arena{};
+        const size_t bytes = ps * slots;
+        cudaError_t e = cudaMalloc(&a.base, bytes);
+        if (e != cudaSuccess) { a = Arena{}; return fail(ctx, NEC_ENOMEM, "cudaMalloc(%zu B workspace) failed: %s", bytes, cudaGetErrorString(e)); }
+        a.bytes = bytes; a.n = n; a.n_slots = slots; a.dist_bytes = dist_bytes; a.qcap = qcap; a.max_levels = max_levels;
+        // planes are grouped by kind so that one memset clears all slots' masks / partial loads
+        uint8_t *p = (uint8_t *)a.base;
+        auto carve = [&](size_t per_slot) { uint8_t *r = p; p += align_up(per_slot, 256) * slots; return r; };
+        a.dist = carve((size_t)n * nec::kLanes * dist_bytes);      a.dist_stride = align_up((size_t)n * nec::kLanes * dist_bytes, 256);
+        a.q = (double *)carve((size_t)n * nec::kLanes * 8);         a.q_stride = align_up((size_t)n * nec::kLanes * 8, 256) / 8;
+        a.mask = (uint32_t *)carve((size_t)n * 2 * 4);              a.mask_stride = align_up((size_t)n * 2 * 4, 256) / 4;
+        a.bslot = (double *)carve((size_t)n * 8);                   a.bslot_stride = align_up((size_t)n * 8, 256) / 8;
+        a.queue = (uint2 *)carve(qcap * 8);                         a.queue_stride = align_up(qcap * 8, 256) / 8;  // pitch; >= qcap
+        a.lvl = (uint32_t *)carve(((size_t)max_levels + 2) * 4);    a.lvl_stride = align_up(((size_t)max_levels + 2) * 4, 256) / 4;
+    }
+    return NEC_OK;
+}
+
+template <typename DistT, bool kDebug>
+int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
+                  uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk) {
+    const Arena &a = ctx->arena;
+    nec::EngineParams p{};
+    p.n = g->n; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
+    p.sources = ctx->d_sources; p.n_sources = n_sources;
+    p.work_list = d_worklist; p.n_work = n_work; p.include_endpoints = include_endpoints;
+    p.dist_base = a.dist; p.dist_stride = a.dist_stride;
+    p.q_base = a.q; p.q_stride = a.q_stride;
+    p.mask_base = a.mask; p.mask_stride = a.mask_stride;
+    p.bslot_base = a.bslot; p.bslot_stride = a.bslot_stride;
+    p.queue_base = a.queue; p.queue_stride = a.queue_stride;   // pitch doubles as capacity
+    p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride;
+    p.max_levels = a.max_levels;
+    p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
+    p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
+    nec::vertex_load_engine<DistT, kDebug><<<slots, nec::kEngineThreads, 0, ctx->stream>>>(p);
+    NEC_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return NEC_OK;
+}
+
+int engine_occupancy(nec_ctx *ctx) {
+    int o8 = 0, o32 = 0;
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, false>, nec::kEngineThreads, 0));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, false>, nec::kEngineThreads, 0));
+    if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
+    ctx->occ_u8 = o8; ctx->occ_u32 = o32;
+    return NEC_OK;
+}
+
+// Core: partial load of `n_sources` sources into device vector d_out (n doubles).
+int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
+                int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
+    ctx->stats = nec_stats{};
+    ctx->stats.n_sources = n_sources;
+    const uint32_t n = g->n;
+    if (n == 0) return NEC_OK;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_sources == 0) {
+        NEC_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(double), ctx->stream));
+        return NEC_OK;
+    }
+    for (uint32_t k = 0; k < n_sources; ++k)
+        if (h_sources[k] >= n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, n);
+
+    const uint32_t n_batches = (n_sources + nec::kLanes - 1) / nec::kLanes;
+    ctx->stats.n_batches = n_batches;
+    int rc;
+    if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches)) != NEC_OK) return rc;
+    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, n_batches, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+
+    // ---- pass 1: 8-bit distances -----------------------------------------------------
+    uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)(ctx->occ_u8 * ctx->prop.multiProcessorCount));
+    if (debug) want = 1;
+    if ((rc = ensure_arena(ctx, n, 1, want)) != NEC_OK) return rc;
+    uint32_t slots = std::min<uint32_t>(want, ctx->arena.n_slots);
+    const Arena &a = ctx->arena;
+    NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * sizeof(uint32_t) * slots, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = debug ? launch_engine<uint8_t, true>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
+               : launch_engine<uint8_t, false>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
+    if (rc != NEC_OK) return rc;
+    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
+    NEC_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->stats.n_slots = slots;
+    ctx->stats.workspace_bytes = ctx->arena.bytes;
+
+    // ---- read back the per-batch verdicts (small, but a host sync) ---------------------
+    std::vector<uint8_t> status(n_batches);
+    unsigned long long counters[4];
+    NEC_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.kernel_ms = ms;
+
+    std::vector<uint32_t> deep;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        if (status[b] == nec::kTooDeep) deep.push_back(b);
+        else if (status[b] == nec::kQueueOverflow)
+            return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
+        else if (status[b] != nec::kDone)
+            return fail(ctx, NEC_EINTERNAL, "batch %u was not processed (status %u)", b, (unsigned)status[b]);
+    }
+
+    // ---- pass 2: batches deeper than 253 levels, 32-bit distances ----------------------
+    if (!deep.empty()) {
+        ctx->stats.wide_batches = (uint32_t)deep.size();
+        // keep pass-1 result: d_out already holds the sum of the shallow batches
+        double *d_keep = nullptr;
+        NEC_CUDA(ctx, cudaMalloc((void **)&d_keep, (size_t)n * sizeof(double)));
+        cudaMemcpyAsync(d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, deep.size())) != NEC_OK) { cudaFree(d_keep); return rc; }
+        cudaMemcpyAsync(ctx->d_worklist, deep.data(), deep.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
+        if (debug) want2 = 1;
+        cudaStreamSynchronize(ctx->stream);  // arena may be reallocated below
+        if ((rc = ensure_arena(ctx, n, 4, want2)) != NEC_OK) { cudaFree(d_keep); return rc; }
+        const Arena &w = ctx->arena;
+        uint32_t slots2 = std::min<uint32_t>(want2, w.n_slots);
+        cudaMemsetAsync(w.mask, 0, w.mask_stride * sizeof(uint32_t) * slots2, ctx->stream);
+        cudaMemsetAsync(w.bslot, 0, w.bslot_stride * sizeof(double) * slots2, ctx->stream);
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        rc = debug ? launch_engine<uint32_t, true>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, dbg_npred, dbg_bk)
+                   : launch_engine<uint32_t, false>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr);
+        if (rc != NEC_OK) { cudaFree(d_keep); return rc; }
+        // slot 0's partial absorbs the pass-1 sums so that one reduction produces the result
+        nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, d_keep, n);
+        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, w.bslot_stride, slots2, n, d_out);
+        ctx->stats.kernel_launches += 2;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_keep);
+        if (e != cudaSuccess) return fail(ctx, NEC_ECUDA, "wide-distance pass failed: %s", cudaGetErrorString(e));
+        float ms2 = 0.f;
+        cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1);
+        ctx->stats.kernel_ms += ms2;
+        ctx->stats.workspace_bytes = std::max<uint64_t>(ctx->stats.workspace_bytes, ctx->arena.bytes);
+        for (uint32_t b : deep)
+            if (status[b] != nec::kDone)
+                return fail(ctx, NEC_EINTERNAL, "batch %u failed in the 32-bit distance pass (status %u)", b, (unsigned)status[b]);
+    }
+    ctx->stats.reached_pairs = counters[0];
+    ctx->stats.edge_pairs = counters[1];
+    ctx->stats.vertex_visits = counters[2];
+    ctx->stats.max_depth = (uint32_t)counters[3];
+    return NEC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nec_version(void) { return "net_ensembles_cuda 0.1.0 sm_100a"; }
+
+const char *nec_last_error(const nec_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int nec_init(nec_ctx **out, const int *devices, int n_devices) {
+    if (!out) return fail(nullptr, NEC_EINVAL, "nec_init: out is NULL");
+    *out = nullptr;
+    if (n_devices != 1) return fail(nullptr, NEC_EINVAL, "nec_init: n_devices must be 1 (one context per GPU; got %d)", n_devices);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NEC_ENODEVICE, "no CUDA device available (%s); net_ensembles_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev = 0;
+    if (devices) dev = devices[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (dev < 0 || dev >= count) return fail(nullptr, NEC_EINVAL, "nec_init: device %d out of range (have %d)", dev, count);
+    nec_ctx *ctx = new (std::nothrow) nec_ctx();
+    if (!ctx) return fail(nullptr, NEC_ENOMEM, "nec_init: out of host memory");
+    ctx->device = dev;
+    auto bail = [&](int code, const char *what, cudaError_t err) {
+        int rc = fail(nullptr, code, "nec_init: %s: %s", what, cudaGetErrorString(err));
+        nec_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail(NEC_ECUDA, "cudaSetDevice", e);
+    if ((e = cudaGetDeviceProperties(&ctx->prop, dev)) != cudaSuccess) return bail(NEC_ECUDA, "cudaGetDeviceProperties", e);
+    if (ctx->prop.major != 10) {
+        int rc = fail(nullptr, NEC_ENODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", dev, ctx->prop.major, ctx->prop.minor);
+        nec_destroy(ctx);
+        return rc;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(NEC_ECUDA, "cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
+    if ((e = cudaMalloc((void **)&ctx->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(NEC_ENOMEM, "cudaMalloc", e);
+    if (engine_occupancy(ctx) != NEC_OK) {
+        g_init_error = ctx->err;
+        nec_destroy(ctx);
+        return NEC_ECUDA;
+    }
+    *out = ctx;
+    return NEC_OK;
+}
+
+void nec_destroy(nec_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->d_sources) cudaFree(ctx->d_sources);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_worklist) cudaFree(ctx->d_worklist);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    ctx->small.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int nec_set_stream(nec_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return NEC_EINVAL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NEC_OK;
+}
+
+int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return NEC_EINVAL;
+    ctx->ws_limit = bytes;
+    return NEC_OK;
+}
+
+int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr, const uint32_t *col_idx, nec_graph **out) {
+    if (!ctx) return NEC_EINVAL;
+    if (!out) return fail(ctx, NEC_EINVAL, "nec_graph_upload: out is NULL");
+    *out = nullptr;
+    if (!row_ptr || (nnz && !col_idx)) return fail(ctx, NEC_EINVAL, "nec_graph_upload: NULL CSR pointer");
+    if (nnz >= 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload: nnz=%llu does not fit 32-bit row pointers", (unsigned long long)nnz);
+    if (n > 0x7FFFFFFFu / nec::kLanes * 16) return fail(ctx, NEC_EINVAL, "nec_graph_upload: n=%u too large", n);
+    if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr[0] must be 0 and row_ptr[n] == nnz");
+    std::vector<uint32_t> rp32((size_t)n + 1);
+    uint32_t max_deg = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        if (row_ptr[v + 1] < row_ptr[v]) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr not monotone at %u", v);
+        rp32[v] = (uint32_t)row_ptr[v];
+        max_deg = std::max<uint32_t>(max_deg, (uint32_t)(row_ptr[v + 1] - row_ptr[v]));
+    }
+    rp32[n] = (uint32_t)nnz;
+    for (uint64_t e = 0; e < nnz; ++e)
+        if (col_idx[e] >= n) return fail(ctx, NEC_EINVAL, "nec_graph_upload: col_idx[%llu]=%u out of range (n=%u)", (unsigned long long)e, col_idx[e], n);
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    nec_graph *g = new (std::nothrow) nec_graph();
+    if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
+    g->n = n; g->nnz = nnz; g->max_degree = max_deg;
+    cudaError_t e = cudaMalloc((void **)&g->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&g->d_col_idx, std::max<size_t>(nnz, 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, rp32.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        nec_graph_free(ctx, g);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? NEC_ENOMEM : NEC_ECUDA, "nec_graph_upload: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return NEC_OK;
+}
+
+void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
+    if (!g) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (g->d_row_ptr) cudaFree(g->d_row_ptr);
+    if (g->d_col_idx) cudaFree(g->d_col_idx);
+    delete g;
+}
+
+int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                                   int include_endpoints, double *d_out) {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || (g->n && !d_out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources_device: NULL argument");
+    return run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, d_out, false, nullptr, nullptr);
+}
+
+int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                            int include_endpoints, double *out) {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || (g->n && !out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources: NULL argument");
+    if (g->n == 0) { ctx->stats = nec_stats{}; return NEC_OK; }
+    int rc = grow(ctx, ctx->d_out, ctx->d_out_cap, g->n);
+    if (rc != NEC_OK) return rc;
+    rc = run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, ctx->d_out, false, nullptr, nullptr);
+    if (rc != NEC_OK) return rc;
+    NEC_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, (size_t)g->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NEC_OK;
+}
+
+int nec_vertex_load(nec_ctx *ctx, const nec_graph *g, int include_endpoints, double *out) {
+    if (!ctx) return NEC_EINVAL;
+    if (!g) return fail(ctx, NEC_EINVAL, "nec_vertex_load: graph is NULL");
+    std::vector<uint32_t> all(g->n);
+    for (uint32_t v = 0; v < g->n; ++v) all[v] = v;   // generic_graph.rs:1321 — every vertex is a source
+    return nec_vertex_load_sources(ctx, g, all.data(), g->n, include_endpoints, out);
+}
+
+int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *dist, uint32_t *npred, double *sigma, double *bk) {
+    if (!ctx) return NEC_EINVAL;
+    if (!g) return fail(ctx, NEC_EINVAL, "nec_bfs_debug: graph is NULL");
+    const uint32_t n = g->n;
+    if (source >= n) return fail(ctx, NEC_EINVAL, "nec_bfs_debug: source %u out of range (n=%u)", source, n);
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // Runs the PRODUCTION engine (debug instantiation: identical code plus two plane stores)
+    // on a one-source batch and reads lane 0 of the slot's planes.
+    uint32_t *d_np_plane = nullptr, *d_u32 = nullptr;
+    double *d_bk_plane = nullptr, *d_f64 = nullptr, *d_load = nullptr;
+    const size_t plane = (size_t)n * nec::kLanes;
+    auto cleanup = [&]() { cudaFree(d_np_plane); cudaFree(d_bk_plane); cudaFree(d_u32); cudaFree(d_f64); cudaFree(d_load); };
+    cudaError_t e = cudaMalloc((void **)&d_np_plane, plane * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bk_plane, plane * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_u32, (size_t)n * 4 * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_f64, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_load, (size_t)n * 8);
+    if (e != cudaSuccess) { cleanup(); return fail(ctx, NEC_ENOMEM, "nec_bfs_debug: %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(d_np_plane, 0, plane * 4, ctx->stream);
+    nec::fill_f64_kernel<<<std::min<size_t>((plane + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(d_bk_plane, plane, 1.0);
+    int rc = run_sources(ctx, g, &source, 1, 1, d_load, true, d_np_plane, d_bk_plane);
+    if (rc != NEC_OK) { cleanup(); return rc; }
+    const Arena &a = ctx->arena;
+    const uint32_t blocks = std::min<uint32_t>((n + 255) / 256, 148u * 8u);
+    uint32_t *d_dist32 = d_u32, *d_np = d_u32 + n;
+    if (a.dist_bytes == 1) nec::extract_lane_kernel<uint8_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)a.dist, n, 0, d_dist32);
+    else nec::extract_lane_kernel<uint32_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint32_t *)a.dist, n, 0, d_dist32);
+    if (a.dist_bytes == 1) nec::widen_inf_kernel<<<blocks, 256, 0, ctx->stream>>>(d_dist32, n);
+    nec::extract_lane_kernel<uint32_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>(d_np_plane, n, 0, d_np);
+    nec::extract_lane_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>(d_bk_plane, n, 0, d_f64);
+    if (dist) cudaMemcpyAsync(dist, d_dist32, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (npred) cudaMemcpyAsync(npred, d_np, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (bk) cudaMemcpyAsync(bk, d_f64, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (sigma) {
+        nec::sigma_debug_kernel<<<1, 1024, 0, ctx->stream>>>(n, g->d_row_ptr, g->d_col_idx, d_dist32, ctx->stats.max_depth, d_load);
+        cudaMemcpyAsync(sigma, d_load, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, NEC_ECUDA, "nec_bfs_debug: %s", cudaGetErrorString(e));
+    return NEC_OK;
+}
+
+int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,
+                          const uint32_t *row_ptr_concat, const uint64_t *col_offsets, const uint32_t *col_idx_concat,
+                          int include_endpoints, double *out_concat) {
+    if (!ctx) return NEC_EINVAL;
+    if (n_graphs && (!n_per_graph || !row_ptr_offsets || !row_ptr_concat || !col_offsets || !out_concat))
+        return fail(ctx, NEC_EINVAL, "nec_vertex_load_batch: NULL argument");
+    ctx->stats = nec_stats{};
+    cudaSetDevice(ctx->device);
+    return nec::small_batch_run(ctx->small, ctx->stream, ctx->ev0, ctx->ev1, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
+                                row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
+}
+
+int nec_get_stats(const nec_ctx *ctx, nec_stats *out) {
+    if (!ctx || !out) return NEC_EINVAL;
+    *out = ctx->stats;
+    return NEC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/net_ensembles_cuda.h declares;
+without a GPU it refuses to work (no CPU fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "net_ensembles_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nec_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(built):
+    from net_ensembles_b200 import _lib
+    lib = ctypes.CDLL(built.LIB_PATH)
+    names = _declared_functions()
+    assert "nec_vertex_load" in names and "nec_vertex_load_batch" in names and len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), "missing export " + name
+        assert name in _lib.NEC_SYMBOLS, "ctypes stub lacks " + name
+    assert set(_lib.NEC_SYMBOLS) == set(names)
+    _lib.load()
+    lib.nec_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.nec_version()
+
+
+def test_library_contains_only_sm100a_code(built):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", built.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_means_loud_failure(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import net_ensembles_b200 as ne
+    with pytest.raises(ne.NecError) as ei:
+        ne.Context()
+    assert ei.value.code == -4 and "no CPU fallback" in str(ei.value)
+    g = ne.ErEnsembleC(30, 3.0, 1)
+    with pytest.raises(ne.NecError):
+        g.vertex_load(True)
+
+
+def test_product_package_does_not_touch_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may use oracle/."""
+    pkg = os.path.join(ROOT, "net_ensembles_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) and f != "_build.py":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "ref_vertex_load" not in text and "py_oracle" not in text, f

@@ -1,0 +1,199 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the pinned oracle on
+identical inputs.  Integer state (distances, predecessor counts) must be exact; path counts are
+exact while they fit in f64; load values agree within relative 1e-9 (absolute floor 1e-9 for
+|x| < 1) — the tolerance BASELINE.json's north_star states, because the GPU summation order
+(pull, lane tree, per-slot partials) differs from the crate's push order."""
+import numpy as np
+import pytest
+
+import net_ensembles_b200 as ne
+from tests.helpers import adj_from_edges, close, csr_from_adj, edge_case_graphs
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9
+
+
+def _gpu_load(ctx, adj, incl):
+    rp, col = csr_from_adj(adj)
+    g = ctx.upload(rp, col)
+    try:
+        return g.vertex_load(incl)
+    finally:
+        g.free()
+
+
+def test_reference_known_answers(ctx, golden):
+    for ka in golden["known_answers"]:
+        adj = adj_from_edges(ka["n"], ka["edges_in_insertion_order"])
+        for key, incl in (("include_endpoints_true", True), ("include_endpoints_false", False)):
+            if key in ka:
+                got = _gpu_load(ctx, adj, incl)
+                assert close(got, ka[key], REL), (ka["name"], key, got)
+    # integers are exact whatever the summation order
+    k4 = adj_from_edges(4, [(i, j) for i in range(4) for j in range(i + 1, 4)])
+    assert _gpu_load(ctx, k4, True).tolist() == [3.0] * 4
+    assert _gpu_load(ctx, k4, False).tolist() == [0.0] * 4
+
+
+@pytest.mark.parametrize("name", ["erc_1", "erc_2", "erm_1", "erm_2", "sw_1", "sw_2", "sw_3", "sw_4"])
+def test_reference_fixture_graphs(ctx, oracle, golden, name):
+    g = golden["graphs"][name]
+    rp, col = csr_from_adj(g["adj"])
+    dg = ctx.upload(rp, col)
+    for incl in (True, False):
+        got = dg.vertex_load(incl)
+        want = np.array([float.fromhex(h) for h in golden["derived_load"][name]["true_hex" if incl else "false_hex"]])
+        assert close(got, want, REL), name
+        assert close(got, oracle.vertex_load(rp, col, incl), REL), name
+    st = ctx.stats()
+    assert st["n_sources"] == g["n"] and st["kernel_launches"] >= 2
+    oracle.vertex_load(rp, col, True)
+    assert st["edge_pairs"] == oracle.last_stats["edge_pairs"]
+    assert st["reached_pairs"] == oracle.last_stats["reached_pairs"]
+    dg.free()
+
+
+@pytest.mark.parametrize("name", sorted(edge_case_graphs()))
+def test_edge_cases(ctx, oracle, name):
+    adj = edge_case_graphs()[name]
+    rp, col = csr_from_adj(adj)
+    for incl in (True, False):
+        assert close(_gpu_load(ctx, adj, incl), oracle.vertex_load(rp, col, incl), REL), name
+
+
+def test_empty_graph(ctx):
+    g = ctx.upload(np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+    assert g.vertex_load(True).shape == (0,)
+
+
+def test_ensemble_drop_in_call(ctx, oracle):
+    """ensemble.vertex_load(include_endpoints) — same call shape as the crate's trait method."""
+    for e in (ne.ErEnsembleC(1000, 4.0, 123_239_010), ne.ErEnsembleM(200, 700, 4), ne.SwEnsemble(500, 0.1, 9),
+              ne.BAensemble(400, 3, 2, 3), ne.ErEnsembleC(50, 4.0, 123_239_010)):
+        rp, col = e.export_csr()
+        for incl in (True, False):
+            assert close(e.vertex_load(incl, ctx), oracle.vertex_load(rp, col, incl), REL)
+
+
+def test_intermediate_state_exact(ctx, oracle, golden):
+    for name in ("erc_1", "erm_1", "sw_1", "sw_3"):
+        g = golden["graphs"][name]
+        rp, col = csr_from_adj(g["adj"])
+        dg = ctx.upload(rp, col)
+        for s in (0, 7, g["n"] - 1):
+            dist, npred, sigma, bk = dg.bfs_debug(s)
+            rd, rn, rs, rb = oracle.bfs_debug(rp, col, s)
+            assert dist.tolist() == rd.tolist(), (name, s)
+            assert npred.tolist() == rn.tolist(), (name, s)
+            assert sigma.tolist() == rs.tolist(), (name, s)     # exact: counts fit in f64 here
+            assert close(bk, rb, REL), (name, s)
+        dg.free()
+
+
+def test_sources_subset_is_the_sharding_primitive(ctx, oracle):
+    e = ne.ErEnsembleC(700, 3.0, 17)
+    rp, col = e.export_csr()
+    dg = ctx.upload(rp, col)
+    full = dg.vertex_load(True)
+    parts = [dg.vertex_load_sources(np.arange(r, 700, 3), True) for r in range(3)]
+    assert close(sum(parts), full, REL)
+    sub = np.array([5, 99, 100, 640, 5], dtype=np.uint32)          # duplicates count twice
+    assert close(dg.vertex_load_sources(sub, False), oracle.vertex_load(rp, col, False, sources=sub), REL)
+    assert dg.vertex_load_sources(np.zeros(0, np.uint32), True).tolist() == [0.0] * 700
+    with pytest.raises(ne.NecError):
+        dg.vertex_load_sources(np.array([700], np.uint32), True)
+    dg.free()
+
+
+def test_deep_graphs_take_the_wide_distance_path(ctx, oracle):
+    """BFS depth >= 254 does not fit the 8-bit distance rows; those batches re-run with u32."""
+    n = 700
+    path = adj_from_edges(n, [(i, i + 1) for i in range(n - 1)])
+    rp, col = csr_from_adj(path)
+    dg = ctx.upload(rp, col)
+    got = dg.vertex_load(True)
+    assert ctx.stats()["wide_batches"] > 0 and ctx.stats()["max_depth"] == n - 1
+    assert close(got, oracle.vertex_load(rp, col, True), REL)
+    # path: a source left of v sends the n-v vertices at/behind v through it, one right of v sends v+1
+    v = np.arange(n)
+    assert close(got, 1.0 * (v * (n - v) + (n - 1 - v) * (v + 1)), REL)
+    dist = dg.bfs_debug(0)[0]
+    assert dist.tolist() == list(range(n))
+    dg.free()
+    ring = ne.SwEnsemble(1100, 0.0, 1)                       # un-rewired ring-2: depth n/4 = 275
+    rp, col = ring.export_csr()
+    assert close(ring.vertex_load(False, ctx), oracle.vertex_load(rp, col, False), REL)
+
+
+def test_run_to_run_bitwise_reproducible(ctx):
+    e = ne.SwEnsemble(3000, 0.1, 5)
+    dg = e.to_device(ctx)
+    a, b = dg.vertex_load(True), dg.vertex_load(True)
+    assert a.tobytes() == b.tobytes()
+    dg.free()
+
+
+def test_batch_of_small_graphs_equals_singles_bitwise(ctx, oracle):
+    """One CTA per graph; results bit-identical to nec_vertex_load on each graph."""
+    ens = [ne.ErEnsembleC(256, 4.0, 123_239_010 + g) for g in range(24)]
+    ens += [ne.ErEnsembleC(33, 2.0, 3), ne.SwEnsemble(100, 0.2, 8), ne.ErEnsembleM(64, 200, 2), ne.ErEnsembleC(512, 3.0, 77)]
+    graphs = [e.export_csr() for e in ens]
+    graphs.append(csr_from_adj([[]]))                                   # n = 1
+    graphs.append(csr_from_adj(adj_from_edges(300, [(i, i + 1) for i in range(299)])))  # depth 299
+    for incl in (True, False):
+        outs = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in graphs], incl)
+        for (rp, col), got in zip(graphs, outs):
+            dg = ctx.upload(rp, col)
+            single = dg.vertex_load(incl)
+            dg.free()
+            assert got.tobytes() == single.tobytes()
+            assert close(got, oracle.vertex_load(rp, col, incl), REL)
+    with pytest.raises(ne.NecError):
+        big = csr_from_adj([[] for _ in range(513)])
+        ne.vertex_load_batch(ctx, [(big[0].astype(np.uint32), big[1])], True)
+
+
+def test_markov_chain_measure_after_every_step(ctx, oracle):
+    """BASELINE config 3 in miniature: chains of ErC graphs, one m_step, vertex_load(true) of all."""
+    chains = [ne.ErEnsembleC(64, 4.0, 100 + g) for g in range(16)]
+    for _ in range(3):
+        for c in chains:
+            c.m_step()
+        csr = [c.export_csr() for c in chains]
+        outs = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in csr], True)
+        for (rp, col), got in zip(csr, outs):
+            assert close(got, oracle.vertex_load(rp, col, True), REL)
+
+
+def test_invariants_at_scale(ctx):
+    """Sizes the oracle cannot finish: integer invariants instead."""
+    e = ne.SwEnsemble(1 << 14, 0.1, 123_239_010)
+    dg = e.to_device(ctx)
+    t, f = dg.vertex_load(True), dg.vertex_load(False)
+    st = ctx.stats()
+    n = 1 << 14
+    assert st["reached_pairs"] == n * n                      # connected
+    assert close(t - f, np.full(n, n - 1.0), REL)
+    # sum_v load_true(v) = sum of all BFS distances; cross-check with a sampled set of sources
+    src = np.arange(0, n, 257, dtype=np.uint32)
+    part = dg.vertex_load_sources(src, True)
+    dsum = sum(int(dg.bfs_debug(int(s))[0].astype(np.int64).sum()) for s in src[:8])
+    part8 = dg.vertex_load_sources(src[:8], True)
+    assert abs(part8.sum() - dsum) <= 1e-9 * dsum
+    assert np.all(part <= t + 1e-6)
+    dg.free()
+
+
+def test_sampled_parity_on_larger_graph(ctx, oracle):
+    g = ne.gnm_scalable(1 << 15, 1 << 17, 42)
+    rp, col = g.export_csr()
+    dg = ctx.upload(rp, col)
+    src = np.arange(0, 1 << 15, 509, dtype=np.uint32)
+    for incl in (True, False):
+        assert close(dg.vertex_load_sources(src, incl), oracle.vertex_load(rp, col, incl, sources=src, threads=0), REL)
+    b = ne.ba_scalable(1 << 14, 4, 5, 7)
+    rp, col = b.export_csr()
+    dg2 = ctx.upload(rp, col)
+    src = np.arange(0, 1 << 14, 251, dtype=np.uint32)
+    assert close(dg2.vertex_load_sources(src, True), oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
+    dg.free(), dg2.free()
