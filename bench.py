@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py — vertex_load GTEPS (all-source) on B200, one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  (N > 1: launched by torch.distributed.run, one rank per GPU.)
+
+A step = one all-source vertex_load(true) pass over the workload graph, sources sharded
+block-cyclically over the ranks, partial loads combined by one all-reduce.  Definitions follow
+SURVEY.md section 8(d):
+  TE(s)    = undirected edges in the component of source s = E_s / 2
+  GTEPS    = sum_s TE(s) / seconds / 1e9
+  B_alg(s) = 24*E_s + 40*|R_s| bytes;  roofline.achieved = sum_s B_alg(s) / traversal-kernel time
+
+`value`: device-timed (CUDA events on the launching stream), CSR resident in HBM.
+`e2e`:   same pass through the host API with host buffers: pinned-host CSR -> H2D upload ->
+         kernels (-> all-reduce) -> D2H of the load vector, every step.
+`--impl reference`: the reference's CPU algorithm (oracle port; the Rust crate cannot be built
+here), all host threads, on a bounded sample of sources of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vertex_load GTEPS (all-source)"
+SEED = 123_239_010  # the crate's bench seed (benches/bench_vertex_load.rs:8)
+
+WORKLOADS = {
+    # name: (description, builder, sampled sources per rank-step or None for all sources)
+    "erc1000": "ErC N=1000 c=4 vertex_load(include_endpoint=true), seeded Pcg64 (BASELINE configs[0])",
+    "sw65536": "SwEnsemble N=2^16 neighbor_distance=2 p=0.1 vertex_load(true), all 65536 sources (BASELINE configs[1])",
+    "erm2p20": "G(n,m) N=2^20 M=2^22 (ErM avg degree 8, scalable generator) vertex_load(true), sampled sources (BASELINE configs[3])",
+    "ba2p22": "Barabasi-Albert N=2^22 m=4 (scalable generator) vertex_load(true), sampled sources (BASELINE configs[4])",
+}
+
+
+def build_workload(name):
+    import net_ensembles_b200 as ne
+    if name == "erc1000":
+        return ne.ErEnsembleC(1000, 4.0, SEED)
+    if name == "sw65536":
+        return ne.SwEnsemble(1 << 16, 0.1, SEED, 2)
+    if name == "erm2p20":
+        return ne.gnm_scalable(1 << 20, 1 << 22, SEED)
+    if name == "ba2p22":
+        return ne.ba_scalable(1 << 22, 4, 5, SEED)
+    raise SystemExit("unknown workload %r (have: %s)" % (name, ", ".join(WORKLOADS)))
+
+
+def step_sources(name, n, sample):
+    """All sources, or (large graphs) a fixed strided sample made of whole 32-blocks."""
+    if sample is None or sample >= n:
+        return np.arange(n, dtype=np.uint32)
+    nblocks = max(1, sample // 32)
+    stride = (n // 32) // nblocks
+    blocks = np.arange(nblocks, dtype=np.uint64) * max(stride, 1)
+    return (blocks[:, None] * 32 + np.arange(32, dtype=np.uint64)[None, :]).reshape(-1).astype(np.uint32)
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
+
+
+def cpu_oracle():
+    from net_ensembles_b200 import _build
+    from tests.helpers import Oracle
+    return Oracle(_build.build_oracle())
+
+
+def run_reference(args, rank):
+    """The reference's CPU path (oracle port, OpenMP over sources) on a bounded sample."""
+    if rank != 0:
+        return
+    g = build_workload(args.workload)
+    rp, col = g.export_csr()
+    n = len(rp) - 1
+    orc = cpu_oracle()
+    cores = orc.max_threads()
+    # size the sample from one probe source so that a step is ~2 s of wall time
+    t0 = time.perf_counter()
+    orc.vertex_load(rp, col, True, sources=np.array([n // 2], np.uint32))
+    per_source = max(time.perf_counter() - t0, 1e-5)
+    per_step = int(min(n, max(cores, min(4096, 2.0 * cores / per_source))))
+    src_all = step_sources(args.workload, n, per_step)
+    times, te = [], 0
+    for it in range(args.warmup + args.steps):
+        src = np.roll(src_all, 7 * it)[:per_step]
+        t0 = time.perf_counter()
+        orc.vertex_load(rp, col, True, sources=src, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            te += orc.last_stats["edge_pairs"] / 2
+    total = sum(times)
+    value = te / total / 1e9
+    sample = "%d strided sources per step of %d (%s)" % (per_step, n, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "sample": sample,
+                   "note": "CPU port of generic_graph.rs:1310-1385 (Rust crate not buildable here), OpenMP over sources"},
+        "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import net_ensembles_b200 as ne
+    from net_ensembles_b200.parallel import shard_sources
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    g = build_workload(args.workload)                   # same seed on every rank: identical replicas
+    rp, col = g.export_csr()
+    n, nnz = len(rp) - 1, len(col)
+    sample = args.sources
+    if sample is None and args.workload in ("erm2p20", "ba2p22"):
+        sample = 2048 * world if args.workload == "erm2p20" else 512 * world
+    sources = step_sources(args.workload, n, sample)
+    mine = sources[shard_sources(len(sources), rank, world)]
+
+    ctx = ne.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    dg = ctx.upload(rp, col)
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+
+    def step():
+        dg.vertex_load_sources_device(mine, True, out.data_ptr())
+        st = ctx.stats()
+        if world > 1:
+            dist.all_reduce(out)
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    engine_ms, launches, st = 0.0, 0, None
+    for _ in range(args.steps):
+        st = step()
+        engine_ms += st["engine_ms"]
+        launches += st["kernel_launches"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    work = torch.tensor([st["edge_pairs"], st["reached_pairs"], launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work)
+    ms_total = float(ms.item())
+    edge_pairs, reached_pairs, launches_all = (float(x) for x in work.tolist())
+    ms_per_step = ms_total / args.steps
+    value = (edge_pairs / 2) / (ms_per_step * 1e-3) / 1e9
+    result_dev = out.clone()
+
+    # ---- e2e: host buffers in, host vector out, every step ---------------------------------
+    rp_pin = torch.from_numpy(rp.astype(np.uint64).view(np.int64)).pin_memory()
+    col_pin = torch.from_numpy(col.astype(np.uint32).view(np.int32)).pin_memory()
+    rp_h, col_h = rp_pin.numpy().view(np.uint64), col_pin.numpy().view(np.uint32)
+    host_out = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        g2 = ctx.upload(rp_h, col_h)                                   # H2D of the CSR
+        if world == 1:
+            res = g2.vertex_load_sources(mine, True)                   # kernels + D2H
+        else:
+            g2.vertex_load_sources_device(mine, True, out.data_ptr())
+            dist.all_reduce(out)
+            host_out.copy_(out, non_blocking=False)                    # D2H
+            res = host_out.numpy()
+        g2.free()
+        return res
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = (edge_pairs / 2) / (float(e2e_s.item()) / args.steps) / 1e9
+    h2d = (n + 1) * 4 + nnz * 4 + len(mine) * 4        # what crosses PCIe per step on this rank (row_ptr is narrowed to u32)
+    d2h = n * 8
+
+    if rank == 0:
+        # device and host-API results must be the same vector
+        assert np.array_equal(np.asarray(res), result_dev.cpu().numpy()), "e2e result differs from device-timed result"
+        peak, peak_src = hbm_peak()
+        st0 = st                                            # rank 0's last step
+        b_alg = 24.0 * st0["edge_pairs"] + 40.0 * st0["reached_pairs"]
+        eng_s = engine_ms / args.steps * 1e-3
+        achieved = b_alg / eng_s / 1e9 if eng_s > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if sample is None else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "n": n, "undirected_edges": nnz // 2,
+                       "sources_per_step": int(len(sources)), "include_endpoints": True,
+                       "sharding": "block-cyclic 32-source blocks over %d rank(s), one f64 all-reduce" % world,
+                       "l2": "per-batch state (%.1f GB of HBM arenas on rank 0) is far larger than the 126 MB L2; "
+                             "no explicit flush between steps" % (st0["workspace_bytes"] / 1e9),
+                       "slots": st0["n_slots"], "max_depth": st0["max_depth"]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload),
+                         "kernel": "vertex_load_engine<u8>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": b_alg, "kernel_ms_per_launch": eng_s * 1e3},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            orc = cpu_oracle()
+            # bounded sample: ~10-20 s of single-thread CPU work (the crate is single-threaded)
+            t0 = time.perf_counter()
+            orc.vertex_load(rp, col, True, sources=np.array([n // 2], np.uint32))
+            per_source = max(time.perf_counter() - t0, 1e-5)
+            k = int(min(len(sources), max(32, min(8192, 12.0 / per_source))))
+            src = sources[:: max(1, len(sources) // k)][:k]
+            t0 = time.perf_counter()
+            want = orc.vertex_load(rp, col, True, sources=src)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": (orc.last_stats["edge_pairs"] / 2) / dt / 1e9, "unit": "GTEPS", "cores": 1,
+                                    "kind": "port", "sample": "%d strided sources of %d, 1 thread (the crate is single-threaded)" % (len(src), n)}
+            # correctness gate beside the timing: same sample on the GPU, <= 1e-9 relative
+            got = dg.vertex_load_sources(src, True)
+            err = np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))
+            line["config"]["parity_vs_oracle_max_rel_err"] = float(err)
+            assert err <= 1e-9, "GPU result differs from the oracle: %g" % err
+        print(json.dumps(line), flush=True)
+    dg.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sw65536", choices=sorted(WORKLOADS))
+    ap.add_argument("--sources", type=int, default=None, help="sample this many sources per step (whole 32-blocks)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torch.distributed.run with --nproc-per-node %d" % (args.gpus, args.gpus))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

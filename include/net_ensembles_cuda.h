@@ -92,8 +92,9 @@ int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *so
                             uint32_t n_sources, int include_endpoints, double *out);
 
 /* Same, but the result stays on the device: d_out is a device pointer to n doubles
- * (overwritten) and the call only enqueues work on the context's stream (no host
- * synchronisation, no D2H) — the caller may hand d_out straight to ncclAllReduce.
+ * (overwritten); no D2H of the result — the caller may hand d_out straight to
+ * ncclAllReduce on the same stream.  The call still waits for the kernels in order to
+ * read back a few bytes of per-batch status (errors are reported, never swallowed).
  * sources is a HOST pointer (copied during the call). */
 int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources,
                                    uint32_t n_sources, int include_endpoints, double *d_out);
@@ -131,8 +132,8 @@ typedef struct nec_stats {
     uint32_t kernel_launches; /* kernels of this library launched by the call */
     uint32_t wide_batches;    /* batches re-run with 32-bit distances (depth >= 255) */
     uint32_t n_slots;         /* resident batch slots (CTAs) used */
-    float kernel_ms;          /* CUDA-event time of the traversal kernels (0 for the
-                                 *_device entry point, which does not synchronise) */
+    float kernel_ms;          /* CUDA-event time of all kernels of the call (traversal + reduction) */
+    float engine_ms;          /* CUDA-event time of the traversal kernel(s) alone (the dominant kernel) */
     uint64_t workspace_bytes; /* scratch arena in use */
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);

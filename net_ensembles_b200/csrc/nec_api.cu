@@ -49,7 +49,7 @@ struct nec_ctx {
     int device = 0;
     cudaDeviceProp prop{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
     uint64_t ws_limit = 0;
     Arena arena;
@@ -217,6 +217,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     rc = debug ? launch_engine<uint8_t, true>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
                : launch_engine<uint8_t, false>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
     if (rc != NEC_OK) return rc;
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
     NEC_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -233,6 +234,8 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     float ms = 0.f;
     NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms = ms;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
+    ctx->stats.engine_ms = ms;
 
     std::vector<uint32_t> deep;
     for (uint32_t b = 0; b < n_batches; ++b) {
@@ -264,6 +267,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
         rc = debug ? launch_engine<uint32_t, true>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, dbg_npred, dbg_bk)
                    : launch_engine<uint32_t, false>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr);
         if (rc != NEC_OK) { cudaFree(d_keep); return rc; }
+        cudaEventRecord(ctx->ev_mid, ctx->stream);
         // slot 0's partial absorbs the pass-1 sums so that one reduction produces the result
         nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, d_keep, n);
         nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, w.bslot_stride, slots2, n, d_out);
@@ -277,6 +281,8 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
         float ms2 = 0.f;
         cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1);
         ctx->stats.kernel_ms += ms2;
+        cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev_mid);
+        ctx->stats.engine_ms += ms2;
         ctx->stats.workspace_bytes = std::max<uint64_t>(ctx->stats.workspace_bytes, ctx->arena.bytes);
         for (uint32_t b : deep)
             if (status[b] != nec::kDone)
@@ -329,6 +335,7 @@ int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     ctx->stream = ctx->own_stream;
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaMalloc((void **)&ctx->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(NEC_ENOMEM, "cudaMalloc", e);
     if (engine_occupancy(ctx) != NEC_OK) {
         g_init_error = ctx->err;
@@ -351,6 +358,7 @@ void nec_destroy(nec_ctx *ctx) {
     ctx->small.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
