@@ -277,7 +277,9 @@ def run_ours(args, rank, world, local_rank):
                        "sharding": "block-cyclic 32-source blocks over %d rank(s), one f64 all-reduce" % world,
                        "l2": "per-batch state (%.1f GB of HBM arenas on rank 0) is far larger than the 126 MB L2; "
                              "no explicit flush between steps" % (st0["workspace_bytes"] / 1e9),
-                       "slots": st0["n_slots"], "max_depth": st0["max_depth"]},
+                       "slots": st0["n_slots"], "max_depth": st0["max_depth"],
+                       "queue_entries_per_vertex_per_batch": st0["vertex_visits"] / max(1, st0["n_batches"] * n),
+                       "phase_share": {"reset": st0["frac_reset"], "forward": st0["frac_forward"], "backward": st0["frac_backward"]}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),

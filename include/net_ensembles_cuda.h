@@ -134,6 +134,9 @@ typedef struct nec_stats {
     uint32_t n_slots;         /* resident batch slots (CTAs) used */
     float kernel_ms;          /* CUDA-event time of all kernels of the call (traversal + reduction) */
     float engine_ms;          /* CUDA-event time of the traversal kernel(s) alone (the dominant kernel) */
+    float frac_reset;         /* share of CTA time spent resetting per-batch state ... */
+    float frac_forward;       /* ... in the forward (BFS) pass ... */
+    float frac_backward;      /* ... in the backward (accumulation) pass (clock64, summed over CTAs) */
     uint64_t workspace_bytes; /* scratch arena in use */
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);

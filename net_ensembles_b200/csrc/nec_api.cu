@@ -57,7 +57,7 @@ struct nec_ctx {
     uint32_t *d_sources = nullptr; size_t d_sources_cap = 0;
     uint8_t *d_status = nullptr;   size_t d_status_cap = 0;
     uint32_t *d_worklist = nullptr; size_t d_worklist_cap = 0;
-    unsigned long long *d_counters = nullptr;       // 4
+    unsigned long long *d_counters = nullptr;       // 8
     double *d_out = nullptr; size_t d_out_cap = 0;  // result staging for host-pointer calls
     int occ_u8 = 0, occ_u32 = 0;
     nec::SmallWorkspace small;
@@ -100,7 +100,7 @@ size_t per_slot_bytes(uint32_t n, uint32_t dist_bytes, size_t qcap, uint32_t max
     size_t b = 0;
     b += align_up((size_t)n * nec::kLanes * dist_bytes, 256);
     b += align_up((size_t)n * nec::kLanes * sizeof(double), 256);
-    b += align_up((size_t)n * 2 * sizeof(uint32_t), 256);
+    b += align_up((size_t)n * 3 * sizeof(uint32_t), 256);
     b += align_up((size_t)n * sizeof(double), 256);
     b += align_up(qcap * sizeof(uint2), 256);
     b += align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);
@@ -141,7 +141,7 @@ int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_sl
         auto carve = [&](size_t per_slot) { uint8_t *r = p; p += align_up(per_slot, 256) * slots; return r; };
         a.dist = carve((size_t)n * nec::kLanes * dist_bytes);      a.dist_stride = align_up((size_t)n * nec::kLanes * dist_bytes, 256);
         a.q = (double *)carve((size_t)n * nec::kLanes * 8);         a.q_stride = align_up((size_t)n * nec::kLanes * 8, 256) / 8;
-        a.mask = (uint32_t *)carve((size_t)n * 2 * 4);              a.mask_stride = align_up((size_t)n * 2 * 4, 256) / 4;
+        a.mask = (uint32_t *)carve((size_t)n * 3 * 4);              a.mask_stride = align_up((size_t)n * 3 * 4, 256) / 4;
         a.bslot = (double *)carve((size_t)n * 8);                   a.bslot_stride = align_up((size_t)n * 8, 256) / 8;
         a.queue = (uint2 *)carve(qcap * 8);                         a.queue_stride = align_up(qcap * 8, 256) / 8;  // pitch; >= qcap
         a.lvl = (uint32_t *)carve(((size_t)max_levels + 2) * 4);    a.lvl_stride = align_up(((size_t)max_levels + 2) * 4, 256) / 4;
@@ -203,7 +203,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches)) != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, n_batches, ctx->stream));
-    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
     // ---- pass 1: 8-bit distances -----------------------------------------------------
     uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)(ctx->occ_u8 * ctx->prop.multiProcessorCount));
@@ -227,7 +227,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
 
     // ---- read back the per-batch verdicts (small, but a host sync) ---------------------
     std::vector<uint8_t> status(n_batches);
-    unsigned long long counters[4];
+    unsigned long long counters[8];
     NEC_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream));
     NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
     NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -292,6 +292,12 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     ctx->stats.edge_pairs = counters[1];
     ctx->stats.vertex_visits = counters[2];
     ctx->stats.max_depth = (uint32_t)counters[3];
+    {
+        const double tot = (double)(counters[4] + counters[5] + counters[6]);
+        ctx->stats.frac_reset = tot > 0 ? (float)(counters[4] / tot) : 0.f;
+        ctx->stats.frac_forward = tot > 0 ? (float)(counters[5] / tot) : 0.f;
+        ctx->stats.frac_backward = tot > 0 ? (float)(counters[6] / tot) : 0.f;
+    }
     return NEC_OK;
 }
 
@@ -336,7 +342,7 @@ int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
-    if ((e = cudaMalloc((void **)&ctx->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(NEC_ENOMEM, "cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(NEC_ENOMEM, "cudaMalloc", e);
     if (engine_occupancy(ctx) != NEC_OK) {
         g_init_error = ctx->err;
         nec_destroy(ctx);

@@ -6,25 +6,29 @@
 // b[v] = sum_{s != v, s reaches v} (bk_s(v) - [!include_endpoints]).
 //
 // How it is laid out for the GPU — "batched multi-source, source-minor":
-//   * 32 sources form a BATCH; lane k of every warp owns source k of the batch.
-//   * per-batch state is stored source-minor: dist[v][32] (u8, 32 B = one sector per vertex
-//     row; u32 for graphs deeper than 253 levels) and q[v][32] (f64, 256 B per row), so a
-//     neighbour gather by a warp is one fully used sector / two fully used lines, and the
-//     CSR row of a vertex is read once for 32 sources.
-//   * one CTA owns one batch SLOT (its arena of dist/q/queues) and walks the batch
-//     level-synchronously with __syncthreads only; CTAs are persistent and take batches
-//     round-robin (static: batch -> slot mapping and therefore every sum is reproducible).
-//   * forward pass (push): frontier queue per level; an entry is (vertex, mask of lanes whose
-//     BFS has the vertex on this level).  A warp expands one entry: for each neighbour row it
-//     marks the lanes that see it for the first time (dist = level+1, plain byte stores, all
-//     racing writers store the same value) and, warp-ballot, ORs the lane mask into
-//     nextmask[x]; the warp that turns nextmask[x] from 0 to non-zero appends x to the next
-//     level's queue (shared-memory tail counter).
-//   * backward pass (pull, atomic-free, deterministic): levels deepest -> 1, same queues.  The
-//     warp owning (w, level l) scans w's row once: lanes with dist[x]==l+1 pull q[x], lanes
-//     count dist[x]==l-1 as predecessors; bk = 1 + sum, q[w] = bk / npred, and the lane sum of
-//     bk is added to this slot's private b[] (one writer per vertex per level => no atomics).
-//     Predecessor lists are never materialised; sigma never enters the value.
+//   * 32 sources form a BATCH; source k of the batch is bit k / lane k everywhere.
+//   * one CTA owns one batch SLOT (its arena of state) and walks the batch level by level
+//     with __syncthreads only; CTAs are persistent and take batches round-robin (static
+//     batch -> slot mapping, so every floating-point sum is reproducible run to run).
+//   * per-slot state: seen[v] (u32: sources that have reached v), next[2][v] (u32: sources
+//     that reach v on the level being built; double-buffered by level parity, self-cleaning),
+//     dist[v][32] (u8, one 32 B sector per vertex; u32 rows for graphs deeper than 253
+//     levels), q[v][32] (f64, 256 B per vertex), the level queues of (vertex, source-mask)
+//     entries, and a private partial load vector.
+//   * FORWARD pass, bit-parallel, one LANE PER EDGE: a warp takes a tile of 32 queue
+//     entries, flattens their adjacency lists (warp scan + per-lane owner search) and every
+//     lane handles one (u -> x) entry for all 32 sources at once:
+//     new = mask(u) & ~seen[x]; atomicOr(seen[x]) filters races; the truly new bits get their
+//     dist bytes written and are ORed into next[x]; the lane that turns next[x] non-zero
+//     appends x to the next level's queue (warp-aggregated shared-memory tail).
+//   * BACKWARD pass (pull, atomic-free, deterministic), one LANE PER SOURCE: levels deepest
+//     -> 1 over the same queues, again in tiles of 32 entries with flattened edges so that 8
+//     neighbour rows are in flight per warp.  For entry (w, mask) and neighbour x, lane k
+//     reads dist[x][k] (one coalesced sector per row); lanes with dist == level+1 pull
+//     q[x][k], lanes count dist == level-1 as predecessors; at the end of w's row
+//     bk = 1 + sum, q[w][k] = bk / npred and the lane-sum of bk goes to the slot's private
+//     b[] (exactly one writer per vertex per level => no atomics).  Predecessor lists are
+//     never materialised; sigma never enters the value.
 //   * slots' private b[] are summed in slot order by reduce_slots_kernel.
 #pragma once
 #include <cuda_runtime.h>
@@ -35,7 +39,8 @@ namespace nec {
 constexpr int kLanes = 32;            // sources per batch
 constexpr int kEngineThreads = 512;   // 16 warps per CTA
 constexpr int kEngineMinBlocks = 2;   // CTAs per SM the register budget is sized for
-constexpr int kUnroll = 4;            // neighbour rows in flight per warp step
+constexpr int kUnroll = 8;            // neighbour rows in flight per warp step (backward)
+constexpr int kFwdUnroll = 4;         // flattened adjacency entries per lane and step (forward)
 
 enum BatchStatus : uint8_t { kPending = 0, kDone = 1, kTooDeep = 2, kQueueOverflow = 3 };
 
@@ -53,14 +58,14 @@ struct EngineParams {
     // per-slot arenas (slot = blockIdx.x)
     uint8_t *dist_base;   size_t dist_stride;   // bytes per slot
     double *q_base;       size_t q_stride;      // doubles per slot
-    uint32_t *mask_base;  size_t mask_stride;   // u32 per slot (2n: two level parities)
+    uint32_t *mask_base;  size_t mask_stride;   // u32 per slot (3n: seen, next[even], next[odd])
     double *bslot_base;   size_t bslot_stride;  // doubles per slot (n)
     uint2 *queue_base;    size_t queue_stride;  // entries per slot (= capacity)
     uint32_t *lvl_base;   size_t lvl_stride;    // u32 per slot (max_levels + 2)
     uint32_t max_levels;                        // deepest level index the slot can record
     // outputs
     uint8_t *batch_status;                      // per batch id
-    unsigned long long *counters;               // [0] reached pairs [1] edge pairs [2] visits [3] max depth
+    unsigned long long *counters;               // [0] reached pairs [1] edge pairs [2] visits [3] max depth [4..6] CTA cycles in reset/forward/backward
     // optional per-(vertex,lane) debug planes of slot 0 (nec_bfs_debug)
     uint32_t *dbg_npred;
     double *dbg_bk;
@@ -76,6 +81,28 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Inclusive warp scan of per-lane counts.
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Flattened item t (0 <= t < incl[31]) belongs to the first lane whose inclusive prefix
+// exceeds t; lanes with zero items are skipped automatically.  Branch-free 5-step search.
+__device__ __forceinline__ int tile_owner(uint32_t incl, uint32_t t) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, lo + step - 1);
+        if (v <= t) lo += step;
+    }
+    return lo;
+}
+
 // The engine.  One CTA = one slot; loops over its batches.
 template <typename DistT, bool kDebug>
 __global__ void __launch_bounds__(kEngineThreads, kEngineMinBlocks)
@@ -84,12 +111,14 @@ vertex_load_engine(const EngineParams p) {
     constexpr int kWarps = kEngineThreads / 32;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
     const uint32_t n = p.n;
 
     DistT *__restrict__ dist = reinterpret_cast<DistT *>(p.dist_base + (size_t)blockIdx.x * p.dist_stride);
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
-    uint32_t *mask_even = p.mask_base + (size_t)blockIdx.x * p.mask_stride;
-    uint32_t *mask_odd = mask_even + n;
+    uint32_t *seen = p.mask_base + (size_t)blockIdx.x * p.mask_stride;
+    uint32_t *next_even = seen + n;
+    uint32_t *next_odd = next_even + n;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
     uint2 *__restrict__ queue = p.queue_base + (size_t)blockIdx.x * p.queue_stride;
     uint32_t *__restrict__ lvl = p.lvl_base + (size_t)blockIdx.x * p.lvl_stride;
@@ -99,16 +128,21 @@ vertex_load_engine(const EngineParams p) {
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
     __shared__ unsigned long long s_cnt[3];
+    __shared__ uint2 s_stage[kWarps][32];       // backward: (neighbour, owner's source mask) per flattened edge
 
-    unsigned long long my_reached = 0, my_edges = 0, my_visits = 0;  // lane 0 of each warp
     uint32_t my_depth = 0;
+    long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 
     for (uint32_t work = blockIdx.x; work < p.n_work; work += gridDim.x) {
         const uint32_t batch = p.work_list ? p.work_list[work] : work;
-        unsigned long long b_reached = 0, b_edges = 0, b_visits = 0;  // counted only if the batch completes
+        uint32_t b_reached = 0, b_edges = 0, b_visits = 0;   // per lane, per batch; counted only if the batch completes
 
-        // ---- reset this slot's distances (streaming 16 B stores) ----------------------
-        {
+        long long t_phase = clock64();
+        // ---- reset: only `seen` (next[] cleans itself; stale dist/q are never read because the
+        //      backward pass touches lane k of a row only if source k reached that vertex) -----
+        for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) __stcg(&seen[v], 0u);
+        if (kDebug) {
             const size_t n16 = ((size_t)n * kLanes * sizeof(DistT)) / 16;
             uint4 *d16 = reinterpret_cast<uint4 *>(dist);
             const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -117,19 +151,21 @@ vertex_load_engine(const EngineParams p) {
         if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; }
         __syncthreads();
 
-        // ---- seed level 0: lane k <-> source k of the batch ---------------------------
+        // ---- seed level 0: bit k <-> source k of the batch ------------------------------
         if (warp == 0) {
             const uint32_t sidx = batch * kLanes + lane;
             if (sidx < p.n_sources) {
                 const uint32_t s = p.sources[sidx];
                 dist[(size_t)s * kLanes + lane] = (DistT)0;
-                const uint32_t old = atomicOr(&mask_even[s], 1u << lane);
+                atomicOr(&seen[s], 1u << lane);
+                const uint32_t old = atomicOr(&next_even[s], 1u << lane);
                 if (old == 0) queue[atomicAdd(&s_tail, 1u)].x = s;
             }
         }
-        __syncthreads();
 
-        // ---- forward: level-synchronous push --------------------------------------------
+        __syncthreads();
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
+        // ---- forward: level-synchronous, bit-parallel, one lane per adjacency entry -----
         uint32_t level = 0, qbeg = 0, qend = 0;
         bool too_deep = false;
         for (;;) {
@@ -141,51 +177,69 @@ vertex_load_engine(const EngineParams p) {
             if (threadIdx.x == 0) lvl[level] = qbeg;
             if (qend == qbeg) break;                 // level `level` is empty: done
             if (level >= level_limit) { too_deep = true; break; }
-            uint32_t *mask_cur = (level & 1) ? mask_odd : mask_even;
-            uint32_t *mask_nxt = (level & 1) ? mask_even : mask_odd;
+            uint32_t *next_cur = (level & 1) ? next_odd : next_even;
+            uint32_t *next_nxt = (level & 1) ? next_even : next_odd;
             const DistT next_d = (DistT)(level + 1);
 
-            for (uint32_t idx = qbeg + warp; idx < qend; idx += kWarps) {
-                uint32_t u = 0, m = 0;
-                if (lane == 0) {
-                    u = queue[idx].x;
-                    m = mask_cur[u];
-                    mask_cur[u] = 0;                 // self-cleaning: parity is reused at level+2
+            for (uint32_t tile = qbeg + warp * 32; tile < qend; tile += kWarps * 32) {
+                const uint32_t idx = tile + lane;
+                uint32_t m = 0, rs = 0, deg = 0;
+                if (idx < qend) {
+                    const uint32_t u = queue[idx].x;
+                    m = __ldcg(&next_cur[u]);
+                    __stcg(&next_cur[u], 0u);        // self-cleaning: this parity is reused at level+2
                     queue[idx].y = m;                // the backward pass reads (vertex, mask)
-                }
-                u = __shfl_sync(0xFFFFFFFFu, u, 0);
-                m = __shfl_sync(0xFFFFFFFFu, m, 0);
-                const bool active = (m >> lane) & 1u;
-                const uint32_t rs = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
-                if (lane == 0) {
+                    rs = __ldg(p.row_ptr + u);
+                    deg = __ldg(p.row_ptr + u + 1) - rs;
                     const uint32_t pc = __popc(m);
                     b_reached += pc;
-                    b_edges += (unsigned long long)pc * (re - rs);
+                    b_edges += pc * deg;
                     b_visits += 1;
                 }
-                for (uint32_t e = rs; e < re; e += 32) {
-                    const uint32_t c = min(32u, re - e);
-                    const uint32_t xl = lane < c ? __ldg(p.col_idx + e + lane) : 0u;
-                    for (uint32_t j0 = 0; j0 < c; j0 += kUnroll) {
-                        uint32_t x[kUnroll];
-                        uint32_t dx[kUnroll];
+                const uint32_t incl = warp_inclusive_scan(deg, lane);
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t off = incl - deg;
+                // kFwdUnroll flattened entries per lane and step: every stage below is a batch of
+                // independent memory operations (col -> seen -> atomicOr(seen) -> atomicOr(next)).
+                for (uint32_t t0 = 0; t0 < total; t0 += 32 * kFwdUnroll) {
+                    uint32_t x[kFwdUnroll], fresh[kFwdUnroll];
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj) {
-                            x[jj] = __shfl_sync(0xFFFFFFFFu, xl, (j0 + jj) & 31);
-                            dx[jj] = (j0 + jj < c) ? (uint32_t)dist[(size_t)x[jj] * kLanes + lane] : 0u;
+                    for (int j = 0; j < kFwdUnroll; ++j) {
+                        const uint32_t t = t0 + j * 32 + lane;
+                        const int o = tile_owner(incl, t);
+                        const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
+                        const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
+                        const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o);
+                        x[j] = 0; fresh[j] = 0;
+                        if (t < total) { x[j] = __ldg(p.col_idx + rs_o + (t - off_o)); fresh[j] = m_o; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kFwdUnroll; ++j)
+                        if (fresh[j]) fresh[j] &= ~__ldcg(&seen[x[j]]);
+#pragma unroll
+                    for (int j = 0; j < kFwdUnroll; ++j)          // exact: racing lanes each keep disjoint bits
+                        if (fresh[j]) fresh[j] &= ~atomicOr(&seen[x[j]], fresh[j]);
+                    uint32_t enq_bits = 0;
+#pragma unroll
+                    for (int j = 0; j < kFwdUnroll; ++j)
+                        if (fresh[j]) {
+                            for (uint32_t bits = fresh[j]; bits; bits &= bits - 1)
+                                dist[(size_t)x[j] * kLanes + (__ffs(bits) - 1)] = next_d;
+                            if (atomicOr(&next_nxt[x[j]], fresh[j]) == 0) enq_bits |= 1u << j;
                         }
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj) {
-                            const bool fresh = active && dx[jj] == kInf;
-                            if (fresh) dist[(size_t)x[jj] * kLanes + lane] = next_d;
-                            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, fresh);
-                            if (bal != 0 && lane == 0) {
-                                const uint32_t old = atomicOr(&mask_nxt[x[jj]], bal);
-                                if (old == 0) {
-                                    const uint32_t pos = atomicAdd(&s_tail, 1u);
-                                    if (pos < qcap) queue[pos].x = x[jj];
-                                    else s_fail = 1;
-                                }
+                    for (int j = 0; j < kFwdUnroll; ++j) {
+                        const bool enqueue = (enq_bits >> j) & 1u;
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, enqueue);
+                        if (bal) {
+                            uint32_t base = 0;
+                            const int leader = __ffs(bal) - 1;
+                            if (lane == leader) base = atomicAdd(&s_tail, (uint32_t)__popc(bal));
+                            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                            if (enqueue) {
+                                const uint32_t pos = base + __popc(bal & lane_lt);
+                                if (pos < qcap) queue[pos].x = x[j];
+                                else s_fail = 1;
                             }
                         }
                     }
@@ -200,60 +254,99 @@ vertex_load_engine(const EngineParams p) {
 
         if (too_deep || failed) {
             // leave the slot clean for the next batch: drop pending mask bits (rare path)
-            for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) { mask_even[v] = 0; mask_odd[v] = 0; }
+            for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) { __stcg(&next_even[v], 0u); __stcg(&next_odd[v], 0u); }
             if (threadIdx.x == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
             __syncthreads();
             continue;
         }
-        my_reached += b_reached; my_edges += b_edges; my_visits += b_visits;
+        atomicAdd(&s_cnt[0], (unsigned long long)b_reached);
+        atomicAdd(&s_cnt[1], (unsigned long long)b_edges);
+        atomicAdd(&s_cnt[2], (unsigned long long)b_visits);
         const uint32_t depth = level - 1;             // deepest non-empty level
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
         if (depth > my_depth) my_depth = depth;
 
         // ---- backward: levels depth .. 1, pull from successors --------------------------
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t lb = lvl[l], le = lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
-            for (uint32_t idx = lb + warp; idx < le; idx += kWarps) {
-                const uint2 ent = queue[idx];
-                const uint32_t w = ent.x;
-                const bool active = (ent.y >> lane) & 1u;
-                const uint32_t rs = __ldg(p.row_ptr + w), re = __ldg(p.row_ptr + w + 1);
-                double acc = 0.0;
-                uint32_t npred = 0;
-                for (uint32_t e = rs; e < re; e += 32) {
-                    const uint32_t c = min(32u, re - e);
-                    const uint32_t xl = lane < c ? __ldg(p.col_idx + e + lane) : 0u;
-                    for (uint32_t j0 = 0; j0 < c; j0 += kUnroll) {
-                        uint32_t x[kUnroll];
+            for (uint32_t tile = lb + warp * 32; tile < le; tile += kWarps * 32) {
+                const uint32_t idx = tile + lane;
+                uint32_t w = 0, m = 0, rs = 0, deg = 0;
+                if (idx < le) {
+                    const uint2 ent = queue[idx];
+                    w = ent.x; m = ent.y;
+                    rs = __ldg(p.row_ptr + w);
+                    deg = __ldg(p.row_ptr + w + 1) - rs;
+                }
+                const uint32_t incl = warp_inclusive_scan(deg, lane);
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t off = incl - deg;
+                // running state of the entry whose row is being consumed (warp-uniform `cur`)
+                int cur = -1;
+                uint32_t cur_end = 0, npred = 0;
+                double acc = 0.0, my_total = 0.0;
+
+                auto finish_entry = [&]() {
+                    const uint32_t w_c = __shfl_sync(0xFFFFFFFFu, w, cur);
+                    const uint32_t m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
+                    const double bk = 1.0 + acc;
+                    double contrib = 0.0;
+                    if ((m_c >> lane) & 1u) {
+                        q[(size_t)w_c * kLanes + lane] = bk / (double)npred;
+                        contrib = p.include_endpoints ? bk : bk - 1.0;
+                        if (kDebug) {
+                            p.dbg_npred[(size_t)w_c * kLanes + lane] = npred;
+                            p.dbg_bk[(size_t)w_c * kLanes + lane] = bk;
+                        }
+                    }
+                    const double tot = warp_sum(contrib);
+                    if (lane == cur) my_total = tot;
+                };
+
+                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    const int o = tile_owner(incl, t);
+                    const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
+                    const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
+                    const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o);
+                    uint2 st = make_uint2(0u, 0u);
+                    if (t < total) st = make_uint2(__ldg(p.col_idx + rs_o + (t - off_o)), m_o);
+                    __syncwarp();
+                    s_stage[warp][lane] = st;
+                    __syncwarp();
+                    const uint32_t cnt = min(32u, total - t0);
+                    for (uint32_t c0 = 0; c0 < cnt; c0 += kUnroll) {
                         uint32_t dx[kUnroll];
                         double qv[kUnroll];
 #pragma unroll
                         for (int jj = 0; jj < kUnroll; ++jj) {
-                            x[jj] = __shfl_sync(0xFFFFFFFFu, xl, (j0 + jj) & 31);
-                            dx[jj] = (j0 + jj < c) ? (uint32_t)dist[(size_t)x[jj] * kLanes + lane] : kInf;
+                            const uint2 e = s_stage[warp][(c0 + jj) & 31];       // broadcast read; mask 0 past the end
+                            dx[jj] = ((e.y >> lane) & 1u) ? (uint32_t)dist[(size_t)e.x * kLanes + lane] : kInf;
                         }
+                        uint32_t pred_bits = 0;                                  // bit jj: neighbour jj is a predecessor
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj)
-                            qv[jj] = (active && dx[jj] == d_succ) ? q[(size_t)x[jj] * kLanes + lane] : 0.0;
+                        for (int jj = 0; jj < kUnroll; ++jj) {
+                            qv[jj] = (dx[jj] == d_succ) ? q[(size_t)s_stage[warp][(c0 + jj) & 31].x * kLanes + lane] : 0.0;
+                            pred_bits |= (dx[jj] == d_pred ? 1u : 0u) << jj;
+                        }
 #pragma unroll
                         for (int jj = 0; jj < kUnroll; ++jj) {   // CSR order: fixes the rounding
-                            acc += qv[jj];
-                            npred += (dx[jj] == d_pred) ? 1u : 0u;
+                            const uint32_t tt = t0 + c0 + jj;
+                            if (c0 + jj < cnt) {
+                                if (tt >= cur_end) {              // warp-uniform: next entry's row starts
+                                    if (cur >= 0) finish_entry();
+                                    do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
+                                    acc = 0.0; npred = 0;
+                                }
+                                acc += qv[jj];
+                                npred += (pred_bits >> jj) & 1u;
+                            }
                         }
                     }
                 }
-                const double bk = 1.0 + acc;
-                double contrib = 0.0;
-                if (active) {
-                    q[(size_t)w * kLanes + lane] = bk / (double)npred;
-                    contrib = p.include_endpoints ? bk : bk - 1.0;
-                    if (kDebug) {
-                        p.dbg_npred[(size_t)w * kLanes + lane] = npred;
-                        p.dbg_bk[(size_t)w * kLanes + lane] = bk;
-                    }
-                }
-                const double total = warp_sum(contrib);
-                if (lane == 0) bslot[w] += total;
+                if (cur >= 0) finish_entry();
+                if (idx < le && deg != 0) bslot[w] += my_total;     // one writer per vertex per level
             }
             __syncthreads();
         }
@@ -275,21 +368,19 @@ vertex_load_engine(const EngineParams p) {
                 }
             }
         }
-        if (threadIdx.x == 0) p.batch_status[batch] = kDone;
+        if (threadIdx.x == 0) { p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
         __syncthreads();
     }
 
     // ---- flush counters -------------------------------------------------------------------
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    if (lane == 0) {
-        atomicAdd(&s_cnt[0], my_reached);
-        atomicAdd(&s_cnt[1], my_edges);
-        atomicAdd(&s_cnt[2], my_visits);
-    }
     __syncthreads();
     if (threadIdx.x < 3) atomicAdd(&p.counters[threadIdx.x], s_cnt[threadIdx.x]);
-    if (threadIdx.x == 0) atomicMax(&p.counters[3], (unsigned long long)my_depth);
+    if (threadIdx.x == 0) {
+        atomicMax(&p.counters[3], (unsigned long long)my_depth);
+        atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
+        atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
+        atomicAdd(&p.counters[6], (unsigned long long)cyc_bwd);
+    }
 }
 
 // out[v] = sum over slots (ascending) of the slot-private partial loads.
