@@ -73,6 +73,16 @@ int nec_set_stream(nec_ctx *ctx, void *cuda_stream);
  * 0 restores the default (60 % of free device memory at first use). */
 int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
+/* Engine selection (tests and profiling; the default 0 chooses by graph size):
+ *   NEC_ENGINE_AUTO    0  n in [2048, 100000]: one source per CTA, per-source state in shared
+ *                         memory; otherwise the batched 32-source engine
+ *   NEC_ENGINE_BATCHED 1  always the batched engine
+ *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 100000 */
+#define NEC_ENGINE_AUTO 0
+#define NEC_ENGINE_BATCHED 1
+#define NEC_ENGINE_MID 2
+int nec_set_engine(nec_ctx *ctx, int engine);
+
 /* Upload one graph (H2D copy of the CSR; validates row_ptr monotonicity and
  * col_idx < n).  Replaces the per-call traversal of the crate's adjacency lists. */
 int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr,

@@ -31,6 +31,7 @@ NEC_SYMBOLS = {
     "nec_last_error": (ctypes.c_char_p, [c_vp]),
     "nec_set_stream": (c_int, [c_vp, c_vp]),
     "nec_set_workspace_limit": (c_int, [c_vp, c_u64]),
+    "nec_set_engine": (c_int, [c_vp, c_int]),
     "nec_graph_upload": (c_int, [c_vp, c_u32, c_u64, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nec_graph_free": (None, [c_vp, c_vp]),
     "nec_vertex_load": (c_int, [c_vp, c_vp, c_int, c_vp]),

@@ -51,6 +51,10 @@ class Context:
     def set_workspace_limit(self, nbytes):
         self._check(self._lib.nec_set_workspace_limit(self._h, int(nbytes)))
 
+    def set_engine(self, engine):
+        """0 auto, 1 batched (32 sources per CTA), 2 mid (one source per CTA, n <= 100000)."""
+        self._check(self._lib.nec_set_engine(self._h, int(engine)))
+
     def stats(self):
         s = NecStats()
         self._check(self._lib.nec_get_stats(self._h, ctypes.byref(s)))

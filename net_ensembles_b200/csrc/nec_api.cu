@@ -15,6 +15,7 @@
 #include "../../include/net_ensembles_cuda.h"
 #include "nec_kernels.cuh"
 #include "nec_small.cuh"
+#include "nec_mid.cuh"
 
 namespace {
 
@@ -60,6 +61,10 @@ struct nec_ctx {
     unsigned long long *d_counters = nullptr;       // 8
     double *d_out = nullptr; size_t d_out_cap = 0;  // result staging for host-pointer calls
     int occ_u8 = 0, occ_u32 = 0;
+    void *mid_base = nullptr; size_t mid_bytes = 0;   // arena of the one-source-per-CTA engine
+    uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
+    bool mid_attr_set = false;
+    int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
     nec::SmallWorkspace small;
     nec_stats stats{};
 };
@@ -121,8 +126,8 @@ int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_sl
     if (ps * slots > budget) {
         // prefer keeping one slot per SM; shrink the queue bound (overflow is detected) first
         const uint32_t floor_slots = std::min<uint32_t>(slots, (uint32_t)ctx->prop.multiProcessorCount);
-        while (ps * floor_slots > budget && qcap > (size_t)n * 4 + nec::kLanes) {
-            qcap = std::max((size_t)n * 4 + nec::kLanes, qcap / 2);
+        while (ps * floor_slots > budget && qcap > (size_t)n * 16 + nec::kLanes) {
+            qcap = std::max((size_t)n * 16 + nec::kLanes, qcap / 2);
             ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
         }
         slots = (uint32_t)std::min<size_t>(slots, budget / ps);
@@ -181,8 +186,8 @@ int engine_occupancy(nec_ctx *ctx) {
     return NEC_OK;
 }
 
-// Core: partial load of `n_sources` sources into device vector d_out (n doubles).
-int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
+// Batched engine: partial load of `n_sources` sources into device vector d_out (n doubles).
+int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
     ctx->stats = nec_stats{};
     ctx->stats.n_sources = n_sources;
@@ -301,6 +306,118 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     return NEC_OK;
 }
 
+// One-source-per-CTA engine (nec_mid.cuh).  Sources it hands back (too deep / predecessor
+// count overflow) are appended to `fallback`.
+int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
+                    int include_endpoints, double *d_out, std::vector<uint32_t> &fallback) {
+    const uint32_t n = g->n;
+    ctx->stats = nec_stats{};
+    ctx->stats.n_sources = n_sources;
+    ctx->stats.n_batches = n_sources;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = nec::mid_smem_bytes(n);
+    if (!ctx->mid_attr_set) {
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
+        ctx->mid_attr_set = true;
+    }
+    int occ = 0;
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine, nec::kMidThreads, smem));
+    if (occ < 1) return fail(ctx, NEC_ECUDA, "mid engine cannot be resident for n=%u (%zu B shared memory)", n, smem);
+    const uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
+    const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 4, 256) / 4;
+    const size_t need = (q_stride * 8 * 2 + o_stride * 4) * slots;
+    if (need > ctx->mid_bytes) {
+        if (ctx->mid_base) cudaFree(ctx->mid_base);
+        ctx->mid_base = nullptr; ctx->mid_bytes = 0;
+        cudaError_t e = cudaMalloc(&ctx->mid_base, need);
+        if (e != cudaSuccess) return fail(ctx, NEC_ENOMEM, "cudaMalloc(%zu B mid-engine workspace) failed: %s", need, cudaGetErrorString(e));
+        ctx->mid_bytes = need;
+    }
+    int rc;
+    if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_src_status, ctx->d_src_status_cap, n_sources)) != NEC_OK) return rc;
+    double *d_q = (double *)ctx->mid_base;
+    double *d_bslot = d_q + q_stride * slots;
+    uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
+    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, n_sources, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(d_bslot, 0, q_stride * 8 * slots, ctx->stream));
+    nec::MidParams p{};
+    p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
+    p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
+    p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
+    p.bslot_base = d_bslot; p.bslot_stride = q_stride;
+    p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    nec::mid_engine<<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
+    NEC_CUDA(ctx, cudaGetLastError());
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
+    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
+    NEC_CUDA(ctx, cudaGetLastError());
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    std::vector<uint8_t> status(n_sources);
+    unsigned long long counters[8];
+    NEC_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_src_status, n_sources, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.kernel_ms = ms;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
+    ctx->stats.engine_ms = ms;
+    ctx->stats.kernel_launches = 2;
+    ctx->stats.n_slots = slots;
+    ctx->stats.workspace_bytes = ctx->mid_bytes;
+    for (uint32_t k = 0; k < n_sources; ++k) {
+        if (status[k] == nec::kMidTooDeep || status[k] == nec::kMidPredOverflow) fallback.push_back(h_sources[k]);
+        else if (status[k] != nec::kMidDone) return fail(ctx, NEC_EINTERNAL, "source index %u was not processed (status %u)", k, (unsigned)status[k]);
+    }
+    ctx->stats.reached_pairs = counters[0];
+    ctx->stats.edge_pairs = counters[1];
+    ctx->stats.vertex_visits = counters[2];
+    ctx->stats.max_depth = (uint32_t)counters[3];
+    const double tot = (double)(counters[4] + counters[5] + counters[6]);
+    ctx->stats.frac_reset = tot > 0 ? (float)(counters[4] / tot) : 0.f;
+    ctx->stats.frac_forward = tot > 0 ? (float)(counters[5] / tot) : 0.f;
+    ctx->stats.frac_backward = tot > 0 ? (float)(counters[6] / tot) : 0.f;
+    return NEC_OK;
+}
+
+// Engine choice: graphs whose distance vector fits in shared memory take the one-source-per-CTA
+// engine; everything else (and whatever that engine hands back) takes the batched engine.
+int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
+                int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
+    const bool mid_ok = !debug && g->n <= nec::kMidMaxN && n_sources > 0 && ctx->force_engine != 1 &&
+                        (g->n >= nec::kMidMinN || ctx->force_engine == 2) && g->n > 0;
+    if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
+    std::vector<uint32_t> fallback;
+    int rc = run_sources_mid(ctx, g, h_sources, n_sources, include_endpoints, d_out, fallback);
+    if (rc != NEC_OK || fallback.empty()) return rc;
+    // the few sources the mid engine could not encode (depth > 253 or > 255 predecessors)
+    const nec_stats first = ctx->stats;
+    double *d_tmp = nullptr;
+    NEC_CUDA(ctx, cudaMalloc((void **)&d_tmp, (size_t)g->n * sizeof(double)));
+    rc = run_sources_batched(ctx, g, fallback.data(), (uint32_t)fallback.size(), include_endpoints, d_tmp, false, nullptr, nullptr);
+    if (rc == NEC_OK) {
+        nec::add_into_kernel<<<std::min<uint32_t>((g->n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_out, d_tmp, g->n);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, NEC_ECUDA, "fallback merge failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_tmp);
+    if (rc != NEC_OK) return rc;
+    nec_stats &st = ctx->stats;                      // merge the two passes
+    st.n_sources += first.n_sources - fallback.size();
+    st.n_batches += first.n_batches;
+    st.reached_pairs += first.reached_pairs; st.edge_pairs += first.edge_pairs; st.vertex_visits += first.vertex_visits;
+    st.max_depth = std::max(st.max_depth, first.max_depth);
+    st.kernel_launches += first.kernel_launches + 1;
+    st.kernel_ms += first.kernel_ms; st.engine_ms += first.engine_ms;
+    st.wide_batches += (uint32_t)fallback.size();
+    st.workspace_bytes = std::max(st.workspace_bytes, first.workspace_bytes);
+    return NEC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -361,6 +478,8 @@ void nec_destroy(nec_ctx *ctx) {
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->mid_base) cudaFree(ctx->mid_base);
+    if (ctx->d_src_status) cudaFree(ctx->d_src_status);
     ctx->small.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -372,6 +491,12 @@ void nec_destroy(nec_ctx *ctx) {
 int nec_set_stream(nec_ctx *ctx, void *cuda_stream) {
     if (!ctx) return NEC_EINVAL;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NEC_OK;
+}
+
+int nec_set_engine(nec_ctx *ctx, int engine) {
+    if (!ctx || engine < 0 || engine > 2) return NEC_EINVAL;
+    ctx->force_engine = engine;
     return NEC_OK;
 }
 

@@ -1,0 +1,294 @@
+// "Mid" engine: one source per CTA with the per-source integer state in shared memory.
+// Used when a whole distance vector fits on chip (n <= kMidMaxN): the regime of BASELINE
+// config 2 (small-world N = 2^16), where 32-source batches are incoherent (a vertex sits
+// on ~7 different levels within a batch) and the batched engine wastes 6/7 of its lanes.
+//
+// Same arithmetic as everywhere else (reference: generic_graph.rs:1310-1385): BFS distances,
+// then deepest level first  bk(w) = 1 + sum_{x in N(w), d(x)=d(w)+1} q(x),  q(w) = bk(w)/npred(w),
+// sums taken in adjacency (CSR) order by ONE thread per vertex, so the result is
+// reproducible run to run.  No predecessor lists, no sigma, no atomics on floating point.
+//
+// Memory placement per CTA (= per in-flight source):
+//   shared : dist[n] u8, npred[n] u8, claim bitmap n/8 B, level offsets        (~2.1 B / vertex)
+//   global : q[n] f64      — the only randomly accessed global array; 512 KB at N = 2^16, so
+//                            all resident CTAs together (~76 MB) stay inside the 126 MB L2
+//            order[n] u32  — BFS order = the level queues; written/read as a stream
+//            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
+//                            after each source (streams through HBM; evict-first hints)
+// Per source: reset (shared memory only) -> forward (thread per frontier vertex, claim via
+// shared-memory atomicOr, warp-aggregated queue append) -> backward (thread per vertex, pull)
+// -> sweep  bslot[v] += q[v] * npred[v].  Vertices of degree > kMidHubDeg are expanded by a
+// whole warp (lanes over adjacency entries; the backward sum stays in CSR order).
+// Sources whose BFS is deeper than 253 levels or that meet a vertex with > 255 predecessors
+// are reported back (status) and re-run by the batched engine; nothing is approximated.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nec {
+
+constexpr int kMidThreads = 1024;
+constexpr uint32_t kMidMaxN = 100000;     // 2.125 B/vertex of shared memory + bookkeeping <= 227 KB
+constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
+constexpr uint32_t kMidHubDeg = 64;
+constexpr int kMidHubCap = 512;
+constexpr uint32_t kMidMaxLevel = 253;
+
+enum MidStatus : uint8_t { kMidPending = 0, kMidDone = 1, kMidTooDeep = 2, kMidPredOverflow = 3 };
+
+struct MidParams {
+    uint32_t n, n_pad;                        // n_pad: n rounded up to 16
+    const uint32_t *__restrict__ row_ptr;
+    const uint32_t *__restrict__ col_idx;
+    const uint32_t *__restrict__ sources;
+    uint32_t n_sources;
+    int include_endpoints;
+    double *q_base;        size_t q_stride;
+    uint32_t *order_base;  size_t order_stride;
+    double *bslot_base;    size_t bslot_stride;
+    uint8_t *source_status;                   // per source index
+    unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
+};
+
+__host__ __device__ inline size_t mid_smem_bytes(uint32_t n) {
+    const size_t n_pad = ((size_t)n + 15) / 16 * 16;
+    return 2 * n_pad + ((size_t)n + 31) / 32 * 4 + 16;
+}
+
+__global__ void __launch_bounds__(kMidThreads, 1)
+mid_engine(const MidParams p) {
+    extern __shared__ __align__(16) unsigned char mid_smem[];
+    constexpr int kWarps = kMidThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint32_t n = p.n;
+    uint8_t *dist = mid_smem;
+    uint8_t *npv = dist + p.n_pad;
+    uint32_t *claim = reinterpret_cast<uint32_t *>(npv + p.n_pad);
+    const uint32_t claim_words = (n + 31) / 32;
+
+    __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
+    __shared__ uint32_t s_tail, s_flag, s_hub_n;
+    __shared__ uint32_t s_hub[kMidHubCap];
+    __shared__ unsigned long long s_cnt[2];
+
+    double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
+    uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
+    double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
+
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    uint32_t my_depth = 0;
+    long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;
+
+    for (uint32_t si = blockIdx.x; si < p.n_sources; si += gridDim.x) {
+        const uint32_t s = p.sources[si];
+        long long t_phase = clock64();
+        uint32_t t_reached = 0, t_edges = 0;      // per thread, this source
+        // ---- reset (shared memory only) ------------------------------------------------
+        {
+            uint4 *d16 = reinterpret_cast<uint4 *>(dist);
+            const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (uint32_t i = threadIdx.x; i < p.n_pad / 16; i += kMidThreads) d16[i] = inf4;
+            for (uint32_t i = threadIdx.x; i < claim_words; i += kMidThreads) claim[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            dist[s] = 0;
+            claim[s >> 5] = 1u << (s & 31);
+            order[0] = s;
+            s_tail = 1; s_flag = 0; s_hub_n = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
+
+        // ---- forward ---------------------------------------------------------------------
+        // expands one frontier vertex per thread (k-th neighbour of all 32 lanes per step so the
+        // queue append can be warp-aggregated); hubs are deferred to a warp-cooperative pass
+        auto try_claim = [&](uint32_t x, uint32_t next_d) -> bool {
+            if (dist[x] != 0xFFu) return false;
+            const uint32_t bit = 1u << (x & 31);
+            if (atomicOr(&claim[x >> 5], bit) & bit) return false;
+            dist[x] = (uint8_t)next_d;
+            return true;
+        };
+        auto append = [&](bool found, uint32_t x) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found);
+            if (bal) {
+                uint32_t base = 0;
+                const int leader = __ffs(bal) - 1;
+                if (lane == leader) base = atomicAdd(&s_tail, (uint32_t)__popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (found) __stcs(&order[base + __popc(bal & lane_lt)], x);
+            }
+        };
+
+        uint32_t level = 0, lb = 0, le = 0;
+        bool too_deep = false;
+        for (;;) {
+            __syncthreads();
+            const uint32_t tail_now = s_tail;
+            const uint32_t hubs = min(s_hub_n, (uint32_t)kMidHubCap);
+            __syncthreads();
+            // hubs deferred by the level that just ran belong to `level - 1`: expand them now,
+            // before the frontier of `level` is frozen
+            if (hubs) {
+                const uint32_t next_d = level;            // they were on level-1
+                for (uint32_t h = warp; h < hubs; h += kWarps) {
+                    const uint32_t u = s_hub[h];
+                    const uint32_t rs = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
+                    for (uint32_t e0 = rs; e0 < re; e0 += 32) {
+                        const uint32_t e = e0 + lane;
+                        uint32_t x = 0;
+                        bool found = false;
+                        if (e < re) { x = __ldg(p.col_idx + e); found = try_claim(x, next_d); }
+                        append(found, x);
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) s_hub_n = 0;
+                continue;                                 // re-sample the tail
+            }
+            lb = le;
+            le = tail_now;
+            if (threadIdx.x == 0) s_lvl[level] = lb;
+            if (le == lb) break;
+            if (level >= kMidMaxLevel) { too_deep = true; break; }
+            const uint32_t next_d = level + 1;
+            for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kWarps * 32) {
+                const uint32_t i = wbase + lane;
+                uint32_t rs = 0, deg = 0;
+                if (i < le) {
+                    const uint32_t u = __ldcs(&order[i]);
+                    rs = __ldg(p.row_ptr + u);
+                    deg = __ldg(p.row_ptr + u + 1) - rs;
+                    t_reached += 1;
+                    t_edges += deg;
+                    if (deg > kMidHubDeg) {
+                        const uint32_t pos = atomicAdd(&s_hub_n, 1u);
+                        if (pos < (uint32_t)kMidHubCap) { s_hub[pos] = u; deg = 0; }   // else: expand inline (slow, correct)
+                    }
+                }
+                const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
+                for (uint32_t k0 = 0; k0 < maxdeg; k0 += 4) {
+                    uint32_t xs[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool found = xs[j] != 0xFFFFFFFFu && try_claim(xs[j], next_d);
+                        append(found, xs[j]);
+                    }
+                }
+            }
+            ++level;
+        }
+        __syncthreads();
+        if (too_deep) {
+            if (threadIdx.x == 0) p.source_status[si] = kMidTooDeep;
+            continue;
+        }
+        const uint32_t depth = level - 1;
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
+
+        // ---- backward: deepest level first; one thread per vertex, CSR-order sums -----------
+        for (uint32_t l = depth; l >= 1; --l) {
+            const uint32_t b0 = s_lvl[l], b1 = s_lvl[l + 1];
+            const uint32_t d_succ = l + 1, d_pred = l - 1;
+            for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kWarps * 32) {
+                const uint32_t i = wbase + lane;
+                uint32_t w = 0, rs = 0, deg = 0;
+                if (i < b1) {
+                    w = __ldcs(&order[i]);
+                    rs = __ldg(p.row_ptr + w);
+                    deg = __ldg(p.row_ptr + w + 1) - rs;
+                }
+                const bool hub = deg > kMidHubDeg;
+                double acc = 0.0;
+                uint32_t np = 0;
+                if (!hub) {
+                    for (uint32_t k0 = 0; k0 < deg; k0 += 4) {
+                        uint32_t xs[4], dx[4];
+                        double qv[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dx[j] = xs[j] != 0xFFFFFFFFu ? (uint32_t)dist[xs[j]] : 0xFFFFu;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) qv[j] = dx[j] == d_succ ? q[xs[j]] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { acc += qv[j]; np += dx[j] == d_pred ? 1u : 0u; }
+                    }
+                }
+                // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum
+                // over each 32-entry chunk is taken lane by lane so the order is still CSR order
+                uint32_t hub_mask = __ballot_sync(0xFFFFFFFFu, hub);
+                while (hub_mask) {
+                    const int owner = __ffs(hub_mask) - 1;
+                    hub_mask &= hub_mask - 1;
+                    const uint32_t h_rs = __shfl_sync(0xFFFFFFFFu, rs, owner);
+                    const uint32_t h_deg = __shfl_sync(0xFFFFFFFFu, deg, owner);
+                    double h_acc = 0.0;
+                    uint32_t h_np = 0;
+                    for (uint32_t e0 = 0; e0 < h_deg; e0 += 32) {
+                        double v = 0.0;
+                        bool is_pred = false;
+                        if (e0 + lane < h_deg) {
+                            const uint32_t x = __ldg(p.col_idx + h_rs + e0 + lane);
+                            const uint32_t dxx = dist[x];
+                            if (dxx == d_succ) v = q[x];
+                            is_pred = dxx == d_pred;
+                        }
+                        h_np += __popc(__ballot_sync(0xFFFFFFFFu, is_pred));
+                        const uint32_t live = __ballot_sync(0xFFFFFFFFu, v != 0.0);
+                        for (uint32_t bits = live; bits; bits &= bits - 1)      // ascending lane = CSR order
+                            h_acc += __shfl_sync(0xFFFFFFFFu, v, __ffs(bits) - 1);
+                    }
+                    if (lane == owner) { acc = h_acc; np = h_np; }
+                }
+                if (i < b1) {
+                    const double bk = 1.0 + acc;
+                    q[w] = bk / (double)np;
+                    if (np > 255u) s_flag = 1;
+                    npv[w] = (uint8_t)np;
+                }
+            }
+            __syncthreads();
+        }
+        const bool overflow = s_flag != 0;
+        if (overflow) {
+            if (threadIdx.x == 0) p.source_status[si] = kMidPredOverflow;
+            __syncthreads();
+            continue;
+        }
+        // ---- sweep: this source's contribution, coalesced ------------------------------------
+        {
+            const double sub = p.include_endpoints ? 0.0 : 1.0;
+            for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
+                const uint32_t d = dist[v];
+                if (d != 0xFFu && d != 0u) {
+                    const double bk = q[v] * (double)npv[v];
+                    __stcs(&bslot[v], __ldcs(&bslot[v]) + (bk - sub));
+                }
+            }
+        }
+        if (depth > my_depth) my_depth = depth;
+        {
+            const uint32_t wr = __reduce_add_sync(0xFFFFFFFFu, t_reached), we = __reduce_add_sync(0xFFFFFFFFu, t_edges);
+            if (lane == 0) { atomicAdd(&s_cnt[0], (unsigned long long)wr); atomicAdd(&s_cnt[1], (unsigned long long)we); }
+        }
+        if (threadIdx.x == 0) { p.source_status[si] = kMidDone; cyc_bwd += clock64() - t_phase; }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&p.counters[0], s_cnt[0]);
+        atomicAdd(&p.counters[1], s_cnt[1]);
+        atomicAdd(&p.counters[2], s_cnt[0]);
+        atomicMax(&p.counters[3], (unsigned long long)my_depth);
+        atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
+        atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
+        atomicAdd(&p.counters[6], (unsigned long long)cyc_bwd);
+    }
+}
+
+}  // namespace nec

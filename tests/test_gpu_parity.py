@@ -11,6 +11,15 @@ from tests.helpers import adj_from_edges, close, csr_from_adj, edge_case_graphs
 
 pytestmark = pytest.mark.gpu
 REL = 1e-9
+ENGINES = {"auto": 0, "batched": 1, "mid": 2}
+
+
+@pytest.fixture(params=["batched", "mid"])
+def engine_ctx(ctx, request):
+    """Runs a test once per traversal engine (the C ABI picks by graph size by default)."""
+    ctx.set_engine(ENGINES[request.param])
+    yield ctx
+    ctx.set_engine(0)
 
 
 def _gpu_load(ctx, adj, incl):
@@ -22,7 +31,8 @@ def _gpu_load(ctx, adj, incl):
         g.free()
 
 
-def test_reference_known_answers(ctx, golden):
+def test_reference_known_answers(engine_ctx, golden):
+    ctx = engine_ctx
     for ka in golden["known_answers"]:
         adj = adj_from_edges(ka["n"], ka["edges_in_insertion_order"])
         for key, incl in (("include_endpoints_true", True), ("include_endpoints_false", False)):
@@ -36,7 +46,8 @@ def test_reference_known_answers(ctx, golden):
 
 
 @pytest.mark.parametrize("name", ["erc_1", "erc_2", "erm_1", "erm_2", "sw_1", "sw_2", "sw_3", "sw_4"])
-def test_reference_fixture_graphs(ctx, oracle, golden, name):
+def test_reference_fixture_graphs(engine_ctx, oracle, golden, name):
+    ctx = engine_ctx
     g = golden["graphs"][name]
     rp, col = csr_from_adj(g["adj"])
     dg = ctx.upload(rp, col)
@@ -54,7 +65,8 @@ def test_reference_fixture_graphs(ctx, oracle, golden, name):
 
 
 @pytest.mark.parametrize("name", sorted(edge_case_graphs()))
-def test_edge_cases(ctx, oracle, name):
+def test_edge_cases(engine_ctx, oracle, name):
+    ctx = engine_ctx
     adj = edge_case_graphs()[name]
     rp, col = csr_from_adj(adj)
     for incl in (True, False):
@@ -66,7 +78,8 @@ def test_empty_graph(ctx):
     assert g.vertex_load(True).shape == (0,)
 
 
-def test_ensemble_drop_in_call(ctx, oracle):
+def test_ensemble_drop_in_call(engine_ctx, oracle):
+    ctx = engine_ctx
     """ensemble.vertex_load(include_endpoints) — same call shape as the crate's trait method."""
     for e in (ne.ErEnsembleC(1000, 4.0, 123_239_010), ne.ErEnsembleM(200, 700, 4), ne.SwEnsemble(500, 0.1, 9),
               ne.BAensemble(400, 3, 2, 3), ne.ErEnsembleC(50, 4.0, 123_239_010)):
@@ -90,7 +103,8 @@ def test_intermediate_state_exact(ctx, oracle, golden):
         dg.free()
 
 
-def test_sources_subset_is_the_sharding_primitive(ctx, oracle):
+def test_sources_subset_is_the_sharding_primitive(engine_ctx, oracle):
+    ctx = engine_ctx
     e = ne.ErEnsembleC(700, 3.0, 17)
     rp, col = e.export_csr()
     dg = ctx.upload(rp, col)
@@ -105,7 +119,8 @@ def test_sources_subset_is_the_sharding_primitive(ctx, oracle):
     dg.free()
 
 
-def test_deep_graphs_take_the_wide_distance_path(ctx, oracle):
+def test_deep_graphs_take_the_wide_distance_path(engine_ctx, oracle):
+    ctx = engine_ctx
     """BFS depth >= 254 does not fit the 8-bit distance rows; those batches re-run with u32."""
     n = 700
     path = adj_from_edges(n, [(i, i + 1) for i in range(n - 1)])
@@ -125,7 +140,8 @@ def test_deep_graphs_take_the_wide_distance_path(ctx, oracle):
     assert close(ring.vertex_load(False, ctx), oracle.vertex_load(rp, col, False), REL)
 
 
-def test_run_to_run_bitwise_reproducible(ctx):
+def test_run_to_run_bitwise_reproducible(engine_ctx):
+    ctx = engine_ctx
     e = ne.SwEnsemble(3000, 0.1, 5)
     dg = e.to_device(ctx)
     a, b = dg.vertex_load(True), dg.vertex_load(True)
@@ -181,6 +197,38 @@ def test_invariants_at_scale(ctx):
     part8 = dg.vertex_load_sources(src[:8], True)
     assert abs(part8.sum() - dsum) <= 1e-9 * dsum
     assert np.all(part <= t + 1e-6)
+    dg.free()
+
+
+def test_many_predecessors_and_hubs(engine_ctx, oracle):
+    """A vertex with 300 predecessors (> 255: the mid engine hands the source back) and hubs of
+    degree 300 (> 64: warp-cooperative expansion)."""
+    ctx = engine_ctx
+    edges = [(0, 1 + i) for i in range(300)] + [(1 + i, 301) for i in range(300)] + [(301, 302), (302, 303)]
+    adj = adj_from_edges(304, edges)
+    rp, col = csr_from_adj(adj)
+    for incl in (True, False):
+        assert close(_gpu_load(ctx, adj, incl), oracle.vertex_load(rp, col, incl), REL)
+    b = ne.ba_scalable(5000, 4, 5, 11)
+    rp, col = b.export_csr()
+    assert max(np.diff(rp.astype(np.int64))) > 64
+    dg = ctx.upload(rp, col)
+    assert close(dg.vertex_load(True), oracle.vertex_load(rp, col, True, threads=0), REL)
+    dg.free()
+
+
+def test_mid_engine_is_the_default_for_mid_size_graphs(ctx, oracle):
+    e = ne.SwEnsemble(4096, 0.1, 3)
+    rp, col = e.export_csr()
+    dg = ctx.upload(rp, col)
+    got = dg.vertex_load(True)
+    assert ctx.stats()["n_batches"] == 4096            # one source per CTA step, not 128 batches of 32
+    assert close(got, oracle.vertex_load(rp, col, True, threads=0), REL)
+    ctx.set_engine(1)
+    got_b = dg.vertex_load(True)
+    ctx.set_engine(0)
+    assert ctx.stats()["n_batches"] == 128
+    assert close(got, got_b, REL)
     dg.free()
 
 
