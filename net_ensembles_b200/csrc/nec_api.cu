@@ -388,6 +388,8 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
 // engine; everything else (and whatever that engine hands back) takes the batched engine.
 int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
+    for (uint32_t k = 0; k < n_sources; ++k)
+        if (h_sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, g->n);
     const bool mid_ok = !debug && g->n <= nec::kMidMaxN && n_sources > 0 && ctx->force_engine != 1 &&
                         (g->n >= nec::kMidMinN || ctx->force_engine == 2) && g->n > 0;
     if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
