@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -44,6 +45,8 @@ struct nec_graph {
     uint32_t *d_row_ptr = nullptr;   // n+1
     uint32_t *d_col_idx = nullptr;   // nnz
     uint32_t max_degree = 0;
+    uint4 *d_slab = nullptr;         // n rows of slab_w u32 (mid engine), nullptr if n > kMidMaxN
+    int slab_w = 0;
 };
 
 struct nec_ctx {
@@ -317,15 +320,22 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t smem = nec::mid_smem_bytes(n);
     if (!ctx->mid_attr_set) {
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
         ctx->mid_attr_set = true;
     }
     int occ = 0;
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine, nec::kMidThreads, smem));
+    if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8>, nec::kMidThreads, smem));
+    else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16>, nec::kMidThreads, smem));
     if (occ < 1) return fail(ctx, NEC_ECUDA, "mid engine cannot be resident for n=%u (%zu B shared memory)", n, smem);
+    if (const char *env = getenv("NEC_MID_CTAS_PER_SM")) {       // profiling knob
+        const int v = atoi(env);
+        if (v >= 1 && v < occ) occ = v;
+    }
     const uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
     const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 4, 256) / 4;
-    const size_t need = (q_stride * 8 * 2 + o_stride * 4) * slots;
+    const size_t np_stride = align_up((size_t)n, 256);
+    const size_t need = (q_stride * 8 * 2 + o_stride * 4 + np_stride) * slots;
     if (need > ctx->mid_bytes) {
         if (ctx->mid_base) cudaFree(ctx->mid_base);
         ctx->mid_base = nullptr; ctx->mid_bytes = 0;
@@ -339,18 +349,21 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     double *d_q = (double *)ctx->mid_base;
     double *d_bslot = d_q + q_stride * slots;
     uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
+    uint8_t *d_np = (uint8_t *)(d_order + o_stride * slots);
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, n_sources, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(d_bslot, 0, q_stride * 8 * slots, ctx->stream));
     nec::MidParams p{};
-    p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
+    p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab;
     p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
+    p.np_base = d_np; p.np_stride = np_stride;
     p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    nec::mid_engine<<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
+    if (g->slab_w == 8) nec::mid_engine<8><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
+    else nec::mid_engine<16><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
     NEC_CUDA(ctx, cudaGetLastError());
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
@@ -390,7 +403,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
     for (uint32_t k = 0; k < n_sources; ++k)
         if (h_sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, g->n);
-    const bool mid_ok = !debug && g->n <= nec::kMidMaxN && n_sources > 0 && ctx->force_engine != 1 &&
+    const bool mid_ok = !debug && g->d_slab && g->n <= nec::kMidMaxN && n_sources > 0 && ctx->force_engine != 1 &&
                         (g->n >= nec::kMidMinN || ctx->force_engine == 2) && g->n > 0;
     if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
     std::vector<uint32_t> fallback;
@@ -534,6 +547,22 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     if (e == cudaSuccess) e = cudaMalloc((void **)&g->d_col_idx, std::max<size_t>(nnz, 1) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, rp32.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    std::vector<uint32_t> slab;
+    if (e == cudaSuccess && n > 0 && n <= nec::kMidMaxN) {
+        // slab rows: [degree, first W-1 neighbours]; W = 8 unless more than 10 % of the rows would overflow
+        size_t over8 = 0;
+        for (uint32_t v = 0; v < n; ++v) over8 += (row_ptr[v + 1] - row_ptr[v]) > 7;
+        g->slab_w = over8 * 10 > n ? 16 : 8;
+        const int W = g->slab_w;
+        slab.assign((size_t)n * W, 0u);
+        for (uint32_t v = 0; v < n; ++v) {
+            const uint64_t rs = row_ptr[v], deg = row_ptr[v + 1] - rs;
+            slab[(size_t)v * W] = (uint32_t)deg;
+            for (uint64_t k = 0; k < deg && k < (uint64_t)(W - 1); ++k) slab[(size_t)v * W + 1 + k] = col_idx[rs + k];
+        }
+        e = cudaMalloc((void **)&g->d_slab, slab.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_slab, slab.data(), slab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         nec_graph_free(ctx, g);
@@ -548,6 +577,7 @@ void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
     if (ctx) cudaSetDevice(ctx->device);
     if (g->d_row_ptr) cudaFree(g->d_row_ptr);
     if (g->d_col_idx) cudaFree(g->d_col_idx);
+    if (g->d_slab) cudaFree(g->d_slab);
     delete g;
 }
 

@@ -9,9 +9,11 @@
 // reproducible run to run.  No predecessor lists, no sigma, no atomics on floating point.
 //
 // Memory placement per CTA (= per in-flight source):
-//   shared : dist[n] u8, npred[n] u8, claim bitmap n/8 B, level offsets        (~2.1 B / vertex)
-//   global : q[n] f64      — the only randomly accessed global array; 512 KB at N = 2^16, so
-//                            all resident CTAs together (~76 MB) stay inside the 126 MB L2
+//   shared : dist[n] u8, claim bitmap n/8 B, level offsets                      (~1.1 B / vertex)
+//   global : q[n] f64      — the randomly read global array; it is written on level l+1 and
+//                            read on level l, so only ~two levels' worth of sectors per CTA has
+//                            to survive in the 126 MB L2
+//            npred[n] u8   — written once per vertex (backward), read by the sweep
 //            order[n] u32  — BFS order = the level queues; written/read as a stream
 //            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
 //                            after each source (streams through HBM; evict-first hints)
@@ -27,8 +29,8 @@
 
 namespace nec {
 
-constexpr int kMidThreads = 1024;
-constexpr uint32_t kMidMaxN = 100000;     // 2.125 B/vertex of shared memory + bookkeeping <= 227 KB
+constexpr int kMidThreads = 512;        // two CTAs per SM: one source's narrow levels overlap another's wide ones
+constexpr uint32_t kMidMaxN = 196608;     // 1.125 B/vertex of shared memory + bookkeeping <= 227 KB
 constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
@@ -40,22 +42,41 @@ struct MidParams {
     uint32_t n, n_pad;                        // n_pad: n rounded up to 16
     const uint32_t *__restrict__ row_ptr;
     const uint32_t *__restrict__ col_idx;
+    const uint4 *__restrict__ slab;           // n rows of W u32: [degree, first W-1 neighbours] (see nec_graph)
     const uint32_t *__restrict__ sources;
     uint32_t n_sources;
     int include_endpoints;
     double *q_base;        size_t q_stride;
     uint32_t *order_base;  size_t order_stride;
     double *bslot_base;    size_t bslot_stride;
+    uint8_t *np_base;      size_t np_stride;
     uint8_t *source_status;                   // per source index
     unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
 };
 
 __host__ __device__ inline size_t mid_smem_bytes(uint32_t n) {
     const size_t n_pad = ((size_t)n + 15) / 16 * 16;
-    return 2 * n_pad + ((size_t)n + 31) / 32 * 4 + 16;
+    return n_pad + ((size_t)n + 31) / 32 * 4 + 16;
 }
 
-__global__ void __launch_bounds__(kMidThreads, 1)
+// Adjacency "slab": one aligned row of W 32-bit words per vertex = its degree followed by its first
+// W-1 neighbours in adjacency order.  One 32 B (W=8) or 64 B (W=16) load replaces the dependent
+// row_ptr -> col_idx pair of loads (two L2 round trips and 2-3 sectors) for all low-degree
+// vertices; longer rows continue in the CSR arrays.
+template <int W>
+struct SlabRow {
+    uint32_t w[W];
+    __device__ __forceinline__ void load(const uint4 *__restrict__ slab, uint32_t v) {
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            const uint4 t = __ldg(slab + (size_t)v * (W / 4) + i);
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(kMidThreads, 2)
 mid_engine(const MidParams p) {
     extern __shared__ __align__(16) unsigned char mid_smem[];
     constexpr int kWarps = kMidThreads / 32;
@@ -63,8 +84,7 @@ mid_engine(const MidParams p) {
     const uint32_t lane_lt = (1u << lane) - 1u;
     const uint32_t n = p.n;
     uint8_t *dist = mid_smem;
-    uint8_t *npv = dist + p.n_pad;
-    uint32_t *claim = reinterpret_cast<uint32_t *>(npv + p.n_pad);
+    uint32_t *claim = reinterpret_cast<uint32_t *>(dist + p.n_pad);
     const uint32_t claim_words = (n + 31) / 32;
 
     __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
@@ -75,6 +95,7 @@ mid_engine(const MidParams p) {
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
     uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
+    uint8_t *__restrict__ npv = p.np_base + (size_t)blockIdx.x * p.np_stride;
 
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
@@ -104,12 +125,12 @@ mid_engine(const MidParams p) {
         // ---- forward ---------------------------------------------------------------------
         // expands one frontier vertex per thread (k-th neighbour of all 32 lanes per step so the
         // queue append can be warp-aggregated); hubs are deferred to a warp-cooperative pass
-        auto try_claim = [&](uint32_t x, uint32_t next_d) -> bool {
-            if (dist[x] != 0xFFu) return false;
+        auto try_claim = [&](uint32_t x, uint32_t next_d) -> bool {      // x == ~0u: no neighbour in this slot
+            const bool cand = x != 0xFFFFFFFFu && dist[x] == 0xFFu;
             const uint32_t bit = 1u << (x & 31);
-            if (atomicOr(&claim[x >> 5], bit) & bit) return false;
-            dist[x] = (uint8_t)next_d;
-            return true;
+            const bool won = cand && !(atomicOr(&claim[x >> 5], bit) & bit);
+            if (won) dist[x] = (uint8_t)next_d;
+            return won;
         };
         auto append = [&](bool found, uint32_t x) {
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found);
@@ -140,7 +161,8 @@ mid_engine(const MidParams p) {
                         const uint32_t e = e0 + lane;
                         uint32_t x = 0;
                         bool found = false;
-                        if (e < re) { x = __ldg(p.col_idx + e); found = try_claim(x, next_d); }
+                        if (e < re) x = __ldg(p.col_idx + e); else x = 0xFFFFFFFFu;
+                        found = try_claim(x, next_d);
                         append(found, x);
                     }
                 }
@@ -156,11 +178,14 @@ mid_engine(const MidParams p) {
             const uint32_t next_d = level + 1;
             for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kWarps * 32) {
                 const uint32_t i = wbase + lane;
-                uint32_t rs = 0, deg = 0;
+                uint32_t u = 0, deg = 0;
+                SlabRow<W> row;
+#pragma unroll
+                for (int k = 0; k < W; ++k) row.w[k] = 0;
                 if (i < le) {
-                    const uint32_t u = __ldcs(&order[i]);
-                    rs = __ldg(p.row_ptr + u);
-                    deg = __ldg(p.row_ptr + u + 1) - rs;
+                    u = __ldcs(&order[i]);
+                    row.load(p.slab, u);
+                    deg = row.w[0];
                     t_reached += 1;
                     t_edges += deg;
                     if (deg > kMidHubDeg) {
@@ -168,15 +193,21 @@ mid_engine(const MidParams p) {
                         if (pos < (uint32_t)kMidHubCap) { s_hub[pos] = u; deg = 0; }   // else: expand inline (slow, correct)
                     }
                 }
+#pragma unroll
+                for (int k = 1; k < W; ++k) {
+                    const uint32_t x = (uint32_t)(k - 1) < deg ? row.w[k] : 0xFFFFFFFFu;
+                    append(try_claim(x, next_d), x);
+                }
+                // rows longer than the slab continue in the CSR arrays
                 const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
-                for (uint32_t k0 = 0; k0 < maxdeg; k0 += 4) {
-                    uint32_t xs[4];
+                if (maxdeg > (uint32_t)(W - 1)) {
+                    const uint32_t rs = deg > (uint32_t)(W - 1) ? __ldg(p.row_ptr + u) : 0u;
+                    for (uint32_t k0 = W - 1; k0 < maxdeg; k0 += 4) {
+                        uint32_t xs[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+                        for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool found = xs[j] != 0xFFFFFFFFu && try_claim(xs[j], next_d);
-                        append(found, xs[j]);
+                        for (int j = 0; j < 4; ++j) append(try_claim(xs[j], next_d), xs[j]);
                     }
                 }
             }
@@ -197,26 +228,41 @@ mid_engine(const MidParams p) {
             for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kWarps * 32) {
                 const uint32_t i = wbase + lane;
                 uint32_t w = 0, rs = 0, deg = 0;
+                SlabRow<W> row;
+#pragma unroll
+                for (int k = 0; k < W; ++k) row.w[k] = 0;
                 if (i < b1) {
                     w = __ldcs(&order[i]);
-                    rs = __ldg(p.row_ptr + w);
-                    deg = __ldg(p.row_ptr + w + 1) - rs;
+                    row.load(p.slab, w);
+                    deg = row.w[0];
                 }
                 const bool hub = deg > kMidHubDeg;
                 double acc = 0.0;
                 uint32_t np = 0;
+                if (hub) rs = __ldg(p.row_ptr + w);
                 if (!hub) {
-                    for (uint32_t k0 = 0; k0 < deg; k0 += 4) {
-                        uint32_t xs[4], dx[4];
-                        double qv[4];
+                    uint32_t dx[W - 1];
+                    double qv[W - 1];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+                    for (int k = 1; k < W; ++k) dx[k - 1] = (uint32_t)(k - 1) < deg ? (uint32_t)dist[row.w[k]] : 0xFFFFu;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dx[j] = xs[j] != 0xFFFFFFFFu ? (uint32_t)dist[xs[j]] : 0xFFFFu;
+                    for (int k = 1; k < W; ++k) qv[k - 1] = dx[k - 1] == d_succ ? q[row.w[k]] : 0.0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) qv[j] = dx[j] == d_succ ? q[xs[j]] : 0.0;
+                    for (int k = 1; k < W; ++k) { acc += qv[k - 1]; np += dx[k - 1] == d_pred ? 1u : 0u; }   // CSR order
+                    if (deg > (uint32_t)(W - 1)) {
+                        rs = __ldg(p.row_ptr + w);
+                        for (uint32_t k0 = W - 1; k0 < deg; k0 += 4) {
+                            uint32_t xs[4], dy[4];
+                            double qy[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { acc += qv[j]; np += dx[j] == d_pred ? 1u : 0u; }
+                            for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dy[j] = xs[j] != 0xFFFFFFFFu ? (uint32_t)dist[xs[j]] : 0xFFFFu;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) qy[j] = dy[j] == d_succ ? q[xs[j]] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { acc += qy[j]; np += dy[j] == d_pred ? 1u : 0u; }
+                        }
                     }
                 }
                 // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum
