@@ -318,10 +318,10 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.n_sources = n_sources;
     ctx->stats.n_batches = n_sources;
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = nec::mid_smem_bytes(n);
+    const size_t smem = nec::mid_smem_bytes(n, g->slab_w);
     if (!ctx->mid_attr_set) {
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::mid_smem_bytes(nec::kMidMaxN)));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
         ctx->mid_attr_set = true;
     }
     int occ = 0;
@@ -403,7 +403,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
     for (uint32_t k = 0; k < n_sources; ++k)
         if (h_sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, g->n);
-    const bool mid_ok = !debug && g->d_slab && g->n <= nec::kMidMaxN && n_sources > 0 && ctx->force_engine != 1 &&
+    const bool mid_ok = !debug && g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u && n_sources > 0 && ctx->force_engine != 1 &&
                         (g->n >= nec::kMidMinN || ctx->force_engine == 2) && g->n > 0;
     if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
     std::vector<uint32_t> fallback;

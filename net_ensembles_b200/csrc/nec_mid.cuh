@@ -30,7 +30,7 @@
 namespace nec {
 
 constexpr int kMidThreads = 512;        // two CTAs per SM: one source's narrow levels overlap another's wide ones
-constexpr uint32_t kMidMaxN = 196608;     // 1.125 B/vertex of shared memory + bookkeeping <= 227 KB
+constexpr uint32_t kMidMaxN = 180000;     // 1.125 B/vertex of shared memory + staging + bookkeeping <= 227 KB
 constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
@@ -54,9 +54,11 @@ struct MidParams {
     unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
 };
 
-__host__ __device__ inline size_t mid_smem_bytes(uint32_t n) {
+// dynamic shared memory: dist | claim bitmap | per-thread slab staging slots (cp.async targets)
+__host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
     const size_t n_pad = ((size_t)n + 15) / 16 * 16;
-    return n_pad + ((size_t)n + 31) / 32 * 4 + 16;
+    const size_t claim = (((size_t)n + 31) / 32 * 4 + 15) / 16 * 16;
+    return n_pad + claim + (size_t)kMidThreads * slab_w * 4;
 }
 
 // Adjacency "slab": one aligned row of W 32-bit words per vertex = its degree followed by its first
@@ -75,6 +77,18 @@ struct SlabRow {
     }
 };
 
+// per-thread asynchronous copy of one slab row into this thread's shared-memory staging slot
+template <int W>
+__device__ __forceinline__ void slab_prefetch(uint4 *stage_slot, const uint4 *__restrict__ slab, uint32_t v) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_slot);
+    const uint4 *src = slab + (size_t)v * (W / 4);
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int W>
 __global__ void __launch_bounds__(kMidThreads, 2)
 mid_engine(const MidParams p) {
@@ -86,6 +100,9 @@ mid_engine(const MidParams p) {
     uint8_t *dist = mid_smem;
     uint32_t *claim = reinterpret_cast<uint32_t *>(dist + p.n_pad);
     const uint32_t claim_words = (n + 31) / 32;
+    uint4 *stage = reinterpret_cast<uint4 *>(mid_smem + p.n_pad + (((size_t)claim_words * 4 + 15) / 16 * 16)) + (size_t)threadIdx.x * (W / 4);
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    constexpr uint32_t kStride = kMidThreads;
 
     __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
     __shared__ uint32_t s_tail, s_flag, s_hub_n;
@@ -176,15 +193,33 @@ mid_engine(const MidParams p) {
             if (le == lb) break;
             if (level >= kMidMaxLevel) { too_deep = true; break; }
             const uint32_t next_d = level + 1;
-            for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kWarps * 32) {
-                const uint32_t i = wbase + lane;
-                uint32_t u = 0, deg = 0;
+            // software pipeline over this thread's frontier vertices: the vertex id two steps ahead
+            // is being loaded, the slab row one step ahead is in flight to shared memory (cp.async)
+            uint32_t i = lb + threadIdx.x;
+            uint32_t v_cur = i < le ? __ldcs(&order[i]) : kNone;
+            uint32_t v_nxt = i + kStride < le ? __ldcs(&order[i + kStride]) : kNone;
+            if (v_cur != kNone) slab_prefetch<W>(stage, p.slab, v_cur);
+            cp_async_commit();
+            for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kStride, i += kStride) {
+                uint32_t deg = 0;
                 SlabRow<W> row;
+                cp_async_wait_all();
 #pragma unroll
-                for (int k = 0; k < W; ++k) row.w[k] = 0;
-                if (i < le) {
-                    u = __ldcs(&order[i]);
-                    row.load(p.slab, u);
+                for (int k = 0; k < W / 4; ++k) {
+                    const uint4 t = v_cur != kNone ? stage[k] : make_uint4(0u, 0u, 0u, 0u);
+                    row.w[4 * k] = t.x; row.w[4 * k + 1] = t.y; row.w[4 * k + 2] = t.z; row.w[4 * k + 3] = t.w;
+                }
+                const uint32_t u = v_cur;
+                const uint32_t v_nn = i + 2 * kStride < le ? __ldcs(&order[i + 2 * kStride]) : kNone;
+                // re-arm the staging slot only after the reads above have landed in registers (the
+                // test is always true — ids are < n — but makes the issue depend on every LDS result)
+                bool landed = true;
+#pragma unroll
+                for (int k = 0; k < W / 4; ++k) landed = landed && row.w[4 * k] != kNone;
+                if (v_nxt != kNone && landed) slab_prefetch<W>(stage, p.slab, v_nxt);
+                cp_async_commit();
+                v_cur = v_nxt; v_nxt = v_nn;
+                if (u != kNone) {
                     deg = row.w[0];
                     t_reached += 1;
                     t_edges += deg;
@@ -193,10 +228,26 @@ mid_engine(const MidParams p) {
                         if (pos < (uint32_t)kMidHubCap) { s_hub[pos] = u; deg = 0; }   // else: expand inline (slow, correct)
                     }
                 }
+                // claim all slab neighbours first (independent shared-memory operations), then append
+                // everything this warp found with ONE tail update
+                uint32_t won = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
-                    const uint32_t x = (uint32_t)(k - 1) < deg ? row.w[k] : 0xFFFFFFFFu;
-                    append(try_claim(x, next_d), x);
+                    const uint32_t x = (uint32_t)(k - 1) < deg ? row.w[k] : kNone;
+                    if (try_claim(x, next_d)) won |= 1u << k;
+                }
+                {
+                    const uint32_t cnt = __popc(won);
+                    const uint32_t incl = warp_inclusive_scan(cnt, lane);
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    if (total) {
+                        uint32_t base = 0;
+                        if (lane == 31) base = atomicAdd(&s_tail, total);
+                        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+#pragma unroll
+                        for (int k = 1; k < W; ++k)
+                            if ((won >> k) & 1u) __stcs(&order[base++], row.w[k]);
+                    }
                 }
                 // rows longer than the slab continue in the CSR arrays
                 const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
@@ -205,12 +256,13 @@ mid_engine(const MidParams p) {
                     for (uint32_t k0 = W - 1; k0 < maxdeg; k0 += 4) {
                         uint32_t xs[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+                        for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : kNone;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) append(try_claim(xs[j], next_d), xs[j]);
                     }
                 }
             }
+            cp_async_wait_all();
             ++level;
         }
         __syncthreads();
@@ -225,17 +277,29 @@ mid_engine(const MidParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t b0 = s_lvl[l], b1 = s_lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
-            for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kWarps * 32) {
-                const uint32_t i = wbase + lane;
-                uint32_t w = 0, rs = 0, deg = 0;
+            uint32_t i = b0 + threadIdx.x;
+            uint32_t v_cur = i < b1 ? __ldcs(&order[i]) : kNone;
+            uint32_t v_nxt = i + kStride < b1 ? __ldcs(&order[i + kStride]) : kNone;
+            if (v_cur != kNone) slab_prefetch<W>(stage, p.slab, v_cur);
+            cp_async_commit();
+            for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kStride, i += kStride) {
+                uint32_t rs = 0, deg = 0;
                 SlabRow<W> row;
+                cp_async_wait_all();
 #pragma unroll
-                for (int k = 0; k < W; ++k) row.w[k] = 0;
-                if (i < b1) {
-                    w = __ldcs(&order[i]);
-                    row.load(p.slab, w);
-                    deg = row.w[0];
+                for (int k = 0; k < W / 4; ++k) {
+                    const uint4 t = v_cur != kNone ? stage[k] : make_uint4(0u, 0u, 0u, 0u);
+                    row.w[4 * k] = t.x; row.w[4 * k + 1] = t.y; row.w[4 * k + 2] = t.z; row.w[4 * k + 3] = t.w;
                 }
+                const uint32_t w = v_cur;
+                const uint32_t v_nn = i + 2 * kStride < b1 ? __ldcs(&order[i + 2 * kStride]) : kNone;
+                bool landed = true;
+#pragma unroll
+                for (int k = 0; k < W / 4; ++k) landed = landed && row.w[4 * k] != kNone;
+                if (v_nxt != kNone && landed) slab_prefetch<W>(stage, p.slab, v_nxt);
+                cp_async_commit();
+                v_cur = v_nxt; v_nxt = v_nn;
+                deg = row.w[0];
                 const bool hub = deg > kMidHubDeg;
                 double acc = 0.0;
                 uint32_t np = 0;
@@ -291,13 +355,14 @@ mid_engine(const MidParams p) {
                     }
                     if (lane == owner) { acc = h_acc; np = h_np; }
                 }
-                if (i < b1) {
+                if (w != kNone) {
                     const double bk = 1.0 + acc;
                     q[w] = bk / (double)np;
                     if (np > 255u) s_flag = 1;
                     npv[w] = (uint8_t)np;
                 }
             }
+            cp_async_wait_all();
             __syncthreads();
         }
         const bool overflow = s_flag != 0;
