@@ -275,8 +275,9 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOADS[args.workload], "n": n, "undirected_edges": nnz // 2,
                        "sources_per_step": int(len(sources)), "include_endpoints": True,
                        "sharding": "block-cyclic 32-source blocks over %d rank(s), one f64 all-reduce" % world,
-                       "l2": "per-batch state (%.1f GB of HBM arenas on rank 0) is far larger than the 126 MB L2; "
-                             "no explicit flush between steps" % (st0["workspace_bytes"] / 1e9),
+                       "l2": "no explicit flush: one step streams %.1f GB of per-source state (%.2f GB of arenas on rank 0, "
+                             "> 126 MB L2) and ends with different data in L2 than it starts with; the 2 MB adjacency slab is "
+                             "L2-resident by design" % (16e-6 * len(mine), st0["workspace_bytes"] / 1e9),
                        "slots": st0["n_slots"], "max_depth": st0["max_depth"],
                        "queue_entries_per_vertex_per_batch": st0["vertex_visits"] / max(1, st0["n_batches"] * n),
                        "phase_share": {"reset": st0["frac_reset"], "forward": st0["frac_forward"], "backward": st0["frac_backward"]}},
@@ -285,7 +286,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload),
-                         "kernel": "vertex_load_engine<u8>", "peak_source": peak_src,
+                         "kernel": {1: "vertex_load_engine<u8> (batched, 32 sources per CTA)", 2: "mid_engine (one source per CTA)"}.get(st0["engine"] & 15, "?"),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg, "kernel_ms_per_launch": eng_s * 1e3},
         }
         if world == 1 and not args.no_cpu_baseline:

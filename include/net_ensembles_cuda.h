@@ -148,6 +148,9 @@ typedef struct nec_stats {
     float frac_forward;       /* ... in the forward (BFS) pass ... */
     float frac_backward;      /* ... in the backward (accumulation) pass (clock64, summed over CTAs) */
     uint64_t workspace_bytes; /* scratch arena in use */
+    uint32_t engine;          /* traversal kernel that ran: 1 batched (vertex_load_engine), 2 mid (mid_engine),
+                                 3 small-graph batch (small_graph_kernel); batched|mid<<4 if mid handed sources back */
+    uint32_t reserved;
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);
 

@@ -296,6 +296,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
             if (status[b] != nec::kDone)
                 return fail(ctx, NEC_EINTERNAL, "batch %u failed in the 32-bit distance pass (status %u)", b, (unsigned)status[b]);
     }
+    ctx->stats.engine = 1;
     ctx->stats.reached_pairs = counters[0];
     ctx->stats.edge_pairs = counters[1];
     ctx->stats.vertex_visits = counters[2];
@@ -380,6 +381,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
     ctx->stats.engine_ms = ms;
     ctx->stats.kernel_launches = 2;
+    ctx->stats.engine = 2;
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->mid_bytes;
     for (uint32_t k = 0; k < n_sources; ++k) {
@@ -429,6 +431,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     st.kernel_launches += first.kernel_launches + 1;
     st.kernel_ms += first.kernel_ms; st.engine_ms += first.engine_ms;
     st.wide_batches += (uint32_t)fallback.size();
+    st.engine = 1u | (2u << 4);
     st.workspace_bytes = std::max(st.workspace_bytes, first.workspace_bytes);
     return NEC_OK;
 }
@@ -475,6 +478,13 @@ int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess) return bail(NEC_ECUDA, "cudaEventCreate", e);
     if ((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(NEC_ENOMEM, "cudaMalloc", e);
+    {   // keep freed graph buffers in the device's default memory pool instead of returning them to the OS
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (engine_occupancy(ctx) != NEC_OK) {
         g_init_error = ctx->err;
         nec_destroy(ctx);
@@ -543,8 +553,10 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     nec_graph *g = new (std::nothrow) nec_graph();
     if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
     g->n = n; g->nnz = nnz; g->max_degree = max_deg;
-    cudaError_t e = cudaMalloc((void **)&g->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&g->d_col_idx, std::max<size_t>(nnz, 1) * sizeof(uint32_t));
+    // stream-ordered pool allocations: a Markov chain uploads a fresh graph per sample, and plain
+    // cudaMalloc/cudaFree pairs (device-wide synchronisation, up to 0.5 s observed) would dominate
+    cudaError_t e = cudaMallocAsync((void **)&g->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_col_idx, std::max<size_t>(nnz, 1) * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, rp32.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     std::vector<uint32_t> slab;
@@ -560,7 +572,7 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
             slab[(size_t)v * W] = (uint32_t)deg;
             for (uint64_t k = 0; k < deg && k < (uint64_t)(W - 1); ++k) slab[(size_t)v * W + 1 + k] = col_idx[rs + k];
         }
-        e = cudaMalloc((void **)&g->d_slab, slab.size() * sizeof(uint32_t));
+        e = cudaMallocAsync((void **)&g->d_slab, slab.size() * sizeof(uint32_t), ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_slab, slab.data(), slab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -574,10 +586,12 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
 
 void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
     if (!g) return;
-    if (ctx) cudaSetDevice(ctx->device);
-    if (g->d_row_ptr) cudaFree(g->d_row_ptr);
-    if (g->d_col_idx) cudaFree(g->d_col_idx);
-    if (g->d_slab) cudaFree(g->d_slab);
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        if (g->d_row_ptr) cudaFreeAsync(g->d_row_ptr, ctx->stream);
+        if (g->d_col_idx) cudaFreeAsync(g->d_col_idx, ctx->stream);
+        if (g->d_slab) cudaFreeAsync(g->d_slab, ctx->stream);
+    }
     delete g;
 }
 

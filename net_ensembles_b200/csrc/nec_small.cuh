@@ -236,6 +236,7 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
     stats->kernel_ms = ms;
     stats->engine_ms = ms;
     stats->kernel_launches = 1;
+    stats->engine = 3;
     stats->reached_pairs = cnt[0]; stats->edge_pairs = cnt[1]; stats->vertex_visits = cnt[2]; stats->max_depth = (uint32_t)cnt[3];
     stats->n_slots = n_graphs;
     stats->workspace_bytes = ws.cap;
