@@ -9,18 +9,28 @@
 // reproducible run to run.  No predecessor lists, no sigma, no atomics on floating point.
 //
 // Memory placement per CTA (= per in-flight source):
-//   shared : dist[n] u8, claim bitmap n/8 B, level offsets                      (~1.1 B / vertex)
+//   shared : dist[n] u8, claim bitmap n/8 B, level offsets, per-thread slab staging slots
 //   global : q[n] f64      — the randomly read global array; it is written on level l+1 and
 //                            read on level l, so only ~two levels' worth of sectors per CTA has
 //                            to survive in the 126 MB L2
-//            npred[n] u8   — written once per vertex (backward), read by the sweep
 //            order[n] u32  — BFS order = the level queues; written/read as a stream
+//            cls[n] u32    — per queue position: which slab neighbours are BFS successors and how
+//                            many neighbours are predecessors (see below); streamed
+//            npred[n] u8   — written once per vertex (backward), read by the sweep
 //            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
 //                            after each source (streams through HBM; evict-first hints)
-// Per source: reset (shared memory only) -> forward (thread per frontier vertex, claim via
-// shared-memory atomicOr, warp-aggregated queue append) -> backward (thread per vertex, pull)
-// -> sweep  bslot[v] += q[v] * npred[v].  Vertices of degree > kMidHubDeg are expanded by a
-// whole warp (lanes over adjacency entries; the backward sum stays in CSR order).
+// Forward (thread per frontier vertex): one slab row (cp.async-staged one step ahead) gives the
+// degree and the first W-1 neighbours; each neighbour's distance byte is read ONCE and classifies
+// it for good — unreached or level+1: successor (claim it via shared-memory atomicOr if
+// unreached); level-1: predecessor — because when a level-l vertex is expanded all distances
+// <= l are final and every unreached neighbour is about to become l+1.  The classification
+// (successor mask, predecessor count) is stored per queue position, so the backward pass needs
+// no distance reads at all for slab neighbours and skips the row fetch of BFS leaves.
+// Backward (thread per vertex): bk = 1 + sum of q over the successor bits in CSR order,
+// q = bk / npred.  Then a coalesced sweep adds q[v] * npred[v] to the CTA's partial load.
+// Vertices of degree > kMidHubDeg are expanded by a whole warp (forward: deferred list;
+// backward: lanes over adjacency entries, sum still in CSR order); rows longer than the slab
+// continue in the CSR arrays with distance-based classification.
 // Sources whose BFS is deeper than 253 levels or that meet a vertex with > 255 predecessors
 // are reported back (status) and re-run by the batched engine; nothing is approximated.
 #pragma once
@@ -29,12 +39,13 @@
 
 namespace nec {
 
-constexpr int kMidThreads = 512;        // two CTAs per SM: one source's narrow levels overlap another's wide ones
+constexpr int kMidThreads = 512;          // two CTAs per SM: one source's narrow levels overlap another's wide ones
 constexpr uint32_t kMidMaxN = 180000;     // 1.125 B/vertex of shared memory + staging + bookkeeping <= 227 KB
 constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
 constexpr uint32_t kMidMaxLevel = 253;
+constexpr uint32_t kClsRowFlag = 1u << 15;   // cls: bits 0..14 successor mask, bit 15 "row needed anyway", bits 16..31 npred
 
 enum MidStatus : uint8_t { kMidPending = 0, kMidDone = 1, kMidTooDeep = 2, kMidPredOverflow = 3 };
 
@@ -48,13 +59,14 @@ struct MidParams {
     int include_endpoints;
     double *q_base;        size_t q_stride;
     uint32_t *order_base;  size_t order_stride;
+    uint32_t *cls_base;                       // same stride as order
     double *bslot_base;    size_t bslot_stride;
     uint8_t *np_base;      size_t np_stride;
     uint8_t *source_status;                   // per source index
     unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
 };
 
-// dynamic shared memory: dist | claim bitmap | per-thread slab staging slots (cp.async targets)
+// dynamic shared memory: dist | claim bitmap | slab staging (chunk-major: [W/4][threads] x 16 B)
 __host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
     const size_t n_pad = ((size_t)n + 15) / 16 * 16;
     const size_t claim = (((size_t)n + 31) / 32 * 4 + 15) / 16 * 16;
@@ -62,29 +74,17 @@ __host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
 }
 
 // Adjacency "slab": one aligned row of W 32-bit words per vertex = its degree followed by its first
-// W-1 neighbours in adjacency order.  One 32 B (W=8) or 64 B (W=16) load replaces the dependent
-// row_ptr -> col_idx pair of loads (two L2 round trips and 2-3 sectors) for all low-degree
-// vertices; longer rows continue in the CSR arrays.
+// W-1 neighbours in adjacency order.  One 32 B (W=8) or 64 B (W=16) transfer replaces the dependent
+// row_ptr -> col_idx pair of loads for all low-degree vertices.
+// Staging: thread t's 16-byte chunk k lives at stage[k * kMidThreads + t], so a warp's cp.async
+// writes and LDS.128 reads are 512 contiguous bytes (conflict-free).
 template <int W>
-struct SlabRow {
-    uint32_t w[W];
-    __device__ __forceinline__ void load(const uint4 *__restrict__ slab, uint32_t v) {
-#pragma unroll
-        for (int i = 0; i < W / 4; ++i) {
-            const uint4 t = __ldg(slab + (size_t)v * (W / 4) + i);
-            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-        }
-    }
-};
-
-// per-thread asynchronous copy of one slab row into this thread's shared-memory staging slot
-template <int W>
-__device__ __forceinline__ void slab_prefetch(uint4 *stage_slot, const uint4 *__restrict__ slab, uint32_t v) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_slot);
+__device__ __forceinline__ void slab_prefetch(uint4 *stage_t, const uint4 *__restrict__ slab, uint32_t v) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_t);
     const uint4 *src = slab + (size_t)v * (W / 4);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * kMidThreads * i), "l"(src + i) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -94,15 +94,16 @@ __global__ void __launch_bounds__(kMidThreads, 2)
 mid_engine(const MidParams p) {
     extern __shared__ __align__(16) unsigned char mid_smem[];
     constexpr int kWarps = kMidThreads / 32;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    constexpr uint32_t kStride = kMidThreads;
+    constexpr uint32_t kSlabNbrs = W - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const uint32_t n = p.n;
     uint8_t *dist = mid_smem;
     uint32_t *claim = reinterpret_cast<uint32_t *>(dist + p.n_pad);
     const uint32_t claim_words = (n + 31) / 32;
-    uint4 *stage = reinterpret_cast<uint4 *>(mid_smem + p.n_pad + (((size_t)claim_words * 4 + 15) / 16 * 16)) + (size_t)threadIdx.x * (W / 4);
-    constexpr uint32_t kNone = 0xFFFFFFFFu;
-    constexpr uint32_t kStride = kMidThreads;
+    uint4 *stage = reinterpret_cast<uint4 *>(mid_smem + p.n_pad + (((size_t)claim_words * 4 + 15) / 16 * 16)) + threadIdx.x;
 
     __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
     __shared__ uint32_t s_tail, s_flag, s_hub_n;
@@ -111,12 +112,29 @@ mid_engine(const MidParams p) {
 
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
     uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
+    uint32_t *__restrict__ clsq = p.cls_base + (size_t)blockIdx.x * p.order_stride;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
     uint8_t *__restrict__ npv = p.np_base + (size_t)blockIdx.x * p.np_stride;
 
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;
+
+    auto read_stage = [&](uint32_t (&w)[W], bool valid) {
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) {
+            const uint4 t = valid ? stage[(size_t)k * kMidThreads] : make_uint4(0u, 0u, 0u, 0u);
+            w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+        }
+    };
+    // always true (ids and degrees are < n), but makes the re-arming of a staging slot depend on
+    // every shared-memory read of the previous contents having landed in registers
+    auto landed = [&](const uint32_t (&w)[W]) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < W / 4; ++k) ok = ok && w[4 * k] != kNone;
+        return ok;
+    };
 
     for (uint32_t si = blockIdx.x; si < p.n_sources; si += gridDim.x) {
         const uint32_t s = p.sources[si];
@@ -140,14 +158,15 @@ mid_engine(const MidParams p) {
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
 
         // ---- forward ---------------------------------------------------------------------
-        // expands one frontier vertex per thread (k-th neighbour of all 32 lanes per step so the
-        // queue append can be warp-aggregated); hubs are deferred to a warp-cooperative pass
-        auto try_claim = [&](uint32_t x, uint32_t next_d) -> bool {      // x == ~0u: no neighbour in this slot
-            const bool cand = x != 0xFFFFFFFFu && dist[x] == 0xFFu;
+        auto claim_vertex = [&](uint32_t x, uint32_t next_d) -> bool {     // x is known to read as unreached
             const uint32_t bit = 1u << (x & 31);
-            const bool won = cand && !(atomicOr(&claim[x >> 5], bit) & bit);
+            const bool won = !(atomicOr(&claim[x >> 5], bit) & bit);
             if (won) dist[x] = (uint8_t)next_d;
             return won;
+        };
+        auto try_claim = [&](uint32_t x, uint32_t next_d) -> bool {        // x == kNone: empty slot
+            const bool cand = x != kNone && dist[x] == 0xFFu;
+            return cand && claim_vertex(x, next_d);
         };
         auto append = [&](bool found, uint32_t x) {
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found);
@@ -176,11 +195,8 @@ mid_engine(const MidParams p) {
                     const uint32_t rs = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
                     for (uint32_t e0 = rs; e0 < re; e0 += 32) {
                         const uint32_t e = e0 + lane;
-                        uint32_t x = 0;
-                        bool found = false;
-                        if (e < re) x = __ldg(p.col_idx + e); else x = 0xFFFFFFFFu;
-                        found = try_claim(x, next_d);
-                        append(found, x);
+                        const uint32_t x = e < re ? __ldg(p.col_idx + e) : kNone;
+                        append(try_claim(x, next_d), x);
                     }
                 }
                 __syncthreads();
@@ -192,7 +208,8 @@ mid_engine(const MidParams p) {
             if (threadIdx.x == 0) s_lvl[level] = lb;
             if (le == lb) break;
             if (level >= kMidMaxLevel) { too_deep = true; break; }
-            const uint32_t next_d = level + 1;
+            const uint32_t next_d = level + 1, pred_d = level - 1;   // level 0: pred_d wraps, matches nothing
+
             // software pipeline over this thread's frontier vertices: the vertex id two steps ahead
             // is being loaded, the slab row one step ahead is in flight to shared memory (cp.async)
             uint32_t i = lb + threadIdx.x;
@@ -201,42 +218,44 @@ mid_engine(const MidParams p) {
             if (v_cur != kNone) slab_prefetch<W>(stage, p.slab, v_cur);
             cp_async_commit();
             for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kStride, i += kStride) {
-                uint32_t deg = 0;
-                SlabRow<W> row;
+                uint32_t row[W];
                 cp_async_wait_all();
-#pragma unroll
-                for (int k = 0; k < W / 4; ++k) {
-                    const uint4 t = v_cur != kNone ? stage[k] : make_uint4(0u, 0u, 0u, 0u);
-                    row.w[4 * k] = t.x; row.w[4 * k + 1] = t.y; row.w[4 * k + 2] = t.z; row.w[4 * k + 3] = t.w;
-                }
+                read_stage(row, v_cur != kNone);
                 const uint32_t u = v_cur;
                 const uint32_t v_nn = i + 2 * kStride < le ? __ldcs(&order[i + 2 * kStride]) : kNone;
-                // re-arm the staging slot only after the reads above have landed in registers (the
-                // test is always true — ids are < n — but makes the issue depend on every LDS result)
-                bool landed = true;
-#pragma unroll
-                for (int k = 0; k < W / 4; ++k) landed = landed && row.w[4 * k] != kNone;
-                if (v_nxt != kNone && landed) slab_prefetch<W>(stage, p.slab, v_nxt);
+                if (v_nxt != kNone && landed(row)) slab_prefetch<W>(stage, p.slab, v_nxt);
                 cp_async_commit();
                 v_cur = v_nxt; v_nxt = v_nn;
+
+                uint32_t deg = 0, cls = 0;
                 if (u != kNone) {
-                    deg = row.w[0];
+                    deg = row[0];
                     t_reached += 1;
                     t_edges += deg;
+                    if (deg > kSlabNbrs) cls = kClsRowFlag;
                     if (deg > kMidHubDeg) {
                         const uint32_t pos = atomicAdd(&s_hub_n, 1u);
                         if (pos < (uint32_t)kMidHubCap) { s_hub[pos] = u; deg = 0; }   // else: expand inline (slow, correct)
                     }
                 }
-                // claim all slab neighbours first (independent shared-memory operations), then append
-                // everything this warp found with ONE tail update
+                // read each slab neighbour's distance once: classify it, claim it if unreached
                 uint32_t won = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
-                    const uint32_t x = (uint32_t)(k - 1) < deg ? row.w[k] : kNone;
-                    if (try_claim(x, next_d)) won |= 1u << k;
+                    const bool valid = (uint32_t)(k - 1) < deg;
+                    const uint32_t x = row[k];
+                    const uint32_t d = valid ? (uint32_t)dist[x] : 0xFFFFu;
+                    if (d == 0xFFu) {
+                        cls |= 1u << (k - 1);
+                        if (claim_vertex(x, next_d)) won |= 1u << k;
+                    } else if (d == next_d) {
+                        cls |= 1u << (k - 1);
+                    } else if (d == pred_d) {
+                        cls += 1u << 16;
+                    }
                 }
-                {
+                if (u != kNone) __stcs(&clsq[i], cls);
+                {   // append everything this warp found with ONE tail update
                     const uint32_t cnt = __popc(won);
                     const uint32_t incl = warp_inclusive_scan(cnt, lane);
                     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -246,14 +265,14 @@ mid_engine(const MidParams p) {
                         base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
 #pragma unroll
                         for (int k = 1; k < W; ++k)
-                            if ((won >> k) & 1u) __stcs(&order[base++], row.w[k]);
+                            if ((won >> k) & 1u) __stcs(&order[base++], row[k]);
                     }
                 }
                 // rows longer than the slab continue in the CSR arrays
                 const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
-                if (maxdeg > (uint32_t)(W - 1)) {
-                    const uint32_t rs = deg > (uint32_t)(W - 1) ? __ldg(p.row_ptr + u) : 0u;
-                    for (uint32_t k0 = W - 1; k0 < maxdeg; k0 += 4) {
+                if (maxdeg > kSlabNbrs) {
+                    const uint32_t rs = deg > kSlabNbrs ? __ldg(p.row_ptr + u) : 0u;
+                    for (uint32_t k0 = kSlabNbrs; k0 < maxdeg; k0 += 4) {
                         uint32_t xs[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : kNone;
@@ -277,51 +296,46 @@ mid_engine(const MidParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t b0 = s_lvl[l], b1 = s_lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
+            // pipeline: (vertex, cls) two steps ahead loading, slab row one step ahead in flight —
+            // and only for vertices that have successors (BFS leaves need no row at all)
             uint32_t i = b0 + threadIdx.x;
-            uint32_t v_cur = i < b1 ? __ldcs(&order[i]) : kNone;
-            uint32_t v_nxt = i + kStride < b1 ? __ldcs(&order[i + kStride]) : kNone;
-            if (v_cur != kNone) slab_prefetch<W>(stage, p.slab, v_cur);
+            uint32_t v_cur = kNone, c_cur = 0, v_nxt = kNone, c_nxt = 0;
+            if (i < b1) { v_cur = __ldcs(&order[i]); c_cur = __ldcs(&clsq[i]); }
+            if (i + kStride < b1) { v_nxt = __ldcs(&order[i + kStride]); c_nxt = __ldcs(&clsq[i + kStride]); }
+            if (v_cur != kNone && (c_cur & 0xFFFFu)) slab_prefetch<W>(stage, p.slab, v_cur);
             cp_async_commit();
             for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kStride, i += kStride) {
-                uint32_t rs = 0, deg = 0;
-                SlabRow<W> row;
+                uint32_t row[W];
+                const uint32_t w = v_cur, cls = c_cur;
+                const bool has_row = w != kNone && (cls & 0xFFFFu);
                 cp_async_wait_all();
-#pragma unroll
-                for (int k = 0; k < W / 4; ++k) {
-                    const uint4 t = v_cur != kNone ? stage[k] : make_uint4(0u, 0u, 0u, 0u);
-                    row.w[4 * k] = t.x; row.w[4 * k + 1] = t.y; row.w[4 * k + 2] = t.z; row.w[4 * k + 3] = t.w;
-                }
-                const uint32_t w = v_cur;
-                const uint32_t v_nn = i + 2 * kStride < b1 ? __ldcs(&order[i + 2 * kStride]) : kNone;
-                bool landed = true;
-#pragma unroll
-                for (int k = 0; k < W / 4; ++k) landed = landed && row.w[4 * k] != kNone;
-                if (v_nxt != kNone && landed) slab_prefetch<W>(stage, p.slab, v_nxt);
+                read_stage(row, has_row);
+                uint32_t v_nn = kNone, c_nn = 0;
+                if (i + 2 * kStride < b1) { v_nn = __ldcs(&order[i + 2 * kStride]); c_nn = __ldcs(&clsq[i + 2 * kStride]); }
+                if (v_nxt != kNone && (c_nxt & 0xFFFFu) && landed(row)) slab_prefetch<W>(stage, p.slab, v_nxt);
                 cp_async_commit();
-                v_cur = v_nxt; v_nxt = v_nn;
-                deg = row.w[0];
+                v_cur = v_nxt; c_cur = c_nxt; v_nxt = v_nn; c_nxt = c_nn;
+
+                const uint32_t deg = has_row ? row[0] : 0u;
                 const bool hub = deg > kMidHubDeg;
                 double acc = 0.0;
-                uint32_t np = 0;
-                if (hub) rs = __ldg(p.row_ptr + w);
+                uint32_t np = cls >> 16;
+                uint32_t rs = 0;
+                if (deg > kSlabNbrs) rs = __ldg(p.row_ptr + w);
                 if (!hub) {
-                    uint32_t dx[W - 1];
                     double qv[W - 1];
 #pragma unroll
-                    for (int k = 1; k < W; ++k) dx[k - 1] = (uint32_t)(k - 1) < deg ? (uint32_t)dist[row.w[k]] : 0xFFFFu;
+                    for (int k = 1; k < W; ++k) qv[k - 1] = ((cls >> (k - 1)) & 1u) ? q[row[k]] : 0.0;
 #pragma unroll
-                    for (int k = 1; k < W; ++k) qv[k - 1] = dx[k - 1] == d_succ ? q[row.w[k]] : 0.0;
-#pragma unroll
-                    for (int k = 1; k < W; ++k) { acc += qv[k - 1]; np += dx[k - 1] == d_pred ? 1u : 0u; }   // CSR order
-                    if (deg > (uint32_t)(W - 1)) {
-                        rs = __ldg(p.row_ptr + w);
-                        for (uint32_t k0 = W - 1; k0 < deg; k0 += 4) {
+                    for (int k = 1; k < W; ++k) acc += qv[k - 1];                  // CSR order
+                    if (deg > kSlabNbrs) {
+                        for (uint32_t k0 = kSlabNbrs; k0 < deg; k0 += 4) {
                             uint32_t xs[4], dy[4];
                             double qy[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : 0xFFFFFFFFu;
+                            for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : kNone;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dy[j] = xs[j] != 0xFFFFFFFFu ? (uint32_t)dist[xs[j]] : 0xFFFFu;
+                            for (int j = 0; j < 4; ++j) dy[j] = xs[j] != kNone ? (uint32_t)dist[xs[j]] : 0xFFFFu;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) qy[j] = dy[j] == d_succ ? q[xs[j]] : 0.0;
 #pragma unroll
@@ -330,7 +344,8 @@ mid_engine(const MidParams p) {
                     }
                 }
                 // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum
-                // over each 32-entry chunk is taken lane by lane so the order is still CSR order
+                // over each 32-entry chunk is taken lane by lane so the order is still CSR order.
+                // Hubs ignore cls (the forward pass defers them before classifying).
                 uint32_t hub_mask = __ballot_sync(0xFFFFFFFFu, hub);
                 while (hub_mask) {
                     const int owner = __ffs(hub_mask) - 1;
