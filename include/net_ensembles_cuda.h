@@ -109,15 +109,16 @@ int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *so
 int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources,
                                    uint32_t n_sources, int include_endpoints, double *d_out);
 
-/* Many small graphs in one launch (one CTA per graph, all state in shared memory):
+/* Many small graphs in one launch (one CTA per graph, one warp per source, all state in
+ * shared memory):
  * the shape of a Markov chain that measures after every step
  * (benches/common/mod.rs:79-90).  Graph i has n_per_graph[i] vertices
  * (1..NEC_BATCH_MAX_N); its row pointers are
  * row_ptr_concat[row_ptr_offsets[i] .. row_ptr_offsets[i]+n_i] (inclusive end, i.e.
  * n_i+1 entries, LOCAL: starting at 0) and its neighbour ids (local, < n_i) are
  * col_idx_concat[col_offsets[i] + row_ptr_local[...]].  out_concat receives the load
- * vectors back to back (sum n_i doubles).  Results are bit-identical to calling
- * nec_vertex_load on each graph. */
+ * vectors back to back (sum n_i doubles).  Results are reproducible run to run and agree
+ * with nec_vertex_load on each graph to rounding (sources are added in a different order). */
 #define NEC_BATCH_MAX_N 512u
 int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph,
                           const uint64_t *row_ptr_offsets, const uint32_t *row_ptr_concat,

@@ -398,6 +398,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.frac_reset = tot > 0 ? (float)(counters[4] / tot) : 0.f;
     ctx->stats.frac_forward = tot > 0 ? (float)(counters[5] / tot) : 0.f;
     ctx->stats.frac_backward = tot > 0 ? (float)(counters[6] / tot) : 0.f;
+    if (getenv("NEC_MID_VERBOSE")) fprintf(stderr, "[nec] mid engine: thread-0 time in levels of <= %d vertices: %.1f %% of CTA time\n", nec::kMidThreads, 100.0 * counters[7] / tot);
     return NEC_OK;
 }
 

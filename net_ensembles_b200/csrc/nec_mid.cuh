@@ -118,7 +118,7 @@ mid_engine(const MidParams p) {
 
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
-    long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;
+    long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0, cyc_small = 0;
 
     auto read_stage = [&](uint32_t (&w)[W], bool valid) {
 #pragma unroll
@@ -209,6 +209,8 @@ mid_engine(const MidParams p) {
             if (le == lb) break;
             if (level >= kMidMaxLevel) { too_deep = true; break; }
             const uint32_t next_d = level + 1, pred_d = level - 1;   // level 0: pred_d wraps, matches nothing
+            const long long t_lvl = clock64();
+            const bool small_lvl = le - lb <= kStride;
 
             // software pipeline over this thread's frontier vertices: the vertex id two steps ahead
             // is being loaded, the slab row one step ahead is in flight to shared memory (cp.async)
@@ -282,6 +284,7 @@ mid_engine(const MidParams p) {
                 }
             }
             cp_async_wait_all();
+            if (threadIdx.x == 0 && small_lvl) cyc_small += clock64() - t_lvl;
             ++level;
         }
         __syncthreads();
@@ -296,6 +299,7 @@ mid_engine(const MidParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t b0 = s_lvl[l], b1 = s_lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
+            const long long t_lvl = clock64();
             // pipeline: (vertex, cls) two steps ahead loading, slab row one step ahead in flight —
             // and only for vertices that have successors (BFS leaves need no row at all)
             uint32_t i = b0 + threadIdx.x;
@@ -378,6 +382,7 @@ mid_engine(const MidParams p) {
                 }
             }
             cp_async_wait_all();
+            if (threadIdx.x == 0 && b1 - b0 <= kStride) cyc_small += clock64() - t_lvl;
             __syncthreads();
         }
         const bool overflow = s_flag != 0;
@@ -414,6 +419,7 @@ mid_engine(const MidParams p) {
         atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
         atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
         atomicAdd(&p.counters[6], (unsigned long long)cyc_bwd);
+        atomicAdd(&p.counters[7], (unsigned long long)cyc_small);
     }
 }
 

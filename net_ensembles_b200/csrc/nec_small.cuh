@@ -2,13 +2,15 @@
 // shape of a Markov chain that measures after every step (reference:
 // benches/common/mod.rs:79-90 — m_steps_quiet(k) then vertex_load(true), N = 50..~500).
 //
-// All mutable state of a graph lives in shared memory: dist[n][32] (u16), q[n][32] (f64),
-// two f64 vectors for the per-batch and the running load.  The CTA walks the graph's
-// ceil(n/32) source batches one after the other; lane k of every warp owns source k of the
-// batch (same source-minor layout and the same per-(vertex,lane) arithmetic, lane-sum tree
-// and accumulation order as the large-graph engine in nec_kernels.cuh, so results are
-// bit-identical to nec_vertex_load for these sizes).  Levels are topology-driven (every
-// warp tests its vertices' rows for the current level; n is tiny), no queues, no atomics.
+// One CTA per graph, ONE WARP PER SOURCE: every warp owns a private slice of shared memory
+// (dist u32[n], q f64[n], BFS order u16[n], partial load f64[n]) and runs whole sources —
+// forward BFS (lane per frontier vertex, claim by shared-memory atomicCAS, ballot-aggregated
+// queue append) and the backward pull (lane per vertex, successors summed in CSR order,
+// q = bk / npred) — with __syncwarp only; no block barrier inside a source.  Warp w takes
+// sources w, w+W, ... in order and the warps' partial loads are summed in warp order at the
+// end, so the result is reproducible run to run.  Per-source values bk_s(v) are bit-identical
+// to the other engines (same formula, same CSR order); only the order in which sources are
+// added differs, so the batch agrees with nec_vertex_load to rounding (<= 1e-12), not bitwise.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,7 +25,8 @@
 namespace nec {
 
 constexpr int kSmallThreads = 256;
-constexpr uint32_t kSmallInf = 0xFFFFu;
+constexpr int kSmallWarps = kSmallThreads / 32;
+constexpr uint32_t kSmallInf = 0xFFFFFFFFu;
 
 struct SmallParams {
     uint32_t n_graphs;
@@ -38,113 +41,134 @@ struct SmallParams {
     unsigned long long *counters;   // [0] reached pairs [1] edge pairs [2] visits [3] max depth
 };
 
-__host__ __device__ inline size_t small_smem_bytes(uint32_t n) {
-    return (size_t)n * (kLanes * sizeof(double) + 2 * sizeof(double) + kLanes * sizeof(uint16_t));
+// per warp: q f64[n] | bpart f64[n] | dist u32[n] | order u16[n]   (n rounded up to 4)
+__host__ __device__ inline size_t small_warp_bytes(uint32_t n) {
+    const size_t np = ((size_t)n + 3) / 4 * 4;
+    return np * (8 + 8 + 4 + 2);
 }
+__host__ __device__ inline size_t small_smem_bytes(uint32_t n) { return small_warp_bytes(n) * kSmallWarps; }
 
 __global__ void __launch_bounds__(kSmallThreads)
 small_graph_kernel(const SmallParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int kWarps = kSmallThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_more;
-
-    unsigned long long my_reached = 0, my_edges = 0, my_visits = 0;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    unsigned long long my_reached = 0, my_edges = 0;
     uint32_t my_depth = 0;
 
     for (uint32_t g = blockIdx.x; g < p.n_graphs; g += gridDim.x) {
         const uint32_t n = p.n_per_graph[g];
+        const uint32_t np4 = (n + 3) / 4 * 4;
         const uint32_t *__restrict__ rp = p.rp + p.rp_off[g];
         const uint32_t *__restrict__ col = p.col + p.col_off[g];
-        double *q = reinterpret_cast<double *>(smem_raw);
-        double *bsum = q + (size_t)n * kLanes;
-        double *bpart = bsum + n;
-        uint16_t *dist = reinterpret_cast<uint16_t *>(bpart + n);
+        unsigned char *mine = smem_raw + (size_t)warp * small_warp_bytes(n);
+        double *q = reinterpret_cast<double *>(mine);
+        double *bpart = q + np4;
+        uint32_t *dist = reinterpret_cast<uint32_t *>(bpart + np4);
+        uint16_t *order = reinterpret_cast<uint16_t *>(dist + np4);
+        const double sub = p.include_endpoints ? 0.0 : 1.0;
 
-        for (uint32_t v = threadIdx.x; v < n; v += kSmallThreads) bsum[v] = 0.0;
+        for (uint32_t v = lane; v < n; v += 32) bpart[v] = 0.0;
 
-        const uint32_t n_batches = (n + kLanes - 1) / kLanes;
-        for (uint32_t b = 0; b < n_batches; ++b) {
-            __syncthreads();
-            {   // reset (n*32 u16 = n*16 u32 words)
-                uint32_t *d32 = reinterpret_cast<uint32_t *>(dist);
-                for (uint32_t i = threadIdx.x; i < n * (kLanes / 2); i += kSmallThreads) d32[i] = 0xFFFFFFFFu;
-                for (uint32_t v = threadIdx.x; v < n; v += kSmallThreads) bpart[v] = 0.0;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t s = b * kLanes + lane;
-                if (s < n) dist[(size_t)s * kLanes + lane] = 0;
-            }
-            // ---- forward: expand level by level until nothing new is found ---------------
-            uint32_t level = 0;
-            for (;;) {
-                __syncthreads();
-                if (threadIdx.x == 0) s_more = 0;
-                __syncthreads();
-                bool found = false;
-                for (uint32_t u = warp; u < n; u += kWarps) {
-                    const bool active = dist[(size_t)u * kLanes + lane] == level;
-                    const uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
-                    if (am == 0) continue;
-                    const uint32_t rs = __ldg(rp + u), re = __ldg(rp + u + 1);
-                    if (lane == 0) {
-                        my_reached += __popc(am);
-                        my_edges += (unsigned long long)__popc(am) * (re - rs);
-                        my_visits += 1;
+        for (uint32_t s = warp; s < n; s += kSmallWarps) {
+            for (uint32_t v = lane; v < n; v += 32) dist[v] = kSmallInf;
+            __syncwarp();
+            if (lane == 0) { dist[s] = 0; order[0] = (uint16_t)s; }
+            __syncwarp();
+            // ---- forward: level by level inside the warp -----------------------------------
+            uint32_t lb = 0, le = 1, level = 0;
+            while (lb < le) {
+                uint32_t tail = le;
+                for (uint32_t base = lb; base < le; base += 32) {
+                    const uint32_t i = base + lane;
+                    uint32_t rs = 0, deg = 0;
+                    if (i < le) {
+                        const uint32_t u = order[i];
+                        rs = __ldg(rp + u);
+                        deg = __ldg(rp + u + 1) - rs;
+                        my_reached += 1;
+                        my_edges += deg;
                     }
-                    for (uint32_t e = rs; e < re; ++e) {
-                        const uint32_t x = __ldg(col + e);
-                        if (active && dist[(size_t)x * kLanes + lane] == kSmallInf) {
-                            dist[(size_t)x * kLanes + lane] = (uint16_t)(level + 1);
-                            found = true;
+                    const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
+                    for (uint32_t k = 0; k < maxdeg; ++k) {
+                        bool found = false;
+                        uint32_t x = 0;
+                        if (k < deg) {
+                            x = __ldg(col + rs + k);
+                            if (dist[x] == kSmallInf) found = atomicCAS(&dist[x], kSmallInf, level + 1) == kSmallInf;
                         }
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found);
+                        if (found) order[tail + __popc(bal & lane_lt)] = (uint16_t)x;
+                        tail += __popc(bal);
                     }
                 }
-                if (__any_sync(0xFFFFFFFFu, found) && lane == 0) s_more = 1;
-                __syncthreads();
-                if (!s_more) break;
-                ++level;
+                __syncwarp();
+                lb = le; le = tail; ++level;
             }
-            const uint32_t depth = level;
+            const uint32_t depth = level - 1;               // deepest non-empty level
             if (depth > my_depth) my_depth = depth;
-            // ---- backward: deepest level first, pull from successors ---------------------
+            // ---- backward: walk the BFS order from the back, one level at a time -------------
+            // order[] is sorted by level; level l occupies a contiguous range ending at `hi`
+            uint32_t hi = le;                               // == number of reached vertices
             for (uint32_t l = depth; l >= 1; --l) {
-                for (uint32_t w = warp; w < n; w += kWarps) {
-                    const bool active = dist[(size_t)w * kLanes + lane] == l;
-                    if (__ballot_sync(0xFFFFFFFFu, active) == 0) continue;
-                    const uint32_t rs = __ldg(rp + w), re = __ldg(rp + w + 1);
-                    double acc = 0.0;
-                    uint32_t npred = 0;
-                    for (uint32_t e = rs; e < re; ++e) {       // CSR order: fixes the rounding
-                        const uint32_t x = __ldg(col + e);
-                        const uint32_t dx = dist[(size_t)x * kLanes + lane];
-                        if (active && dx == l + 1) acc += q[(size_t)x * kLanes + lane];
-                        npred += (dx == l - 1) ? 1u : 0u;
-                    }
-                    const double bk = 1.0 + acc;
-                    double contrib = 0.0;
-                    if (active) {
-                        q[(size_t)w * kLanes + lane] = bk / (double)npred;
-                        contrib = p.include_endpoints ? bk : bk - 1.0;
-                    }
-                    const double total = warp_sum(contrib);
-                    if (lane == 0) bpart[w] += total;
+                // find the start of level l: entries [lo, hi) have dist == l
+                uint32_t lo = hi;
+                for (;;) {                                  // step back in chunks of 32
+                    const uint32_t probe = lo > 32 ? lo - 32 : 0;
+                    const uint32_t j = probe + lane;
+                    const bool same = j < lo && dist[order[j]] == l;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, same);
+                    const uint32_t span = lo - probe;       // lanes [0, span) are valid
+                    const uint32_t valid_mask = span >= 32 ? 0xFFFFFFFFu : ((1u << span) - 1u);
+                    if (bal == valid_mask && probe > 0) { lo = probe; continue; }
+                    // the level starts inside this chunk: first lane (from the top) that is not level l
+                    const uint32_t not_l = ~bal & valid_mask;
+                    lo = not_l ? probe + (32 - __clz(not_l)) : probe;
+                    break;
                 }
-                __syncthreads();
+                for (uint32_t base = lo; base < hi; base += 32) {
+                    const uint32_t i = base + lane;
+                    if (i < hi) {
+                        const uint32_t w = order[i];
+                        const uint32_t rs = __ldg(rp + w), re = __ldg(rp + w + 1);
+                        double acc = 0.0;
+                        uint32_t npred = 0;
+                        for (uint32_t e = rs; e < re; ++e) {          // CSR order: fixes the rounding
+                            const uint32_t x = __ldg(col + e);
+                            const uint32_t dx = dist[x];
+                            if (dx == l + 1) acc += q[x];
+                            npred += (dx == l - 1) ? 1u : 0u;
+                        }
+                        const double bk = 1.0 + acc;
+                        q[w] = bk / (double)npred;
+                        bpart[w] += bk - sub;
+                    }
+                }
+                __syncwarp();
+                hi = lo;
             }
-            __syncthreads();
-            for (uint32_t v = threadIdx.x; v < n; v += kSmallThreads) bsum[v] += bpart[v];
+            __syncwarp();
         }
         __syncthreads();
+        // ---- warps' partial loads, summed in warp order ------------------------------------------
         double *out = p.out + p.out_off[g];
-        for (uint32_t v = threadIdx.x; v < n; v += kSmallThreads) out[v] = bsum[v];
+        for (uint32_t v = threadIdx.x; v < n; v += kSmallThreads) {
+            double acc = 0.0;
+            for (int w = 0; w < kSmallWarps; ++w)
+                acc += reinterpret_cast<const double *>(smem_raw + (size_t)w * small_warp_bytes(n))[np4 + v];
+            out[v] = acc;
+        }
         __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_reached += __shfl_xor_sync(0xFFFFFFFFu, my_reached, o);
+        my_edges += __shfl_xor_sync(0xFFFFFFFFu, my_edges, o);
     }
     if (lane == 0) {
         atomicAdd(&p.counters[0], my_reached);
         atomicAdd(&p.counters[1], my_edges);
-        atomicAdd(&p.counters[2], my_visits);
+        atomicAdd(&p.counters[2], my_reached);
         atomicMax(&p.counters[3], (unsigned long long)my_depth);
     }
 }

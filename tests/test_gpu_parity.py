@@ -149,8 +149,9 @@ def test_run_to_run_bitwise_reproducible(engine_ctx):
     dg.free()
 
 
-def test_batch_of_small_graphs_equals_singles_bitwise(ctx, oracle):
-    """One CTA per graph; results bit-identical to nec_vertex_load on each graph."""
+def test_batch_of_small_graphs_equals_singles(ctx, oracle):
+    """One CTA per graph, one warp per source: equal to nec_vertex_load on each graph up to the order in
+    which sources are summed (<= 1e-12), bit-reproducible run to run."""
     ens = [ne.ErEnsembleC(256, 4.0, 123_239_010 + g) for g in range(24)]
     ens += [ne.ErEnsembleC(33, 2.0, 3), ne.SwEnsemble(100, 0.2, 8), ne.ErEnsembleM(64, 200, 2), ne.ErEnsembleC(512, 3.0, 77)]
     graphs = [e.export_csr() for e in ens]
@@ -158,11 +159,13 @@ def test_batch_of_small_graphs_equals_singles_bitwise(ctx, oracle):
     graphs.append(csr_from_adj(adj_from_edges(300, [(i, i + 1) for i in range(299)])))  # depth 299
     for incl in (True, False):
         outs = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in graphs], incl)
-        for (rp, col), got in zip(graphs, outs):
+        again = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in graphs], incl)
+        for (rp, col), got, got2 in zip(graphs, outs, again):
             dg = ctx.upload(rp, col)
             single = dg.vertex_load(incl)
             dg.free()
-            assert got.tobytes() == single.tobytes()
+            assert got.tobytes() == got2.tobytes()
+            assert close(got, single, 1e-12)
             assert close(got, oracle.vertex_load(rp, col, incl), REL)
     with pytest.raises(ne.NecError):
         big = csr_from_adj([[] for _ in range(513)])
