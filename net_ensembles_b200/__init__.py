@@ -6,7 +6,7 @@ operator interface for this path (`Graph`, `SwGraph`-backed `SwEnsemble`, `ErEns
 `ErEnsembleM`, `BAensemble`, each with `vertex_load(include_endpoints)`).
 """
 from .api import (BAensemble, Context, DeviceGraph, ErEnsembleC, ErEnsembleM, Graph, NecError,  # noqa: F401
-                  SwEnsemble, default_context, gnm_scalable, ba_scalable, vertex_load_batch)
+                  SwEnsemble, chains_step_and_load, default_context, gnm_scalable, ba_scalable, vertex_load_batch)
 
 __all__ = ["Context", "DeviceGraph", "Graph", "ErEnsembleC", "ErEnsembleM", "SwEnsemble", "BAensemble",
-           "NecError", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch"]
+           "NecError", "chains_step_and_load", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch"]

@@ -62,6 +62,7 @@ NECH_SYMBOLS = {
     "nech_sw_root_targets": (c_int, [c_vp, c_vp]),
     "nech_rng_state": (c_int, [c_vp, c_vp]),
     "nech_vertex_load_cuda": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "nech_chains_step_and_load_cuda": (c_int, [c_vp, c_u32, c_u64, c_vp, c_int, c_vp]),
     "nech_pcg64_draws": (None, [c_u64, c_u64, c_vp]),
 }
 

@@ -138,6 +138,20 @@ def vertex_load_batch(ctx, graphs, include_endpoints):
     return np.split(out, np.cumsum(ns)[:-1]) if len(graphs) else []
 
 
+def chains_step_and_load(ctx, chains, m_steps, include_endpoints):
+    """Markov-chain measurement (benches/common/mod.rs:79-90): `m_steps` Markov steps on every
+    chain, then vertex_load of all their graphs in ONE launch (export + call happen in C++).
+    Returns a list of load vectors (views into one array)."""
+    lib = _lib.load()
+    handles = (c_vp * len(chains))(*[c._h for c in chains])
+    ns = [c.vertex_count() for c in chains]
+    out = np.empty(int(sum(ns)), dtype=np.float64)
+    rc = lib.nech_chains_step_and_load_cuda(handles, len(chains), int(m_steps), ctx._h, int(bool(include_endpoints)), _ptr(out))
+    if rc != 0:
+        raise NecError(rc, lib.nech_last_error().decode())
+    return np.split(out, np.cumsum(ns)[:-1]) if chains else []
+
+
 class _HostGraph:
     """Base of the host-side mirrors: owns a nech handle (adjacency lists live in C++)."""
 

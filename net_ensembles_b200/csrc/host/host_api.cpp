@@ -181,6 +181,49 @@ int nech_vertex_load_cuda(const void *p, nec_ctx *ctx, int include_endpoints, do
         }); }, NEC_EINVAL);
 }
 
+// Markov-chain shape (benches/common/mod.rs:79-90): `count` m_steps on every chain, then
+// vertex_load(include_endpoints) of ALL chains' graphs in one launch (one CTA per graph).
+// out receives the load vectors back to back.  count == 0 measures without stepping.
+int nech_chains_step_and_load_cuda(void *const *handles, uint32_t n_chains, uint64_t m_steps, nec_ctx *ctx,
+                                   int include_endpoints, double *out) {
+    return guarded([&]() -> int {
+        std::vector<uint32_t> n_per(n_chains);
+        std::vector<uint64_t> rp_off(n_chains), col_off(n_chains);
+        uint64_t rp_total = 0, col_total = 0;
+        for (uint32_t g = 0; g < n_chains; ++g) {
+            Handle *h = static_cast<Handle *>(handles[g]);
+            for (uint64_t k = 0; k < m_steps; ++k) switch (h->kind) {
+                case Kind::ErC: h->erc->m_step(); break;
+                case Kind::ErM: h->erm->m_step(); break;
+                case Kind::Sw: h->sw->m_step(); break;
+                default: g_err = "chain has no Markov step"; return NEC_EINVAL;
+            }
+            with_graph(h, [&](auto &gr) {
+                n_per[g] = (uint32_t)gr.vertex_count();
+                rp_off[g] = rp_total; col_off[g] = col_total;
+                rp_total += gr.vertex_count() + 1; col_total += gr.nnz();
+                return 0;
+            });
+        }
+        std::vector<uint32_t> rp(rp_total), col(col_total ? col_total : 1);
+        for (uint32_t g = 0; g < n_chains; ++g)
+            with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
+                uint32_t *r = rp.data() + rp_off[g];
+                uint32_t *c = col.data() + col_off[g];
+                uint32_t at = 0;
+                for (size_t v = 0; v < gr.vertices.size(); ++v) {
+                    r[v] = at;
+                    for (auto &e : gr.vertices[v].adj) c[at++] = e.to;
+                }
+                r[gr.vertices.size()] = at;
+                return 0;
+            });
+        int rc = nec_vertex_load_batch(ctx, n_chains, n_per.data(), rp_off.data(), rp.data(), col_off.data(), col.data(),
+                                       include_endpoints, out);
+        if (rc != NEC_OK) g_err = nec_last_error(ctx);
+        return rc; }, NEC_EINVAL);
+}
+
 // raw generator access, for the known-answer tests of the rand restatement
 void nech_pcg64_draws(uint64_t seed, uint64_t count, uint64_t *out_u64) {
     Pcg64 r = Pcg64::seed_from_u64(seed);

@@ -128,7 +128,9 @@ vertex_load_engine(const EngineParams p) {
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
     __shared__ unsigned long long s_cnt[3];
-    __shared__ uint2 s_stage[kWarps][32];       // backward: (neighbour, owner's source mask) per flattened edge
+    constexpr bool kStageRows = sizeof(DistT) == 1;      // 32 B distance rows are staged through shared memory
+    __shared__ uint2 s_stage[kWarps][2][32];             // backward: (neighbour, owner's source mask) per flattened entry
+    __shared__ __align__(16) unsigned char s_rows[kStageRows ? kWarps : 1][2][32][32];   // backward: staged distance rows
 
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
@@ -179,13 +181,13 @@ vertex_load_engine(const EngineParams p) {
             if (level >= level_limit) { too_deep = true; break; }
             uint32_t *next_cur = (level & 1) ? next_odd : next_even;
             uint32_t *next_nxt = (level & 1) ? next_even : next_odd;
-            const DistT next_d = (DistT)(level + 1);
+            const DistT cur_d = (DistT)level;
 
             for (uint32_t tile = qbeg + warp * 32; tile < qend; tile += kWarps * 32) {
                 const uint32_t idx = tile + lane;
-                uint32_t m = 0, rs = 0, deg = 0;
+                uint32_t m = 0, rs = 0, deg = 0, u = 0;
                 if (idx < qend) {
-                    const uint32_t u = queue[idx].x;
+                    u = queue[idx].x;
                     m = __ldcg(&next_cur[u]);
                     __stcg(&next_cur[u], 0u);        // self-cleaning: this parity is reused at level+2
                     queue[idx].y = m;                // the backward pass reads (vertex, mask)
@@ -195,6 +197,16 @@ vertex_load_engine(const EngineParams p) {
                     b_reached += pc;
                     b_edges += pc * deg;
                     b_visits += 1;
+                }
+                // distance rows of the dequeued entries: the mask is final now, so each row's bytes are
+                // written by ONE store instruction (lane k = source k) instead of bit by bit at discovery
+                {
+                    const uint32_t n_ent = min(32u, qend - tile);
+                    for (uint32_t e = 0; e < n_ent; ++e) {
+                        const uint32_t u_e = __shfl_sync(0xFFFFFFFFu, u, e);
+                        const uint32_t m_e = __shfl_sync(0xFFFFFFFFu, m, e);
+                        if ((m_e >> lane) & 1u) dist[(size_t)u_e * kLanes + lane] = cur_d;
+                    }
                 }
                 const uint32_t incl = warp_inclusive_scan(deg, lane);
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -222,11 +234,7 @@ vertex_load_engine(const EngineParams p) {
                     uint32_t enq_bits = 0;
 #pragma unroll
                     for (int j = 0; j < kFwdUnroll; ++j)
-                        if (fresh[j]) {
-                            for (uint32_t bits = fresh[j]; bits; bits &= bits - 1)
-                                dist[(size_t)x[j] * kLanes + (__ffs(bits) - 1)] = next_d;
-                            if (atomicOr(&next_nxt[x[j]], fresh[j]) == 0) enq_bits |= 1u << j;
-                        }
+                        if (fresh[j] && atomicOr(&next_nxt[x[j]], fresh[j]) == 0) enq_bits |= 1u << j;
 #pragma unroll
                     for (int j = 0; j < kFwdUnroll; ++j) {
                         const bool enqueue = (enq_bits >> j) & 1u;
@@ -304,30 +312,64 @@ vertex_load_engine(const EngineParams p) {
                     if (lane == cur) my_total = tot;
                 };
 
-                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                // Flattened adjacency entries are consumed in chunks of 32.  Two-deep pipeline per warp:
+                // chunk s+2's neighbour ids are being loaded (registers), chunk s+1's distance rows are
+                // in flight to shared memory (cp.async, 32 rows x 32 B per chunk, two lanes per row),
+                // chunk s is consumed: one LDS byte per (row, lane), then the predicated q loads.
+                auto edge_of = [&](uint32_t t0) -> uint2 {        // (neighbour id, owner's source mask) of flattened entry t0+lane
                     const uint32_t t = t0 + lane;
                     const int o = tile_owner(incl, t);
                     const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
                     const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
                     const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o);
-                    uint2 st = make_uint2(0u, 0u);
-                    if (t < total) st = make_uint2(__ldg(p.col_idx + rs_o + (t - off_o)), m_o);
+                    return t < total ? make_uint2(__ldg(p.col_idx + rs_o + (t - off_o)), m_o) : make_uint2(0u, 0u);
+                };
+                auto stage_rows = [&](int buf) {                  // rows of the chunk whose edges sit in s_stage[warp][buf]
+                    if constexpr (kStageRows) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = h * 16 + (lane >> 1);
+                            const uint2 e = s_stage[warp][buf][r];
+                            if (e.y) {
+                                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rows[warp][buf][r][(lane & 1) * 16]);
+                                const unsigned char *src = reinterpret_cast<const unsigned char *>(dist) + (size_t)e.x * kLanes + (lane & 1) * 16;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                const uint32_t n_chunks = (total + 31) / 32;
+                uint2 st_next = edge_of(0);
+                __syncwarp();
+                s_stage[warp][0][lane] = st_next;
+                __syncwarp();
+                stage_rows(0);
+                st_next = n_chunks > 1 ? edge_of(32) : make_uint2(0u, 0u);
+                for (uint32_t sc = 0; sc < n_chunks; ++sc) {
+                    const int buf = sc & 1;
+                    const uint32_t t0 = sc * 32;
+                    s_stage[warp][buf ^ 1][lane] = st_next;       // chunk sc+1 (zeros past the end); buffer was drained at sc-1
                     __syncwarp();
-                    s_stage[warp][lane] = st;
-                    __syncwarp();
+                    stage_rows(buf ^ 1);
+                    st_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : make_uint2(0u, 0u);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk sc's rows have landed (this lane's copies)
+                    __syncwarp();                                          // ... and every other lane's
                     const uint32_t cnt = min(32u, total - t0);
                     for (uint32_t c0 = 0; c0 < cnt; c0 += kUnroll) {
                         uint32_t dx[kUnroll];
                         double qv[kUnroll];
 #pragma unroll
                         for (int jj = 0; jj < kUnroll; ++jj) {
-                            const uint2 e = s_stage[warp][(c0 + jj) & 31];       // broadcast read; mask 0 past the end
-                            dx[jj] = ((e.y >> lane) & 1u) ? (uint32_t)dist[(size_t)e.x * kLanes + lane] : kInf;
+                            const uint2 e = s_stage[warp][buf][(c0 + jj) & 31];   // broadcast read; mask 0 past the end
+                            const bool act = (e.y >> lane) & 1u;
+                            if constexpr (kStageRows) dx[jj] = act ? (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][lane] : kInf;
+                            else dx[jj] = act ? (uint32_t)dist[(size_t)e.x * kLanes + lane] : kInf;
                         }
                         uint32_t pred_bits = 0;                                  // bit jj: neighbour jj is a predecessor
 #pragma unroll
                         for (int jj = 0; jj < kUnroll; ++jj) {
-                            qv[jj] = (dx[jj] == d_succ) ? q[(size_t)s_stage[warp][(c0 + jj) & 31].x * kLanes + lane] : 0.0;
+                            qv[jj] = (dx[jj] == d_succ) ? q[(size_t)s_stage[warp][buf][(c0 + jj) & 31].x * kLanes + lane] : 0.0;
                             pred_bits |= (dx[jj] == d_pred ? 1u : 0u) << jj;
                         }
 #pragma unroll
@@ -344,7 +386,9 @@ vertex_load_engine(const EngineParams p) {
                             }
                         }
                     }
+                    __syncwarp();                                 // buffer `buf` may be refilled next iteration
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 if (cur >= 0) finish_entry();
                 if (idx < le && deg != 0) bslot[w] += my_total;     // one writer per vertex per level
             }

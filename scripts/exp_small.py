@@ -21,3 +21,11 @@ for step in range(3):
     te = st["edge_pairs"] / 2
     print("step %d: host m_step+export %.1f ms, batch call %.1f ms (kernel %.2f ms) -> %.2f GTEPS kernel, %.2f GTEPS call; depth %d" % (
         step, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st["kernel_ms"], te / st["kernel_ms"] / 1e6, te / (t2 - t1) / 1e9, st["max_depth"]), flush=True)
+
+for step in range(3):
+    t0 = time.perf_counter()
+    outs = ne.chains_step_and_load(ctx, chains, 1, True)
+    t1 = time.perf_counter()
+    st = ctx.stats()
+    print("C++ path step %d: m_step + export + load %.1f ms (kernel %.2f ms) -> %.2f GTEPS end to end" % (
+        step, (t1 - t0) * 1e3, st["kernel_ms"], st["edge_pairs"] / 2 / (t1 - t0) / 1e9), flush=True)

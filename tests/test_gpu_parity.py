@@ -184,6 +184,17 @@ def test_markov_chain_measure_after_every_step(ctx, oracle):
             assert close(got, oracle.vertex_load(rp, col, True), REL)
 
 
+def test_chains_step_and_load_in_cpp(ctx, oracle):
+    chains = [ne.ErEnsembleC(48, 4.0, 500 + g) for g in range(12)] + [ne.SwEnsemble(40, 0.3, 9), ne.ErEnsembleM(30, 60, 4)]
+    twins = [ne.ErEnsembleC(48, 4.0, 500 + g) for g in range(12)] + [ne.SwEnsemble(40, 0.3, 9), ne.ErEnsembleM(30, 60, 4)]
+    for _ in range(2):
+        outs = ne.chains_step_and_load(ctx, chains, 5, False)
+        for t, got in zip(twins, outs):
+            t.m_steps(5)
+            rp, col = t.export_csr()
+            assert close(got, oracle.vertex_load(rp, col, False), REL)
+
+
 def test_invariants_at_scale(ctx):
     """Sizes the oracle cannot finish: integer invariants instead."""
     e = ne.SwEnsemble(1 << 14, 0.1, 123_239_010)
