@@ -81,6 +81,15 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Predicated global atomic OR with return value: one ATOMG instruction under a predicate instead of
+// a branch, so several of them can be in flight per thread.  Returns 0xFFFFFFFF when not executed.
+__device__ __forceinline__ uint32_t atom_or_if(bool pred, uint32_t *addr, uint32_t val) {
+    uint32_t old = 0xFFFFFFFFu;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.global.or.b32 %0, [%1], %2;\n\t}"
+                 : "+r"(old) : "l"(addr), "r"(val), "r"((uint32_t)pred) : "memory");
+    return old;
+}
+
 // Inclusive warp scan of per-lane counts.
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -225,16 +234,31 @@ vertex_load_engine(const EngineParams p) {
                         x[j] = 0; fresh[j] = 0;
                         if (t < total) { x[j] = __ldg(p.col_idx + rs_o + (t - off_o)); fresh[j] = m_o; }
                     }
+                    // every stage is a batch of kFwdUnroll INDEPENDENT operations per lane: all loads /
+                    // atomics of a stage are issued before any result is consumed (predicated PTX, no
+                    // branches, so the compiler cannot serialise the round trips)
+                    {
+                        uint32_t sv[kFwdUnroll];
 #pragma unroll
-                    for (int j = 0; j < kFwdUnroll; ++j)
-                        if (fresh[j]) fresh[j] &= ~__ldcg(&seen[x[j]]);
+                        for (int j = 0; j < kFwdUnroll; ++j) sv[j] = fresh[j] ? __ldcg(&seen[x[j]]) : 0xFFFFFFFFu;
 #pragma unroll
-                    for (int j = 0; j < kFwdUnroll; ++j)          // exact: racing lanes each keep disjoint bits
-                        if (fresh[j]) fresh[j] &= ~atomicOr(&seen[x[j]], fresh[j]);
+                        for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~sv[j];
+                    }
+                    {   // exact filter: racing lanes each keep disjoint bits
+                        uint32_t old[kFwdUnroll];
+#pragma unroll
+                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &seen[x[j]], fresh[j]);
+#pragma unroll
+                        for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~old[j];
+                    }
                     uint32_t enq_bits = 0;
+                    {
+                        uint32_t old[kFwdUnroll];
 #pragma unroll
-                    for (int j = 0; j < kFwdUnroll; ++j)
-                        if (fresh[j] && atomicOr(&next_nxt[x[j]], fresh[j]) == 0) enq_bits |= 1u << j;
+                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &next_nxt[x[j]], fresh[j]);
+#pragma unroll
+                        for (int j = 0; j < kFwdUnroll; ++j) enq_bits |= (fresh[j] != 0 && old[j] == 0 ? 1u : 0u) << j;
+                    }
 #pragma unroll
                     for (int j = 0; j < kFwdUnroll; ++j) {
                         const bool enqueue = (enq_bits >> j) & 1u;
