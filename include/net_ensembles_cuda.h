@@ -125,6 +125,16 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
                           const uint64_t *col_offsets, const uint32_t *col_idx_concat,
                           int include_endpoints, double *out_concat);
 
+/* Distance measures over the listed sources — the all-source BFS measures of the crate that sit
+ * next to vertex_load in its benches (benches/common/mod.rs:53-64): for source sources[i]
+ *   ecc[i]      = depth of the BFS from it   (longest_shortest_path_from_index, generic_graph.rs:1140-1144)
+ *   sum_dist[i] = sum of the distances to every vertex it reaches (closeness_centrality, :1387-1403:
+ *                 count[v] = sum_s d(s,v), which equals this sum for source v in an undirected graph)
+ *   reached[i]  = number of vertices it reaches, itself included (connectivity test of diameter, :1116-1136)
+ * Integer results, exact.  Forward (bit-parallel, 32 sources per pass) only; any output may be NULL. */
+int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached);
+
 /* Intermediate state of one source, for exactness checks: dist[n] (UINT32_MAX =
  * unreached), npred[n] (number of BFS predecessors), sigma[n] (f64 shortest-path
  * counts; NOT used by the load), bk[n] (accumulated value b_k after the backward

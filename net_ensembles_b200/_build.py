@@ -52,7 +52,7 @@ def build_cuda(force=False, verbose=False):
 
 def build_oracle(force=False):
     src = os.path.join(ROOT, "oracle", "ref_vertex_load.c")
-    if not force and not _stale(ORACLE_PATH, [src, os.path.join(ROOT, "oracle", "Makefile")]):
+    if not force and not _stale(ORACLE_PATH, [src, os.path.join(ROOT, "oracle", "ref_measures.c"), os.path.join(ROOT, "oracle", "Makefile")]):
         return ORACLE_PATH
     res = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")] + (["-B"] if force else []),
                          capture_output=True, text=True)

@@ -112,6 +112,36 @@ class DeviceGraph:
         self.ctx._check(self.ctx._lib.nec_vertex_load_sources_device(self.ctx._h, self._h, _ptr(src), src.shape[0],
                                                                      int(bool(include_endpoints)), c_vp(d_out_ptr)))
 
+    def distance_measures(self, sources=None):
+        """(ecc, sum_dist, reached) per listed source (all vertices by default); exact integers."""
+        src = np.arange(self.n, dtype=np.uint32) if sources is None else np.ascontiguousarray(sources, dtype=np.uint32)
+        k = src.shape[0]
+        ecc, sumd, reached = np.zeros(k, np.uint32), np.zeros(k, np.uint64), np.zeros(k, np.uint32)
+        self.ctx._check(self.ctx._lib.nec_distance_measures(self.ctx._h, self._h, _ptr(src), k, _ptr(ecc), _ptr(sumd), _ptr(reached)))
+        return ecc, sumd, reached
+
+    def diameter(self):
+        """`GenericGraph::diameter` (generic_graph.rs:1116-1136): None if empty or not connected."""
+        if self.n == 0:
+            return None
+        ecc, _, reached = self.distance_measures()
+        if int(reached[0]) != self.n:
+            return None
+        return int(ecc[1:].max()) if self.n > 1 else 0          # the crate skips vertex 0; same maximum
+
+    def longest_shortest_path_from_index(self, index):
+        """generic_graph.rs:1140-1144."""
+        if not 0 <= index < self.n:
+            return None
+        return int(self.distance_measures([index])[0][0])
+
+    def closeness_centrality(self):
+        """`GenericGraph::closeness_centrality` (generic_graph.rs:1387-1403): (N-1) / sum_s d(s, v);
+        the sum over sources of the distance TO v equals the sum of distances FROM v (undirected)."""
+        _, sumd, _ = self.distance_measures()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.float64(self.n - 1) / sumd.astype(np.float64)
+
     def bfs_debug(self, source):
         n = self.n
         dist, npred = np.empty(n, np.uint32), np.empty(n, np.uint32)
@@ -209,6 +239,28 @@ class _HostGraph:
     def to_device(self, ctx=None):
         ctx = ctx or default_context()
         return DeviceGraph(ctx, *self.export_csr())
+
+    # the all-source BFS measures that sit beside vertex_load in the crate's benches
+    def diameter(self, ctx=None):
+        dg = self.to_device(ctx)
+        try:
+            return dg.diameter()
+        finally:
+            dg.free()
+
+    def closeness_centrality(self, ctx=None):
+        dg = self.to_device(ctx)
+        try:
+            return dg.closeness_centrality()
+        finally:
+            dg.free()
+
+    def longest_shortest_path_from_index(self, index, ctx=None):
+        dg = self.to_device(ctx)
+        try:
+            return dg.longest_shortest_path_from_index(index)
+        finally:
+            dg.free()
 
 
 class Graph(_HostGraph):

@@ -157,9 +157,16 @@ int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_sl
     return NEC_OK;
 }
 
-template <typename DistT, bool kDebug>
+struct MeasureOut {                  // device outputs of the distance-measure mode, indexed like `sources`
+    uint32_t *ecc;
+    unsigned long long *sumdist;
+    uint32_t *reached;
+};
+
+template <typename DistT, int kMode>
 int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
-                  uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk) {
+                  uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk,
+                  const MeasureOut *mo = nullptr) {
     const Arena &a = ctx->arena;
     nec::EngineParams p{};
     p.n = g->n; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
@@ -174,7 +181,8 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.max_levels = a.max_levels;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
-    nec::vertex_load_engine<DistT, kDebug><<<slots, nec::kEngineThreads, 0, ctx->stream>>>(p);
+    if (mo) { p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
+    nec::vertex_load_engine<DistT, kMode><<<slots, nec::kEngineThreads, 0, ctx->stream>>>(p);
     NEC_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     return NEC_OK;
@@ -182,8 +190,8 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
 
 int engine_occupancy(nec_ctx *ctx) {
     int o8 = 0, o32 = 0;
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, false>, nec::kEngineThreads, 0));
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, false>, nec::kEngineThreads, 0));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, 0>, nec::kEngineThreads, 0));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0>, nec::kEngineThreads, 0));
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
     return NEC_OK;
@@ -191,14 +199,15 @@ int engine_occupancy(nec_ctx *ctx) {
 
 // Batched engine: partial load of `n_sources` sources into device vector d_out (n doubles).
 int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
-                int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
+                int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk,
+                const MeasureOut *mo = nullptr) {
     ctx->stats = nec_stats{};
     ctx->stats.n_sources = n_sources;
     const uint32_t n = g->n;
     if (n == 0) return NEC_OK;
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_sources == 0) {
-        NEC_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(double), ctx->stream));
+        if (d_out) NEC_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(double), ctx->stream));
         return NEC_OK;
     }
     for (uint32_t k = 0; k < n_sources; ++k)
@@ -222,13 +231,16 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * sizeof(uint32_t) * slots, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = debug ? launch_engine<uint8_t, true>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
-               : launch_engine<uint8_t, false>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
+    rc = mo    ? launch_engine<uint8_t, 2>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr, mo)
+       : debug ? launch_engine<uint8_t, 1>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
+               : launch_engine<uint8_t, 0>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
     if (rc != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
-    NEC_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches++;
+    if (!mo) {
+        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
+        NEC_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->arena.bytes;
@@ -260,7 +272,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         // keep pass-1 result: d_out already holds the sum of the shallow batches
         double *d_keep = nullptr;
         NEC_CUDA(ctx, cudaMalloc((void **)&d_keep, (size_t)n * sizeof(double)));
-        cudaMemcpyAsync(d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (!mo) cudaMemcpyAsync(d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
         if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, deep.size())) != NEC_OK) { cudaFree(d_keep); return rc; }
         cudaMemcpyAsync(ctx->d_worklist, deep.data(), deep.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
         uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
@@ -272,14 +284,17 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         cudaMemsetAsync(w.mask, 0, w.mask_stride * sizeof(uint32_t) * slots2, ctx->stream);
         cudaMemsetAsync(w.bslot, 0, w.bslot_stride * sizeof(double) * slots2, ctx->stream);
         cudaEventRecord(ctx->ev0, ctx->stream);
-        rc = debug ? launch_engine<uint32_t, true>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, dbg_npred, dbg_bk)
-                   : launch_engine<uint32_t, false>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr);
+        rc = mo    ? launch_engine<uint32_t, 2>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr, mo)
+           : debug ? launch_engine<uint32_t, 1>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, dbg_npred, dbg_bk)
+                   : launch_engine<uint32_t, 0>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr);
         if (rc != NEC_OK) { cudaFree(d_keep); return rc; }
         cudaEventRecord(ctx->ev_mid, ctx->stream);
-        // slot 0's partial absorbs the pass-1 sums so that one reduction produces the result
-        nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, d_keep, n);
-        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, w.bslot_stride, slots2, n, d_out);
-        ctx->stats.kernel_launches += 2;
+        if (!mo) {
+            // slot 0's partial absorbs the pass-1 sums so that one reduction produces the result
+            nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, d_keep, n);
+            nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, w.bslot_stride, slots2, n, d_out);
+            ctx->stats.kernel_launches += 2;
+        }
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream);
@@ -669,6 +684,31 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
     cleanup();
     if (e != cudaSuccess) return fail(ctx, NEC_ECUDA, "nec_bfs_debug: %s", cudaGetErrorString(e));
     return NEC_OK;
+}
+
+int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_distance_measures: NULL argument");
+    ctx->stats = nec_stats{};
+    if (n_sources == 0 || g->n == 0) return NEC_OK;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    MeasureOut mo{};
+    cudaError_t e = cudaMalloc((void **)&mo.ecc, (size_t)n_sources * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mo.sumdist, (size_t)n_sources * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mo.reached, (size_t)n_sources * 4);
+    auto cleanup = [&]() { cudaFree(mo.ecc); cudaFree(mo.sumdist); cudaFree(mo.reached); };
+    if (e != cudaSuccess) { cleanup(); return fail(ctx, NEC_ENOMEM, "nec_distance_measures: %s", cudaGetErrorString(e)); }
+    int rc = run_sources_batched(ctx, g, sources, n_sources, 1, nullptr, false, nullptr, nullptr, &mo);
+    if (rc == NEC_OK) {
+        if (ecc) cudaMemcpyAsync(ecc, mo.ecc, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (sum_dist) cudaMemcpyAsync(sum_dist, mo.sumdist, (size_t)n_sources * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (reached) cudaMemcpyAsync(reached, mo.reached, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, NEC_ECUDA, "nec_distance_measures: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
 }
 
 int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,

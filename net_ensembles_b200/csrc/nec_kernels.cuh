@@ -69,6 +69,10 @@ struct EngineParams {
     // optional per-(vertex,lane) debug planes of slot 0 (nec_bfs_debug)
     uint32_t *dbg_npred;
     double *dbg_bk;
+    // distance-measure outputs, indexed like `sources` (kMode 2)
+    uint32_t *out_ecc;
+    unsigned long long *out_sumdist;
+    uint32_t *out_reached;
 };
 
 template <typename DistT> struct DistTraits;
@@ -113,9 +117,14 @@ __device__ __forceinline__ int tile_owner(uint32_t incl, uint32_t t) {
 }
 
 // The engine.  One CTA = one slot; loops over its batches.
-template <typename DistT, bool kDebug>
+// kMode 0: vertex_load; 1: vertex_load + per-(vertex,lane) debug planes (nec_bfs_debug);
+// 2: distance measures only — the forward pass alone, per source eccentricity / sum of distances /
+//    reached count (diameter, closeness_centrality: reference generic_graph.rs:1116-1144, :1387-1403).
+template <typename DistT, int kMode>
 __global__ void __launch_bounds__(kEngineThreads, kEngineMinBlocks)
 vertex_load_engine(const EngineParams p) {
+    constexpr bool kDebug = kMode == 1;
+    constexpr bool kMeasure = kMode == 2;
     constexpr uint32_t kInf = DistTraits<DistT>::kInf;
     constexpr int kWarps = kEngineThreads / 32;
     const int lane = threadIdx.x & 31;
@@ -136,6 +145,8 @@ vertex_load_engine(const EngineParams p) {
 
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
+    __shared__ unsigned long long s_msum[kLanes];        // kMode 2: per source of the batch
+    __shared__ uint32_t s_mreach[kLanes], s_mecc[kLanes];
     __shared__ unsigned long long s_cnt[3];
     constexpr bool kStageRows = sizeof(DistT) == 1;      // 32 B distance rows are staged through shared memory
     __shared__ uint2 s_stage[kWarps][2][32];             // backward: (neighbour, owner's source mask) per flattened entry
@@ -160,6 +171,7 @@ vertex_load_engine(const EngineParams p) {
             for (size_t i = threadIdx.x; i < n16; i += kEngineThreads) d16[i] = inf4;
         }
         if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; }
+        if (kMeasure && threadIdx.x < kLanes) { s_msum[threadIdx.x] = 0; s_mreach[threadIdx.x] = 0; s_mecc[threadIdx.x] = 0; }
         __syncthreads();
 
         // ---- seed level 0: bit k <-> source k of the batch ------------------------------
@@ -199,7 +211,7 @@ vertex_load_engine(const EngineParams p) {
                     u = queue[idx].x;
                     m = __ldcg(&next_cur[u]);
                     __stcg(&next_cur[u], 0u);        // self-cleaning: this parity is reused at level+2
-                    queue[idx].y = m;                // the backward pass reads (vertex, mask)
+                    if (!kMeasure) queue[idx].y = m; // the backward pass reads (vertex, mask)
                     rs = __ldg(p.row_ptr + u);
                     deg = __ldg(p.row_ptr + u + 1) - rs;
                     const uint32_t pc = __popc(m);
@@ -209,7 +221,20 @@ vertex_load_engine(const EngineParams p) {
                 }
                 // distance rows of the dequeued entries: the mask is final now, so each row's bytes are
                 // written by ONE store instruction (lane k = source k) instead of bit by bit at discovery
-                {
+                if (kMeasure) {
+                    // source k has popc(ballot(bit k)) vertices of this tile on the current level
+                    uint32_t mine_cnt = 0;
+#pragma unroll
+                    for (int k = 0; k < kLanes; ++k) {
+                        const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, (m >> k) & 1u));
+                        if (lane == k) mine_cnt = c;
+                    }
+                    if (mine_cnt) {
+                        atomicAdd(&s_msum[lane], (unsigned long long)mine_cnt * level);
+                        atomicAdd(&s_mreach[lane], mine_cnt);
+                        atomicMax(&s_mecc[lane], level);
+                    }
+                } else {
                     const uint32_t n_ent = min(32u, qend - tile);
                     for (uint32_t e = 0; e < n_ent; ++e) {
                         const uint32_t u_e = __shfl_sync(0xFFFFFFFFu, u, e);
@@ -296,6 +321,20 @@ vertex_load_engine(const EngineParams p) {
         atomicAdd(&s_cnt[2], (unsigned long long)b_visits);
         const uint32_t depth = level - 1;             // deepest non-empty level
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
+        if (kMeasure) {
+            if (depth > my_depth) my_depth = depth;
+            if (threadIdx.x < kLanes) {
+                const uint32_t sidx = batch * kLanes + threadIdx.x;
+                if (sidx < p.n_sources) {
+                    if (p.out_ecc) p.out_ecc[sidx] = s_mecc[threadIdx.x];
+                    if (p.out_sumdist) p.out_sumdist[sidx] = s_msum[threadIdx.x];
+                    if (p.out_reached) p.out_reached[sidx] = s_mreach[threadIdx.x];
+                }
+            }
+            if (threadIdx.x == 0) p.batch_status[batch] = kDone;
+            __syncthreads();
+            continue;
+        }
         if (depth > my_depth) my_depth = depth;
 
         // ---- backward: levels depth .. 1, pull from successors --------------------------

@@ -46,6 +46,31 @@ class Oracle:
         assert rc == 0
         return dist, npred, sigma, bk
 
+    def distance_measures(self, row_ptr, col, sources=None):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        n = len(row_ptr) - 1
+        src = np.arange(n, dtype=np.uint32) if sources is None else np.ascontiguousarray(sources, np.uint32)
+        ecc, sumd, reached = np.zeros(len(src), np.uint32), np.zeros(len(src), np.uint64), np.zeros(len(src), np.uint32)
+        rc = self.lib.ref_distance_measures(c_u32(n), _p(row_ptr), _p(col), _p(src), c_u32(len(src)), _p(ecc), _p(sumd), _p(reached))
+        assert rc == 0
+        return ecc, sumd, reached
+
+    def diameter(self, row_ptr, col):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        self.lib.ref_diameter.restype = ctypes.c_int64
+        d = int(self.lib.ref_diameter(c_u32(len(row_ptr) - 1), _p(row_ptr), _p(col)))
+        assert d >= -1
+        return None if d < 0 else d
+
+    def closeness_centrality(self, row_ptr, col):
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        out = np.zeros(len(row_ptr) - 1, np.float64)
+        assert self.lib.ref_closeness_centrality(c_u32(len(row_ptr) - 1), _p(row_ptr), _p(col), _p(out)) == 0
+        return out
+
     def max_threads(self):
         return int(self.lib.ref_omp_max_threads())
 
