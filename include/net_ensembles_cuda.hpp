@@ -12,6 +12,7 @@
 // vector owned by the caller.  The reference call is infallible; here a failing device call
 // throws (the Rust shim panics) — there is no CPU fallback.
 #pragma once
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -56,6 +57,30 @@ public:
         std::vector<double> out(n_);
         if (nec_vertex_load(ctx_.raw(), g_, include_endpoints ? 1 : 0, out.data()) != NEC_OK)
             throw std::runtime_error(std::string("nec_vertex_load: ") + nec_last_error(ctx_.raw()));
+        return out;
+    }
+
+    // GenericGraph::diameter (generic_graph.rs:1116-1136): nullopt if empty or not connected
+    std::optional<size_t> diameter() const {
+        if (n_ == 0) return std::nullopt;
+        std::vector<uint32_t> src(n_), ecc(n_), reached(n_);
+        for (uint32_t v = 0; v < n_; ++v) src[v] = v;
+        if (nec_distance_measures(ctx_.raw(), g_, src.data(), n_, ecc.data(), nullptr, reached.data()) != NEC_OK)
+            throw std::runtime_error(std::string("nec_distance_measures: ") + nec_last_error(ctx_.raw()));
+        if (reached[0] != n_) return std::nullopt;
+        uint32_t best = 0;
+        for (uint32_t v = 1; v < n_; ++v) best = ecc[v] > best ? ecc[v] : best;
+        return best;
+    }
+    // GenericGraph::closeness_centrality (generic_graph.rs:1387-1403)
+    std::vector<double> closeness_centrality() const {
+        std::vector<uint32_t> src(n_);
+        std::vector<uint64_t> sum(n_);
+        for (uint32_t v = 0; v < n_; ++v) src[v] = v;
+        if (nec_distance_measures(ctx_.raw(), g_, src.data(), n_, nullptr, sum.data(), nullptr) != NEC_OK)
+            throw std::runtime_error(std::string("nec_distance_measures: ") + nec_last_error(ctx_.raw()));
+        std::vector<double> out(n_);
+        for (uint32_t v = 0; v < n_; ++v) out[v] = (double)(n_ - 1) / (double)sum[v];
         return out;
     }
 

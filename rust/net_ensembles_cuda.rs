@@ -27,6 +27,8 @@ extern "C" {
     fn nec_vertex_load(ctx: *mut NecCtx, g: *const NecGraph, include_endpoints: c_int, out: *mut f64) -> c_int;
     fn nec_vertex_load_sources(ctx: *mut NecCtx, g: *const NecGraph, sources: *const u32, n_sources: u32,
                                include_endpoints: c_int, out: *mut f64) -> c_int;
+    fn nec_distance_measures(ctx: *mut NecCtx, g: *const NecGraph, sources: *const u32, n_sources: u32,
+                             ecc: *mut u32, sum_dist: *mut u64, reached: *mut u32) -> c_int;
     #[allow(dead_code)]
     fn nec_set_stream(ctx: *mut NecCtx, cuda_stream: *mut c_void) -> c_int;
 }
@@ -65,6 +67,28 @@ where T: Node, A: AdjContainer<T>
         row_ptr.push(col_idx.len() as u64);
     }
     (row_ptr, col_idx)
+}
+
+/// `diameter()` (generic_graph.rs:1116-1136) and `closeness_centrality()` (:1387-1403) on the GPU.
+pub fn diameter_and_closeness_cuda<T, A>(ctx: &CudaContext, g: &GenericGraph<T, A>) -> (Option<usize>, Vec<f64>)
+where T: Node, A: AdjContainer<T>
+{
+    let n = g.vertex_count();
+    if n == 0 { return (None, Vec::new()); }
+    let (row_ptr, col_idx) = export_csr(g);
+    let sources: Vec<u32> = (0..n as u32).collect();
+    let (mut ecc, mut sum, mut reached) = (vec![0u32; n], vec![0u64; n], vec![0u32; n]);
+    unsafe {
+        let mut dg = std::ptr::null_mut();
+        let rc = nec_graph_upload(ctx.raw, n as u32, col_idx.len() as u64, row_ptr.as_ptr(), col_idx.as_ptr(), &mut dg);
+        if rc != 0 { panic!("nec_graph_upload failed ({}): {}", rc, last_error(ctx.raw)); }
+        let rc = nec_distance_measures(ctx.raw, dg, sources.as_ptr(), n as u32, ecc.as_mut_ptr(), sum.as_mut_ptr(), reached.as_mut_ptr());
+        nec_graph_free(ctx.raw, dg);
+        if rc != 0 { panic!("nec_distance_measures failed ({}): {}", rc, last_error(ctx.raw)); }
+    }
+    let diameter = if reached[0] as usize == n { Some(ecc[1..].iter().copied().max().unwrap_or(0) as usize) } else { None };
+    let val = (n - 1) as f64;
+    (diameter, sum.iter().map(|&c| val / c as f64).collect())
 }
 
 pub trait VertexLoadCuda {

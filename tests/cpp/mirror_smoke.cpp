@@ -40,6 +40,15 @@ int main(int argc, char **argv) {
     if (!close_enough(vertex_load_cuda(ctx, nec_host::Graph(4), true), {0, 0, 0, 0})) return 12;
     if (!close_enough(vertex_load_cuda(ctx, g8, false),
                       {0.0, 4.666666666666666, 8.0, 0.6666666666666665, 8.666666666666668, 10.0, 0.0, 0.0})) return 13;
+    {   // diameter known answers (tests/integration_test_graph.rs:166-184)
+        nec_host::Graph path5(5);
+        for (uint32_t i = 0; i < 4; ++i) path5.add_edge(i, i + 1);
+        DeviceGraph d(ctx, path5);
+        if (d.diameter().value_or(99) != 4) return 15;
+        DeviceGraph k(ctx, k4);
+        if (k.diameter().value_or(99) != 1) return 16;
+        if (k.closeness_centrality() != std::vector<double>{1.0, 1.0, 1.0, 1.0}) return 17;
+    }
     const std::vector<double> l = vertex_load_cuda(ctx, erc, true);   // ensemble -> graph via the blanket overload
     if (l.size() != 50) return 14;
     std::printf("cpp mirror ok\n");
