@@ -71,7 +71,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # NEC_LIB_PATH: A/B experiments with two builds on the same GPU box (scripts/)
+    return os.environ.get("NEC_LIB_PATH") or _build.LIB_PATH
 
 
 def load():

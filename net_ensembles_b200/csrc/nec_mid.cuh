@@ -89,6 +89,21 @@ __device__ __forceinline__ void slab_prefetch(uint4 *stage_t, const uint4 *__res
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Predicated shared-memory accesses on 32-bit shared addresses (no branches, no generic addressing).
+__device__ __forceinline__ uint32_t lds_u8_if(bool pred, uint32_t saddr, uint32_t otherwise) {
+    uint32_t v = otherwise;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u8 %0, [%1];\n\t}" : "+r"(v) : "r"(saddr), "r"((uint32_t)pred) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8_if(bool pred, uint32_t saddr, uint32_t value) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(saddr), "r"(value), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_or_if(bool pred, uint32_t saddr, uint32_t value) {
+    uint32_t old = 0xFFFFFFFFu;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.or.b32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(saddr), "r"(value), "r"((uint32_t)pred) : "memory");
+    return old;
+}
+
 template <int W>
 __global__ void __launch_bounds__(kMidThreads, 2)
 mid_engine(const MidParams p) {
@@ -103,6 +118,8 @@ mid_engine(const MidParams p) {
     uint8_t *dist = mid_smem;
     uint32_t *claim = reinterpret_cast<uint32_t *>(dist + p.n_pad);
     const uint32_t claim_words = (n + 31) / 32;
+    const uint32_t dist_s32 = (uint32_t)__cvta_generic_to_shared(dist);
+    const uint32_t claim_s32 = (uint32_t)__cvta_generic_to_shared(claim);
     uint4 *stage = reinterpret_cast<uint4 *>(mid_smem + p.n_pad + (((size_t)claim_words * 4 + 15) / 16 * 16)) + threadIdx.x;
 
     __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
@@ -240,21 +257,22 @@ mid_engine(const MidParams p) {
                         if (pos < (uint32_t)kMidHubCap) { s_hub[pos] = u; deg = 0; }   // else: expand inline (slow, correct)
                     }
                 }
-                // read each slab neighbour's distance once: classify it, claim it if unreached
+                // read each slab neighbour's distance once: classify it, claim it if unreached.
+                // Branch-free (predicated shared-memory PTX): lanes differ per slot, branches would serialise.
                 uint32_t won = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
                     const bool valid = (uint32_t)(k - 1) < deg;
                     const uint32_t x = row[k];
-                    const uint32_t d = valid ? (uint32_t)dist[x] : 0xFFFFu;
-                    if (d == 0xFFu) {
-                        cls |= 1u << (k - 1);
-                        if (claim_vertex(x, next_d)) won |= 1u << k;
-                    } else if (d == next_d) {
-                        cls |= 1u << (k - 1);
-                    } else if (d == pred_d) {
-                        cls += 1u << 16;
-                    }
+                    const uint32_t d = lds_u8_if(valid, dist_s32 + x, 0xFFFFu);
+                    const bool unreached = d == 0xFFu;
+                    const uint32_t bit = 1u << (x & 31);
+                    const uint32_t old = atoms_or_if(unreached, claim_s32 + ((x >> 5) << 2), bit);   // ~0 if not executed
+                    const bool mine = !(old & bit);
+                    sts_u8_if(mine, dist_s32 + x, next_d);
+                    won |= (mine ? 1u : 0u) << k;
+                    cls |= ((unreached || d == next_d) ? 1u : 0u) << (k - 1);
+                    cls += (d == pred_d ? 1u : 0u) << 16;
                 }
                 if (u != kNone) __stcs(&clsq[i], cls);
                 {   // append everything this warp found with ONE tail update
