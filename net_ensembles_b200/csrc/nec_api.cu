@@ -328,7 +328,8 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
 // One-source-per-CTA engine (nec_mid.cuh).  Sources it hands back (too deep / predecessor
 // count overflow) are appended to `fallback`.
 int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
-                    int include_endpoints, double *d_out, std::vector<uint32_t> &fallback) {
+                    int include_endpoints, double *d_out, std::vector<uint32_t> &fallback,
+                    const MeasureOut *mo = nullptr, std::vector<uint32_t> *fallback_index = nullptr) {
     const uint32_t n = g->n;
     ctx->stats = nec_stats{};
     ctx->stats.n_sources = n_sources;
@@ -379,13 +380,16 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
     p.np_base = d_np; p.np_stride = np_stride;
     p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
+    if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (g->slab_w == 8) nec::mid_engine<8><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
     else nec::mid_engine<16><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
     NEC_CUDA(ctx, cudaGetLastError());
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
-    NEC_CUDA(ctx, cudaGetLastError());
+    if (!mo) {
+        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
+        NEC_CUDA(ctx, cudaGetLastError());
+    }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<uint8_t> status(n_sources);
     unsigned long long counters[8];
@@ -402,7 +406,10 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->mid_bytes;
     for (uint32_t k = 0; k < n_sources; ++k) {
-        if (status[k] == nec::kMidTooDeep || status[k] == nec::kMidPredOverflow) fallback.push_back(h_sources[k]);
+        if (status[k] == nec::kMidTooDeep || status[k] == nec::kMidPredOverflow) {
+            fallback.push_back(h_sources[k]);
+            if (fallback_index) fallback_index->push_back(k);
+        }
         else if (status[k] != nec::kMidDone) return fail(ctx, NEC_EINTERNAL, "source index %u was not processed (status %u)", k, (unsigned)status[k]);
     }
     ctx->stats.reached_pairs = counters[0];
@@ -699,7 +706,43 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     if (e == cudaSuccess) e = cudaMalloc((void **)&mo.reached, (size_t)n_sources * 4);
     auto cleanup = [&]() { cudaFree(mo.ecc); cudaFree(mo.sumdist); cudaFree(mo.reached); };
     if (e != cudaSuccess) { cleanup(); return fail(ctx, NEC_ENOMEM, "nec_distance_measures: %s", cudaGetErrorString(e)); }
-    int rc = run_sources_batched(ctx, g, sources, n_sources, 1, nullptr, false, nullptr, nullptr, &mo);
+    for (uint32_t k = 0; k < n_sources; ++k)
+        if (sources[k] >= g->n) { cleanup(); return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", sources[k], k, g->n); }
+    const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2) &&
+                        nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u;
+    int rc;
+    if (mid_ok) {
+        std::vector<uint32_t> fb, fb_index;
+        rc = run_sources_mid(ctx, g, sources, n_sources, 1, nullptr, fb, &mo, &fb_index);
+        if (rc == NEC_OK && !fb.empty()) {       // sources deeper than 253 levels: batched engine (32-bit distances), scattered back
+            const nec_stats first = ctx->stats;
+            MeasureOut part{};
+            const size_t k = fb.size();
+            cudaError_t e2 = cudaMalloc((void **)&part.ecc, k * 4);
+            if (e2 == cudaSuccess) e2 = cudaMalloc((void **)&part.sumdist, k * 8);
+            if (e2 == cudaSuccess) e2 = cudaMalloc((void **)&part.reached, k * 4);
+            if (e2 != cudaSuccess) rc = fail(ctx, NEC_ENOMEM, "nec_distance_measures: %s", cudaGetErrorString(e2));
+            if (rc == NEC_OK) rc = run_sources_batched(ctx, g, fb.data(), (uint32_t)k, 1, nullptr, false, nullptr, nullptr, &part);
+            if (rc == NEC_OK) {
+                std::vector<uint32_t> pe(k), pr(k);
+                std::vector<unsigned long long> ps(k);
+                cudaMemcpy(pe.data(), part.ecc, k * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(ps.data(), part.sumdist, k * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(pr.data(), part.reached, k * 4, cudaMemcpyDeviceToHost);
+                for (size_t j = 0; j < k; ++j) {
+                    cudaMemcpy(mo.ecc + fb_index[j], &pe[j], 4, cudaMemcpyHostToDevice);
+                    cudaMemcpy(mo.sumdist + fb_index[j], &ps[j], 8, cudaMemcpyHostToDevice);
+                    cudaMemcpy(mo.reached + fb_index[j], &pr[j], 4, cudaMemcpyHostToDevice);
+                }
+                ctx->stats.kernel_ms += first.kernel_ms; ctx->stats.engine_ms += first.engine_ms;
+                ctx->stats.edge_pairs += first.edge_pairs; ctx->stats.reached_pairs += first.reached_pairs;
+                ctx->stats.n_sources = n_sources; ctx->stats.engine = 1u | (2u << 4);
+            }
+            cudaFree(part.ecc); cudaFree(part.sumdist); cudaFree(part.reached);
+        }
+    } else {
+        rc = run_sources_batched(ctx, g, sources, n_sources, 1, nullptr, false, nullptr, nullptr, &mo);
+    }
     if (rc == NEC_OK) {
         if (ecc) cudaMemcpyAsync(ecc, mo.ecc, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (sum_dist) cudaMemcpyAsync(sum_dist, mo.sumdist, (size_t)n_sources * 8, cudaMemcpyDeviceToHost, ctx->stream);

@@ -62,6 +62,12 @@ struct MidParams {
     uint32_t *cls_base;                       // same stride as order
     double *bslot_base;    size_t bslot_stride;
     uint8_t *np_base;      size_t np_stride;
+    // measure_only != 0: forward pass only; per source index eccentricity / sum of distances / reached
+    // count (nec_distance_measures) — they fall out of the level offsets, no extra traversal work
+    int measure_only;
+    uint32_t *out_ecc;
+    unsigned long long *out_sumdist;
+    uint32_t *out_reached;
     uint8_t *source_status;                   // per source index
     unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
 };
@@ -312,6 +318,23 @@ mid_engine(const MidParams p) {
         }
         const uint32_t depth = level - 1;
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
+        if (p.measure_only) {
+            if (threadIdx.x == 0) {
+                unsigned long long sum = 0;
+                for (uint32_t l = 1; l <= depth; ++l) sum += (unsigned long long)l * (s_lvl[l + 1] - s_lvl[l]);
+                if (p.out_ecc) p.out_ecc[si] = depth;
+                if (p.out_sumdist) p.out_sumdist[si] = sum;
+                if (p.out_reached) p.out_reached[si] = s_lvl[depth + 1];
+                p.source_status[si] = kMidDone;
+            }
+            if (depth > my_depth) my_depth = depth;
+            {
+                const uint32_t wr = __reduce_add_sync(0xFFFFFFFFu, t_reached), we = __reduce_add_sync(0xFFFFFFFFu, t_edges);
+                if (lane == 0) { atomicAdd(&s_cnt[0], (unsigned long long)wr); atomicAdd(&s_cnt[1], (unsigned long long)we); }
+            }
+            __syncthreads();
+            continue;
+        }
 
         // ---- backward: deepest level first; one thread per vertex, CSR-order sums -----------
         for (uint32_t l = depth; l >= 1; --l) {

@@ -74,6 +74,13 @@ def test_gpu_measures_on_ensembles_and_deep_graphs(ctx, oracle):
         rp, col = e.export_csr()
         assert e.diameter(ctx) == oracle.diameter(rp, col)
         assert np.array_equal(e.closeness_centrality(ctx), oracle.closeness_centrality(rp, col), equal_nan=True)
+    ring = ne.SwEnsemble(4096, 0.0, 1)           # mid engine hands every source back (depth 1024 > 253)
+    rp, col = ring.export_csr()
+    dg = ctx.upload(rp, col)
+    got, want = dg.distance_measures(), oracle.distance_measures(rp, col)
+    assert all(a.tolist() == b.tolist() for a, b in zip(got, want))
+    assert dg.diameter() == 1024
+    dg.free()
     g = ne.gnm_scalable(1 << 15, 1 << 17, 3)
     rp, col = g.export_csr()
     dg = ctx.upload(rp, col)
