@@ -18,7 +18,7 @@ CUDA_DEPS = CUDA_SOURCES + [
     os.path.join(ROOT, "include", "net_ensembles_cuda.h"),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
 
 
 def _nvcc():

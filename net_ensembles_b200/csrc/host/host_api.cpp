@@ -189,24 +189,30 @@ int nech_chains_step_and_load_cuda(void *const *handles, uint32_t n_chains, uint
     return guarded([&]() -> int {
         std::vector<uint32_t> n_per(n_chains);
         std::vector<uint64_t> rp_off(n_chains), col_off(n_chains);
-        uint64_t rp_total = 0, col_total = 0;
-        for (uint32_t g = 0; g < n_chains; ++g) {
+        // chains are independent: step them on all host cores (each chain owns its generator)
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+        for (int64_t g = 0; g < (int64_t)n_chains; ++g) {
             Handle *h = static_cast<Handle *>(handles[g]);
             for (uint64_t k = 0; k < m_steps; ++k) switch (h->kind) {
                 case Kind::ErC: h->erc->m_step(); break;
                 case Kind::ErM: h->erm->m_step(); break;
                 case Kind::Sw: h->sw->m_step(); break;
-                default: g_err = "chain has no Markov step"; return NEC_EINVAL;
+                default: bad += 1; k = m_steps; break;
             }
-            with_graph(h, [&](auto &gr) {
+        }
+        if (bad) { g_err = "chain has no Markov step"; return NEC_EINVAL; }
+        uint64_t rp_total = 0, col_total = 0;
+        for (uint32_t g = 0; g < n_chains; ++g)
+            with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
                 n_per[g] = (uint32_t)gr.vertex_count();
                 rp_off[g] = rp_total; col_off[g] = col_total;
                 rp_total += gr.vertex_count() + 1; col_total += gr.nnz();
                 return 0;
             });
-        }
         std::vector<uint32_t> rp(rp_total), col(col_total ? col_total : 1);
-        for (uint32_t g = 0; g < n_chains; ++g)
+#pragma omp parallel for schedule(static)
+        for (int64_t g = 0; g < (int64_t)n_chains; ++g)
             with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
                 uint32_t *r = rp.data() + rp_off[g];
                 uint32_t *c = col.data() + col_off[g];

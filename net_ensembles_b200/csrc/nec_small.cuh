@@ -39,6 +39,7 @@ struct SmallParams {
     int include_endpoints;
     double *__restrict__ out;
     unsigned long long *counters;   // [0] reached pairs [1] edge pairs [2] visits [3] max depth
+    uint32_t csr_budget;            // bytes of shared memory reserved for a graph's CSR in this launch
 };
 
 // per warp: q f64[n] | bpart f64[n] | dist u32[n] | order u16[n]   (n rounded up to 4)
@@ -46,7 +47,8 @@ __host__ __device__ inline size_t small_warp_bytes(uint32_t n) {
     const size_t np = ((size_t)n + 3) / 4 * 4;
     return np * (8 + 8 + 4 + 2);
 }
-__host__ __device__ inline size_t small_smem_bytes(uint32_t n) { return small_warp_bytes(n) * kSmallWarps; }
+constexpr uint32_t kSmallCsrBytes = 24 * 1024;   // shared-memory budget for a graph's CSR (row_ptr u32 + neighbours u16)
+__host__ __device__ inline size_t small_smem_bytes(uint32_t n, uint32_t csr_budget) { return small_warp_bytes(n) * kSmallWarps + csr_budget; }
 
 __global__ void __launch_bounds__(kSmallThreads)
 small_graph_kernel(const SmallParams p) {
@@ -59,8 +61,20 @@ small_graph_kernel(const SmallParams p) {
     for (uint32_t g = blockIdx.x; g < p.n_graphs; g += gridDim.x) {
         const uint32_t n = p.n_per_graph[g];
         const uint32_t np4 = (n + 3) / 4 * 4;
-        const uint32_t *__restrict__ rp = p.rp + p.rp_off[g];
-        const uint32_t *__restrict__ col = p.col + p.col_off[g];
+        const uint32_t *__restrict__ rp_g = p.rp + p.rp_off[g];
+        const uint32_t *__restrict__ col_g = p.col + p.col_off[g];
+        // stage the graph's CSR in shared memory when it fits (it is read ~2 x n times per graph)
+        uint32_t *s_rp = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSmallWarps * small_warp_bytes(n));
+        uint16_t *s_col = reinterpret_cast<uint16_t *>(s_rp + n + 1);
+        const uint32_t nnz = __ldg(rp_g + n);
+        const bool staged = (size_t)(n + 1) * 4 + (size_t)nnz * 2 <= p.csr_budget;
+        if (staged) {
+            for (uint32_t v = threadIdx.x; v <= n; v += kSmallThreads) s_rp[v] = __ldg(rp_g + v);
+            for (uint32_t e = threadIdx.x; e < nnz; e += kSmallThreads) s_col[e] = (uint16_t)__ldg(col_g + e);
+        }
+        __syncthreads();
+        auto rp_at = [&](uint32_t v) -> uint32_t { return staged ? s_rp[v] : __ldg(rp_g + v); };
+        auto col_at = [&](uint32_t e) -> uint32_t { return staged ? (uint32_t)s_col[e] : __ldg(col_g + e); };
         unsigned char *mine = smem_raw + (size_t)warp * small_warp_bytes(n);
         double *q = reinterpret_cast<double *>(mine);
         double *bpart = q + np4;
@@ -84,22 +98,27 @@ small_graph_kernel(const SmallParams p) {
                     uint32_t rs = 0, deg = 0;
                     if (i < le) {
                         const uint32_t u = order[i];
-                        rs = __ldg(rp + u);
-                        deg = __ldg(rp + u + 1) - rs;
+                        rs = rp_at(u);
+                        deg = rp_at(u + 1) - rs;
                         my_reached += 1;
                         my_edges += deg;
                     }
                     const uint32_t maxdeg = __reduce_max_sync(0xFFFFFFFFu, deg);
-                    for (uint32_t k = 0; k < maxdeg; ++k) {
-                        bool found = false;
-                        uint32_t x = 0;
-                        if (k < deg) {
-                            x = __ldg(col + rs + k);
-                            if (dist[x] == kSmallInf) found = atomicCAS(&dist[x], kSmallInf, level + 1) == kSmallInf;
+                    for (uint32_t k0 = 0; k0 < maxdeg; k0 += 2) {
+                        uint32_t x[2];
+                        bool cand[2], found[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            x[j] = k0 + j < deg ? col_at(rs + k0 + j) : 0u;
+                            cand[j] = k0 + j < deg && dist[x[j]] == kSmallInf;
                         }
-                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found);
-                        if (found) order[tail + __popc(bal & lane_lt)] = (uint16_t)x;
-                        tail += __popc(bal);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            found[j] = cand[j] && atomicCAS(&dist[x[j]], kSmallInf, level + 1) == kSmallInf;
+                            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, found[j]);
+                            if (found[j]) order[tail + __popc(bal & lane_lt)] = (uint16_t)x[j];
+                            tail += __popc(bal);
+                        }
                     }
                 }
                 __syncwarp();
@@ -130,11 +149,19 @@ small_graph_kernel(const SmallParams p) {
                     const uint32_t i = base + lane;
                     if (i < hi) {
                         const uint32_t w = order[i];
-                        const uint32_t rs = __ldg(rp + w), re = __ldg(rp + w + 1);
+                        const uint32_t rs = rp_at(w), re = rp_at(w + 1);
                         double acc = 0.0;
                         uint32_t npred = 0;
-                        for (uint32_t e = rs; e < re; ++e) {          // CSR order: fixes the rounding
-                            const uint32_t x = __ldg(col + e);
+                        uint32_t e = rs;
+                        for (; e + 2 <= re; e += 2) {                  // CSR order: fixes the rounding
+                            const uint32_t x0 = col_at(e), x1 = col_at(e + 1);
+                            const uint32_t d0 = dist[x0], d1 = dist[x1];
+                            const double q0 = d0 == l + 1 ? q[x0] : 0.0, q1 = d1 == l + 1 ? q[x1] : 0.0;
+                            acc += q0; acc += q1;
+                            npred += (d0 == l - 1 ? 1u : 0u) + (d1 == l - 1 ? 1u : 0u);
+                        }
+                        if (e < re) {
+                            const uint32_t x = col_at(e);
                             const uint32_t dx = dist[x];
                             if (dx == l + 1) acc += q[x];
                             npred += (dx == l - 1) ? 1u : 0u;
@@ -190,6 +217,7 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
     // ---- validate + size ------------------------------------------------------------------
     uint64_t rp_total = 0, col_total = 0, out_total = 0;
     uint32_t max_n = 0;
+    size_t max_csr = 0;
     std::vector<uint64_t> out_off(n_graphs);
     for (uint32_t g = 0; g < n_graphs; ++g) {
         const uint32_t n = n_per_graph[g];
@@ -208,6 +236,7 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
         out_off[g] = out_total;
         out_total += n;
         max_n = std::max(max_n, n);
+        max_csr = std::max(max_csr, (size_t)(n + 1) * 4 + (size_t)r[n] * 2);
         stats->n_sources += n;
         stats->n_batches += (n + kLanes - 1) / kLanes;
     }
@@ -239,12 +268,14 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
     if (col_total) cudaMemcpyAsync(d_col, col, col_total * 4, cudaMemcpyHostToDevice, stream);
     cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), stream);
 
-    const size_t smem = small_smem_bytes(max_n);
-    cudaError_t e = cudaFuncSetAttribute(small_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N));
+    const uint32_t csr_budget = (uint32_t)std::min<size_t>((max_csr + 255) / 256 * 256, kSmallCsrBytes);   // larger CSRs are read from L1/L2
+    const size_t smem = small_smem_bytes(max_n, csr_budget);
+    cudaError_t e = cudaFuncSetAttribute(small_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
     if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     SmallParams p{};
     p.n_graphs = n_graphs; p.n_per_graph = d_n; p.rp_off = d_rp_off; p.rp = d_rp; p.col_off = d_col_off; p.col = d_col;
     p.out_off = d_out_off; p.include_endpoints = include_endpoints; p.out = d_out; p.counters = d_cnt;
+    p.csr_budget = csr_budget;
     cudaEventRecord(ev0, stream);
     small_graph_kernel<<<n_graphs, kSmallThreads, smem, stream>>>(p);
     cudaEventRecord(ev1, stream);
