@@ -19,7 +19,6 @@ if len(sys.argv) > 1:
     print("%-8s engine_ms %s -> full-run est %.1f ms  fwd %.3f bwd %.3f" % (sys.argv[1], ["%.2f" % t for t in ts], min(ts) * 4, st["frac_forward"], st["frac_backward"]), flush=True)
 else:
     for rep in range(2):
-        for tag, extra in (("base", {}), ("l2pers", {"NEC_MID_L2_PERSIST": "1", "NEC_MID_VERBOSE": "1"}), ("1cta/sm", {"NEC_MID_CTAS_PER_SM": "1"}),
-                           ("1cta+l2p", {"NEC_MID_CTAS_PER_SM": "1", "NEC_MID_L2_PERSIST": "1"})):
-            env = dict(os.environ, **extra)
+        for tag in ("ab_old", "ab_new"):
+            env = dict(os.environ, NEC_LIB_PATH=os.path.join(ROOT, "net_ensembles_b200", "lib", tag + ".so"))
             subprocess.run([sys.executable, __file__, tag], env=env)
