@@ -15,20 +15,25 @@
 //     dist[v][32] (u8, one 32 B sector per vertex; u32 rows for graphs deeper than 253
 //     levels), q[v][32] (f64, 256 B per vertex), the level queues of (vertex, source-mask)
 //     entries, and a private partial load vector.
-//   * FORWARD pass, bit-parallel, one LANE PER EDGE: a warp takes a tile of 32 queue
-//     entries, flattens their adjacency lists (warp scan + per-lane owner search) and every
-//     lane handles one (u -> x) entry for all 32 sources at once:
-//     new = mask(u) & ~seen[x]; atomicOr(seen[x]) filters races; the truly new bits get their
-//     dist bytes written and are ORed into next[x]; the lane that turns next[x] non-zero
-//     appends x to the next level's queue (warp-aggregated shared-memory tail).
+//   * FORWARD pass, bit-parallel, one LANE PER ADJACENCY ENTRY: a warp takes a tile of 32 queue
+//     entries, writes their distance rows (the entry's source mask is final when it is dequeued:
+//     lane k stores byte k, one store instruction per row), flattens their adjacency lists (warp
+//     scan + per-lane owner search) and every lane handles (u -> x) entries for all 32 sources at
+//     once, four per step, each stage a batch of independent memory operations:
+//     new = mask(u) & ~seen[x]; atomicOr(seen[x]) filters races exactly; the truly new bits are
+//     ORed into next[x]; the lane that turns next[x] non-zero appends x to the next level's queue
+//     (warp-aggregated shared-memory tail).
 //   * BACKWARD pass (pull, atomic-free, deterministic), one LANE PER SOURCE: levels deepest
-//     -> 1 over the same queues, again in tiles of 32 entries with flattened edges so that 8
-//     neighbour rows are in flight per warp.  For entry (w, mask) and neighbour x, lane k
-//     reads dist[x][k] (one coalesced sector per row); lanes with dist == level+1 pull
-//     q[x][k], lanes count dist == level-1 as predecessors; at the end of w's row
-//     bk = 1 + sum, q[w][k] = bk / npred and the lane-sum of bk goes to the slot's private
-//     b[] (exactly one writer per vertex per level => no atomics).  Predecessor lists are
-//     never materialised; sigma never enters the value.
+//     -> 1 over the same queues, again in tiles of 32 entries with flattened adjacency entries
+//     consumed in chunks of 32 through a two-deep pipeline: chunk s+2's neighbour ids are being
+//     loaded, chunk s+1's 32 distance rows (32 B each) are in flight to shared memory (cp.async,
+//     two lanes per row), chunk s is consumed.  For entry (w, mask) and neighbour x, lane k reads
+//     byte k of x's staged row; lanes with dist == level+1 pull q[x][k], lanes count
+//     dist == level-1 as predecessors; at the end of w's row bk = 1 + sum, q[w][k] = bk / npred
+//     and the lane-sum of bk goes to the slot's private b[] (exactly one writer per vertex per
+//     level => no atomics).  Predecessor lists are never materialised; sigma never enters the
+//     value.  kMode 2 runs the forward pass only and reports per-source eccentricity, sum of
+//     distances and reached count (nec_distance_measures).
 //   * slots' private b[] are summed in slot order by reduce_slots_kernel.
 #pragma once
 #include <cuda_runtime.h>
