@@ -350,7 +350,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
         if (v >= 1 && v < occ) occ = v;
     }
     const uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
-    const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 4, 256) / 4;
+    const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
     const size_t np_stride = align_up((size_t)n, 256);
     const size_t need = (q_stride * 8 * 2 + o_stride * 4 * 2 + np_stride) * slots;
     if (need > ctx->mid_bytes) {
@@ -406,7 +406,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->mid_bytes;
     for (uint32_t k = 0; k < n_sources; ++k) {
-        if (status[k] == nec::kMidTooDeep || status[k] == nec::kMidPredOverflow) {
+        if (status[k] == nec::kMidTooDeep || status[k] == nec::kMidPredOverflow || status[k] == nec::kMidQueueOverflow) {
             fallback.push_back(h_sources[k]);
             if (fallback_index) fallback_index->push_back(k);
         }

@@ -9,7 +9,7 @@
 // reproducible run to run.  No predecessor lists, no sigma, no atomics on floating point.
 //
 // Memory placement per CTA (= per in-flight source):
-//   shared : dist[n] u8, claim bitmap n/8 B, level offsets, per-thread slab staging slots
+//   shared : dist[n] u8, level offsets, per-thread slab staging slots (16 B chunks, cp.async targets)
 //   global : q[n] f64      — the randomly read global array; it is written on level l+1 and
 //                            read on level l, so only ~two levels' worth of sectors per CTA has
 //                            to survive in the 126 MB L2
@@ -21,13 +21,19 @@
 //                            after each source (streams through HBM; evict-first hints)
 // Forward (thread per frontier vertex): one slab row (cp.async-staged one step ahead) gives the
 // degree and the first W-1 neighbours; each neighbour's distance byte is read ONCE and classifies
-// it for good — unreached or level+1: successor (claim it via shared-memory atomicOr if
+// it for good — unreached or level+1: successor (claim it, see below, if
 // unreached); level-1: predecessor — because when a level-l vertex is expanded all distances
 // <= l are final and every unreached neighbour is about to become l+1.  The classification
 // (successor mask, predecessor count) is stored per queue position, so the backward pass needs
 // no distance reads at all for slab neighbours and skips the row fetch of BFS leaves.
 // Backward (thread per vertex): bk = 1 + sum of q over the successor bits in CSR order,
 // q = bk / npred.  Then a coalesced sweep adds q[v] * npred[v] to the CTA's partial load.
+// Claims are PLAIN STORES (no shared-memory atomics): every thread that reads a neighbour as unreached
+// stores the new distance and appends it.  Two threads racing for the same vertex inside the few
+// cycles between read and store both append it; such a duplicate queue entry is harmless — expanding
+// it finds nothing new, its classification and its q value are identical, and the load is added per
+// VERTEX by the sweep — and it is rare (a few per cent), whereas the atomics cost ~2 LSU cycles per lane
+// on every claim.  The queue has room for 2n entries; a source that overflows it is handed back.
 // Vertices of degree > kMidHubDeg are expanded by a whole warp (forward: deferred list;
 // backward: lanes over adjacency entries, sum still in CSR order); rows longer than the slab
 // continue in the CSR arrays with distance-based classification.
@@ -45,9 +51,10 @@ constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
 constexpr uint32_t kMidMaxLevel = 253;
+constexpr bool kMidAtomicClaims = false;   // false: plain-store claims, harmless duplicate queue entries (see below)
 constexpr uint32_t kClsRowFlag = 1u << 15;   // cls: bits 0..14 successor mask, bit 15 "row needed anyway", bits 16..31 npred
 
-enum MidStatus : uint8_t { kMidPending = 0, kMidDone = 1, kMidTooDeep = 2, kMidPredOverflow = 3 };
+enum MidStatus : uint8_t { kMidPending = 0, kMidDone = 1, kMidTooDeep = 2, kMidPredOverflow = 3, kMidQueueOverflow = 4 };
 
 struct MidParams {
     uint32_t n, n_pad;                        // n_pad: n rounded up to 16
@@ -58,7 +65,7 @@ struct MidParams {
     uint32_t n_sources;
     int include_endpoints;
     double *q_base;        size_t q_stride;
-    uint32_t *order_base;  size_t order_stride;
+    uint32_t *order_base;  size_t order_stride;   // stride == capacity of the per-CTA queue (>= n)
     uint32_t *cls_base;                       // same stride as order
     double *bslot_base;    size_t bslot_stride;
     uint8_t *np_base;      size_t np_stride;
@@ -72,10 +79,10 @@ struct MidParams {
     unsigned long long *counters;             // [0] reached [1] edge pairs [2] visits [3] max depth [4..6] cycles
 };
 
-// dynamic shared memory: dist | claim bitmap | slab staging (chunk-major: [W/4][threads] x 16 B)
+// dynamic shared memory: dist | (claim bitmap, only with kMidAtomicClaims) | slab staging (chunk-major: [W/4][threads] x 16 B)
 __host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
     const size_t n_pad = ((size_t)n + 15) / 16 * 16;
-    const size_t claim = (((size_t)n + 31) / 32 * 4 + 15) / 16 * 16;
+    const size_t claim = kMidAtomicClaims ? (((size_t)n + 31) / 32 * 4 + 15) / 16 * 16 : 0;
     return n_pad + claim + (size_t)kMidThreads * slab_w * 4;
 }
 
@@ -123,13 +130,16 @@ mid_engine(const MidParams p) {
     const uint32_t n = p.n;
     uint8_t *dist = mid_smem;
     uint32_t *claim = reinterpret_cast<uint32_t *>(dist + p.n_pad);
-    const uint32_t claim_words = (n + 31) / 32;
+    const uint32_t claim_words = kMidAtomicClaims ? (n + 31) / 32 : 0;
     const uint32_t dist_s32 = (uint32_t)__cvta_generic_to_shared(dist);
     const uint32_t claim_s32 = (uint32_t)__cvta_generic_to_shared(claim);
     uint4 *stage = reinterpret_cast<uint4 *>(mid_smem + p.n_pad + (((size_t)claim_words * 4 + 15) / 16 * 16)) + threadIdx.x;
 
     __shared__ uint32_t s_lvl[kMidMaxLevel + 3];
-    __shared__ uint32_t s_tail, s_flag, s_hub_n;
+    __shared__ uint32_t s_tail, s_flag, s_hub_n, s_qfull;
+    __shared__ unsigned long long s_msum;
+    __shared__ uint32_t s_mreach;
+    const uint32_t qcap = (uint32_t)p.order_stride;
     __shared__ uint32_t s_hub[kMidHubCap];
     __shared__ unsigned long long s_cnt[2];
 
@@ -173,17 +183,20 @@ mid_engine(const MidParams p) {
         __syncthreads();
         if (threadIdx.x == 0) {
             dist[s] = 0;
-            claim[s >> 5] = 1u << (s & 31);
+            if (kMidAtomicClaims) claim[s >> 5] = 1u << (s & 31);
             order[0] = s;
-            s_tail = 1; s_flag = 0; s_hub_n = 0;
+            s_tail = 1; s_flag = 0; s_hub_n = 0; s_qfull = 0; s_msum = 0; s_mreach = 0;
         }
         __syncthreads();
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
 
         // ---- forward ---------------------------------------------------------------------
         auto claim_vertex = [&](uint32_t x, uint32_t next_d) -> bool {     // x is known to read as unreached
-            const uint32_t bit = 1u << (x & 31);
-            const bool won = !(atomicOr(&claim[x >> 5], bit) & bit);
+            bool won = true;
+            if (kMidAtomicClaims) {
+                const uint32_t bit = 1u << (x & 31);
+                won = !(atomicOr(&claim[x >> 5], bit) & bit);
+            }
             if (won) dist[x] = (uint8_t)next_d;
             return won;
         };
@@ -198,7 +211,8 @@ mid_engine(const MidParams p) {
                 const int leader = __ffs(bal) - 1;
                 if (lane == leader) base = atomicAdd(&s_tail, (uint32_t)__popc(bal));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (found) __stcs(&order[base + __popc(bal & lane_lt)], x);
+                if (base + __popc(bal) > qcap) { if (lane == leader) s_qfull = 1; }
+                else if (found) __stcs(&order[base + __popc(bal & lane_lt)], x);
             }
         };
 
@@ -206,7 +220,7 @@ mid_engine(const MidParams p) {
         bool too_deep = false;
         for (;;) {
             __syncthreads();
-            const uint32_t tail_now = s_tail;
+            const uint32_t tail_now = min(s_tail, qcap);
             const uint32_t hubs = min(s_hub_n, (uint32_t)kMidHubCap);
             __syncthreads();
             // hubs deferred by the level that just ran belong to `level - 1`: expand them now,
@@ -255,8 +269,6 @@ mid_engine(const MidParams p) {
                 uint32_t deg = 0, cls = 0;
                 if (u != kNone) {
                     deg = row[0];
-                    t_reached += 1;
-                    t_edges += deg;
                     if (deg > kSlabNbrs) cls = kClsRowFlag;
                     if (deg > kMidHubDeg) {
                         const uint32_t pos = atomicAdd(&s_hub_n, 1u);
@@ -272,9 +284,12 @@ mid_engine(const MidParams p) {
                     const uint32_t x = row[k];
                     const uint32_t d = lds_u8_if(valid, dist_s32 + x, 0xFFFFu);
                     const bool unreached = d == 0xFFu;
-                    const uint32_t bit = 1u << (x & 31);
-                    const uint32_t old = atoms_or_if(unreached, claim_s32 + ((x >> 5) << 2), bit);   // ~0 if not executed
-                    const bool mine = !(old & bit);
+                    bool mine = unreached;
+                    if (kMidAtomicClaims) {
+                        const uint32_t bit = 1u << (x & 31);
+                        const uint32_t old = atoms_or_if(unreached, claim_s32 + ((x >> 5) << 2), bit);   // ~0 if not executed
+                        mine = !(old & bit);
+                    }
                     sts_u8_if(mine, dist_s32 + x, next_d);
                     won |= (mine ? 1u : 0u) << k;
                     cls |= ((unreached || d == next_d) ? 1u : 0u) << (k - 1);
@@ -288,10 +303,15 @@ mid_engine(const MidParams p) {
                     if (total) {
                         uint32_t base = 0;
                         if (lane == 31) base = atomicAdd(&s_tail, total);
-                        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+                        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+                        if (base + total > qcap) {
+                            if (lane == 31) s_qfull = 1;
+                        } else {
+                            base += incl - cnt;
 #pragma unroll
-                        for (int k = 1; k < W; ++k)
-                            if ((won >> k) & 1u) __stcs(&order[base++], row[k]);
+                            for (int k = 1; k < W; ++k)
+                                if ((won >> k) & 1u) __stcs(&order[base++], row[k]);
+                        }
                     }
                 }
                 // rows longer than the slab continue in the CSR arrays
@@ -312,26 +332,37 @@ mid_engine(const MidParams p) {
             ++level;
         }
         __syncthreads();
-        if (too_deep) {
-            if (threadIdx.x == 0) p.source_status[si] = kMidTooDeep;
+        if (too_deep || s_qfull) {
+            if (threadIdx.x == 0) p.source_status[si] = too_deep ? kMidTooDeep : kMidQueueOverflow;
+            __syncthreads();
             continue;
         }
         const uint32_t depth = level - 1;
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
         if (p.measure_only) {
-            if (threadIdx.x == 0) {
-                unsigned long long sum = 0;
-                for (uint32_t l = 1; l <= depth; ++l) sum += (unsigned long long)l * (s_lvl[l + 1] - s_lvl[l]);
-                if (p.out_ecc) p.out_ecc[si] = depth;
-                if (p.out_sumdist) p.out_sumdist[si] = sum;
-                if (p.out_reached) p.out_reached[si] = s_lvl[depth + 1];
-                p.source_status[si] = kMidDone;
+            // exact per-vertex sums from the distance vector (queue entries may contain duplicates)
+            unsigned long long sum = 0;
+            uint32_t cnt = 0;
+            for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
+                const uint32_t d = dist[v];
+                if (d != 0xFFu) { sum += d; cnt += 1; t_edges += __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v); }
             }
-            if (depth > my_depth) my_depth = depth;
+            t_reached = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); }
+            if (lane == 0) { atomicAdd(&s_msum, sum); atomicAdd(&s_mreach, cnt); }
             {
                 const uint32_t wr = __reduce_add_sync(0xFFFFFFFFu, t_reached), we = __reduce_add_sync(0xFFFFFFFFu, t_edges);
                 if (lane == 0) { atomicAdd(&s_cnt[0], (unsigned long long)wr); atomicAdd(&s_cnt[1], (unsigned long long)we); }
             }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (p.out_ecc) p.out_ecc[si] = depth;
+                if (p.out_sumdist) p.out_sumdist[si] = s_msum;
+                if (p.out_reached) p.out_reached[si] = s_mreach;
+                p.source_status[si] = kMidDone;
+            }
+            if (depth > my_depth) my_depth = depth;
             __syncthreads();
             continue;
         }
@@ -437,9 +468,13 @@ mid_engine(const MidParams p) {
             const double sub = p.include_endpoints ? 0.0 : 1.0;
             for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
                 const uint32_t d = dist[v];
-                if (d != 0xFFu && d != 0u) {
-                    const double bk = q[v] * (double)npv[v];
-                    __stcs(&bslot[v], __ldcs(&bslot[v]) + (bk - sub));
+                if (d != 0xFFu) {
+                    t_reached += 1;                                   // exact (the queue may hold duplicates)
+                    t_edges += __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
+                    if (d != 0u) {
+                        const double bk = q[v] * (double)npv[v];
+                        __stcs(&bslot[v], __ldcs(&bslot[v]) + (bk - sub));
+                    }
                 }
             }
         }
