@@ -351,8 +351,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     }
     const uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
     const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
-    const size_t np_stride = align_up((size_t)n, 256);
-    const size_t need = (q_stride * 8 * 2 + o_stride * 4 * 2 + np_stride) * slots;
+    const size_t need = (q_stride * 8 * 2 + o_stride * 4 * 4) * slots;
     if (need > ctx->mid_bytes) {
         if (ctx->mid_base) cudaFree(ctx->mid_base);
         ctx->mid_base = nullptr; ctx->mid_bytes = 0;
@@ -367,7 +366,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     double *d_bslot = d_q + q_stride * slots;
     uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
     uint32_t *d_cls = d_order + o_stride * slots;
-    uint8_t *d_np = (uint8_t *)(d_cls + o_stride * slots);
+    uint32_t *d_succ = d_cls + o_stride * slots;          // 2 * o_stride per slot
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, n_sources, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -376,9 +375,8 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab;
     p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
-    p.cls_base = d_cls;
+    p.cls_base = d_cls; p.succ_base = d_succ;
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
-    p.np_base = d_np; p.np_stride = np_stride;
     p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
     if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

@@ -50,7 +50,8 @@ constexpr uint32_t kMidMaxN = 180000;     // 1.125 B/vertex of shared memory + s
 constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
-constexpr uint32_t kMidMaxLevel = 253;
+constexpr uint32_t kMidMaxLevel = 126;    // distance bytes < 0x80; the backward pass overwrites them with a 'finished' mark
+constexpr uint32_t kMidMaxPred = 62;      // finished mark = 0x80 | (level parity << 6) | npred  (0xFF stays 'unreached')
 constexpr bool kMidAtomicClaims = false;   // false: plain-store claims, harmless duplicate queue entries (see below)
 constexpr uint32_t kClsRowFlag = 1u << 15;   // cls: bits 0..14 successor mask, bit 15 "row needed anyway", bits 16..31 npred
 
@@ -67,8 +68,8 @@ struct MidParams {
     double *q_base;        size_t q_stride;
     uint32_t *order_base;  size_t order_stride;   // stride == capacity of the per-CTA queue (>= n)
     uint32_t *cls_base;                       // same stride as order
+    uint32_t *succ_base;                      // 2 x order_stride: first and second BFS successor per queue position
     double *bslot_base;    size_t bslot_stride;
-    uint8_t *np_base;      size_t np_stride;
     // measure_only != 0: forward pass only; per source index eccentricity / sum of distances / reached
     // count (nec_distance_measures) — they fall out of the level offsets, no extra traversal work
     int measure_only;
@@ -147,7 +148,8 @@ mid_engine(const MidParams p) {
     uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
     uint32_t *__restrict__ clsq = p.cls_base + (size_t)blockIdx.x * p.order_stride;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
-    uint8_t *__restrict__ npv = p.np_base + (size_t)blockIdx.x * p.np_stride;
+    uint32_t *__restrict__ succ0 = p.succ_base + (size_t)blockIdx.x * 2 * p.order_stride;
+    uint32_t *__restrict__ succ1 = succ0 + p.order_stride;
 
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
@@ -277,13 +279,17 @@ mid_engine(const MidParams p) {
                 }
                 // read each slab neighbour's distance once: classify it, claim it if unreached.
                 // Branch-free (predicated shared-memory PTX): lanes differ per slot, branches would serialise.
-                uint32_t won = 0;
+                uint32_t won = 0, s0 = 0, s1 = 0, nsucc = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
                     const bool valid = (uint32_t)(k - 1) < deg;
                     const uint32_t x = row[k];
                     const uint32_t d = lds_u8_if(valid, dist_s32 + x, 0xFFFFu);
                     const bool unreached = d == 0xFFu;
+                    const bool is_succ = unreached || d == next_d;
+                    s1 = (is_succ && nsucc == 1) ? x : s1;
+                    s0 = (is_succ && nsucc == 0) ? x : s0;
+                    nsucc += is_succ ? 1u : 0u;
                     bool mine = unreached;
                     if (kMidAtomicClaims) {
                         const uint32_t bit = 1u << (x & 31);
@@ -292,10 +298,10 @@ mid_engine(const MidParams p) {
                     }
                     sts_u8_if(mine, dist_s32 + x, next_d);
                     won |= (mine ? 1u : 0u) << k;
-                    cls |= ((unreached || d == next_d) ? 1u : 0u) << (k - 1);
+                    cls |= (is_succ ? 1u : 0u) << (k - 1);
                     cls += (d == pred_d ? 1u : 0u) << 16;
                 }
-                if (u != kNone) __stcs(&clsq[i], cls);
+                if (u != kNone) { __stcs(&clsq[i], cls); __stcs(&succ0[i], s0); __stcs(&succ1[i], s1); }
                 {   // append everything this warp found with ONE tail update
                     const uint32_t cnt = __popc(won);
                     const uint32_t incl = warp_inclusive_scan(cnt, lane);
@@ -368,60 +374,90 @@ mid_engine(const MidParams p) {
         }
 
         // ---- backward: deepest level first; one thread per vertex, CSR-order sums -----------
+        // Everything a vertex needs was recorded per queue position by the forward pass: cls (successor
+        // mask, npred) and its first two successors.  The four streams are read coalesced, one step
+        // ahead; only the q pulls are random.  Vertices with > 2 successors, rows longer than the slab
+        // and hubs (rare) read the slab row / CSR and classify by distance byte: a finished vertex
+        // carries 0x80 | (its level's parity << 6) | npred; a neighbour of a level-l vertex is a
+        // successor <=> it is finished with the parity of l+1 (finished same-level neighbours carry l's).
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t b0 = s_lvl[l], b1 = s_lvl[l + 1];
-            const uint32_t d_succ = l + 1, d_pred = l - 1;
+            const uint32_t d_pred = l - 1;
+            const uint32_t succ_tag = 0x80u | (((l + 1) & 1u) << 6), mark_tag = 0x80u | ((l & 1u) << 6);
+            auto is_successor_byte = [&](uint32_t b) { return (b & 0xC0u) == succ_tag && b != 0xFFu; };
             const long long t_lvl = clock64();
-            // pipeline: (vertex, cls) two steps ahead loading, slab row one step ahead in flight —
-            // and only for vertices that have successors (BFS leaves need no row at all)
+            // two-deep software pipeline: step t+2's four words are being loaded, step t+1's q pulls are
+            // in flight, step t is consumed
             uint32_t i = b0 + threadIdx.x;
-            uint32_t v_cur = kNone, c_cur = 0, v_nxt = kNone, c_nxt = 0;
-            if (i < b1) { v_cur = __ldcs(&order[i]); c_cur = __ldcs(&clsq[i]); }
-            if (i + kStride < b1) { v_nxt = __ldcs(&order[i + kStride]); c_nxt = __ldcs(&clsq[i + kStride]); }
-            if (v_cur != kNone && (c_cur & 0xFFFFu)) slab_prefetch<W>(stage, p.slab, v_cur);
-            cp_async_commit();
+            uint32_t v_c = kNone, c_c = 0, v_n = kNone, c_n = 0, a_n = 0, b_n = 0;
+            double q0_c = 0.0, q1_c = 0.0;
+            if (i < b1) {
+                v_c = __ldcs(&order[i]); c_c = __ldcs(&clsq[i]);
+                const uint32_t a = __ldcs(&succ0[i]), b = __ldcs(&succ1[i]);
+                const uint32_t ns = __popc(c_c & 0x7FFFu);
+                if (ns >= 1) q0_c = q[a];
+                if (ns >= 2) q1_c = q[b];
+            }
+            if (i + kStride < b1) {
+                v_n = __ldcs(&order[i + kStride]); c_n = __ldcs(&clsq[i + kStride]);
+                a_n = __ldcs(&succ0[i + kStride]); b_n = __ldcs(&succ1[i + kStride]);
+            }
             for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kStride, i += kStride) {
-                uint32_t row[W];
-                const uint32_t w = v_cur, cls = c_cur;
-                const bool has_row = w != kNone && (cls & 0xFFFFu);
-                cp_async_wait_all();
-                read_stage(row, has_row);
-                uint32_t v_nn = kNone, c_nn = 0;
-                if (i + 2 * kStride < b1) { v_nn = __ldcs(&order[i + 2 * kStride]); c_nn = __ldcs(&clsq[i + 2 * kStride]); }
-                if (v_nxt != kNone && (c_nxt & 0xFFFFu) && landed(row)) slab_prefetch<W>(stage, p.slab, v_nxt);
-                cp_async_commit();
-                v_cur = v_nxt; c_cur = c_nxt; v_nxt = v_nn; c_nxt = c_nn;
-
-                const uint32_t deg = has_row ? row[0] : 0u;
-                const bool hub = deg > kMidHubDeg;
-                double acc = 0.0;
+                const uint32_t w = v_c, cls = c_c;
+                const double q0 = q0_c, q1 = q1_c;
+                // issue step t+1's pulls, then step t+2's loads
+                v_c = v_n; c_c = c_n; q0_c = 0.0; q1_c = 0.0;
+                {
+                    const uint32_t ns = __popc(c_n & 0x7FFFu);
+                    if (ns >= 1) q0_c = q[a_n];
+                    if (ns >= 2) q1_c = q[b_n];
+                }
+                v_n = kNone; c_n = 0;
+                if (i + 2 * kStride < b1) {
+                    v_n = __ldcs(&order[i + 2 * kStride]); c_n = __ldcs(&clsq[i + 2 * kStride]);
+                    a_n = __ldcs(&succ0[i + 2 * kStride]); b_n = __ldcs(&succ1[i + 2 * kStride]);
+                }
+                const uint32_t smask = cls & 0x7FFFu;
+                const uint32_t nsucc = __popc(smask);
+                double acc = q0 + q1;                                          // successors in CSR order
                 uint32_t np = cls >> 16;
-                uint32_t rs = 0;
-                if (deg > kSlabNbrs) rs = __ldg(p.row_ptr + w);
-                if (!hub) {
-                    double qv[W - 1];
+                uint32_t deg = 0, rs = 0;
+                bool hub = false;
+                if (nsucc > 2 || (cls & kClsRowFlag)) {                        // rare: the row itself is needed
+                    uint32_t row[W];
 #pragma unroll
-                    for (int k = 1; k < W; ++k) qv[k - 1] = ((cls >> (k - 1)) & 1u) ? q[row[k]] : 0.0;
+                    for (int k = 0; k < W / 4; ++k) {
+                        const uint4 t = __ldg(p.slab + (size_t)w * (W / 4) + k);
+                        row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
+                    }
+                    uint32_t rest = smask;
+                    rest &= rest - 1; rest &= rest - 1;                        // beyond the first two successors
 #pragma unroll
-                    for (int k = 1; k < W; ++k) acc += qv[k - 1];                  // CSR order
-                    if (deg > kSlabNbrs) {
-                        for (uint32_t k0 = kSlabNbrs; k0 < deg; k0 += 4) {
-                            uint32_t xs[4], dy[4];
-                            double qy[4];
+                    for (int k = 1; k < W; ++k)
+                        if ((rest >> (k - 1)) & 1u) acc += q[row[k]];
+                    if (cls & kClsRowFlag) {
+                        deg = row[0];
+                        hub = deg > kMidHubDeg;
+                        rs = __ldg(p.row_ptr + w);
+                        if (!hub) {
+                            for (uint32_t k0 = kSlabNbrs; k0 < deg; k0 += 4) {
+                                uint32_t xs[4], dy[4];
+                                double qy[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : kNone;
+                                for (int j = 0; j < 4; ++j) xs[j] = (k0 + j < deg) ? __ldg(p.col_idx + rs + k0 + j) : kNone;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dy[j] = xs[j] != kNone ? (uint32_t)dist[xs[j]] : 0xFFFFu;
+                                for (int j = 0; j < 4; ++j) dy[j] = xs[j] != kNone ? (uint32_t)dist[xs[j]] : 0xFFu;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) qy[j] = dy[j] == d_succ ? q[xs[j]] : 0.0;
+                                for (int j = 0; j < 4; ++j) qy[j] = is_successor_byte(dy[j]) ? q[xs[j]] : 0.0;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) { acc += qy[j]; np += dy[j] == d_pred ? 1u : 0u; }
+                                for (int j = 0; j < 4; ++j) { acc += qy[j]; np += dy[j] == d_pred ? 1u : 0u; }
+                            }
                         }
                     }
                 }
-                // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum
-                // over each 32-entry chunk is taken lane by lane so the order is still CSR order.
-                // Hubs ignore cls (the forward pass defers them before classifying).
+                // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum over
+                // each 32-entry chunk is taken lane by lane so the order is still CSR order.  Hubs ignore
+                // cls (the forward pass defers them before classifying).
                 uint32_t hub_mask = __ballot_sync(0xFFFFFFFFu, hub);
                 while (hub_mask) {
                     const int owner = __ffs(hub_mask) - 1;
@@ -436,7 +472,7 @@ mid_engine(const MidParams p) {
                         if (e0 + lane < h_deg) {
                             const uint32_t x = __ldg(p.col_idx + h_rs + e0 + lane);
                             const uint32_t dxx = dist[x];
-                            if (dxx == d_succ) v = q[x];
+                            if (is_successor_byte(dxx)) v = q[x];
                             is_pred = dxx == d_pred;
                         }
                         h_np += __popc(__ballot_sync(0xFFFFFFFFu, is_pred));
@@ -449,11 +485,10 @@ mid_engine(const MidParams p) {
                 if (w != kNone) {
                     const double bk = 1.0 + acc;
                     q[w] = bk / (double)np;
-                    if (np > 255u) s_flag = 1;
-                    npv[w] = (uint8_t)np;
+                    if (np > kMidMaxPred) s_flag = 1;
+                    dist[w] = (uint8_t)(mark_tag | (np & 0x3Fu));           // finished: the sweep reads npred from here
                 }
             }
-            cp_async_wait_all();
             if (threadIdx.x == 0 && b1 - b0 <= kStride) cyc_small += clock64() - t_lvl;
             __syncthreads();
         }
@@ -472,7 +507,7 @@ mid_engine(const MidParams p) {
                     t_reached += 1;                                   // exact (the queue may hold duplicates)
                     t_edges += __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
                     if (d != 0u) {
-                        const double bk = q[v] * (double)npv[v];
+                        const double bk = q[v] * (double)(d & 0x3Fu);           // finished mark carries npred
                         __stcs(&bslot[v], __ldcs(&bslot[v]) + (bk - sub));
                     }
                 }
