@@ -349,7 +349,11 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
         const int v = atoi(env);
         if (v >= 1 && v < occ) occ = v;
     }
-    const uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
+    uint32_t slots = std::min<uint32_t>(n_sources, (uint32_t)(occ * ctx->prop.multiProcessorCount));
+    if (const char *env = getenv("NEC_MID_SLOTS")) {             // profiling knob: total resident CTAs
+        const int v = atoi(env);
+        if (v >= 1 && (uint32_t)v < slots) slots = (uint32_t)v;
+    }
     const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
     const size_t need = (q_stride * 8 * 2 + o_stride * 4 * 4) * slots;
     if (need > ctx->mid_bytes) {
