@@ -225,12 +225,6 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
             return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: graph " + std::to_string(g) + " has n=" + std::to_string(n) +
                                                    " (allowed 1.." + std::to_string(NEC_BATCH_MAX_N) + "; use nec_vertex_load for larger graphs)");
         const uint32_t *r = rp + rp_off[g];
-        if (r[0] != 0) return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: local row_ptr must start at 0 (graph " + std::to_string(g) + ")");
-        for (uint32_t v = 0; v < n; ++v)
-            if (r[v + 1] < r[v]) return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: row_ptr not monotone (graph " + std::to_string(g) + ")");
-        const uint32_t *c = col + col_off[g];
-        for (uint32_t e = 0; e < r[n]; ++e)
-            if (c[e] >= n) return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: neighbour id out of range (graph " + std::to_string(g) + ")");
         rp_total = std::max<uint64_t>(rp_total, rp_off[g] + n + 1);
         col_total = std::max<uint64_t>(col_total, col_off[g] + r[n]);
         out_off[g] = out_total;
@@ -240,6 +234,27 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t 
         stats->n_sources += n;
         stats->n_batches += (n + kLanes - 1) / kLanes;
     }
+    // structural validation of every graph, on all host cores (graphs are independent)
+    int bad_graph = -1, bad_kind = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < (int64_t)n_graphs; ++g) {
+        const uint32_t n = n_per_graph[g];
+        const uint32_t *r = rp + rp_off[g];
+        const uint32_t *c = col + col_off[g];
+        int kind = r[0] != 0 ? 1 : 0;
+        for (uint32_t v = 0; v < n && !kind; ++v)
+            if (r[v + 1] < r[v]) kind = 2;
+        for (uint32_t e = 0; !kind && e < r[n]; ++e)
+            if (c[e] >= n) kind = 3;
+        if (kind) {
+#pragma omp critical
+            { if (bad_graph < 0 || g < bad_graph) { bad_graph = (int)g; bad_kind = kind; } }
+        }
+    }
+    if (bad_graph >= 0)
+        return small_fail(err, NEC_EINVAL, std::string("nec_vertex_load_batch: ") +
+                                               (bad_kind == 1 ? "local row_ptr must start at 0" : bad_kind == 2 ? "row_ptr not monotone" : "neighbour id out of range") +
+                                               " (graph " + std::to_string(bad_graph) + ")");
     // ---- device staging: one arena -----------------------------------------------------------
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t b_n = up((size_t)n_graphs * 4), b_off = up((size_t)n_graphs * 8);
