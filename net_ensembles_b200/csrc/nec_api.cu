@@ -68,6 +68,7 @@ struct nec_ctx {
     uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
     bool mid_attr_set = false;
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
+    bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
     nec::SmallWorkspace small;
     nec_stats stats{};
 };
@@ -163,6 +164,19 @@ struct MeasureOut {                  // device outputs of the distance-measure m
     uint32_t *reached;
 };
 
+template <typename DistT, int kMode, int kThreads>
+int launch_engine_t(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots) {
+    constexpr size_t smem = nec::engine_smem_bytes<DistT, kThreads>();
+    static bool attr_done = false;                      // per instantiation
+    if (!attr_done && smem > 48 * 1024) {
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::vertex_load_engine<DistT, kMode, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    nec::vertex_load_engine<DistT, kMode, kThreads><<<slots, kThreads, smem, ctx->stream>>>(p);
+    NEC_CUDA(ctx, cudaGetLastError());
+    return NEC_OK;
+}
+
 template <typename DistT, int kMode>
 int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
                   uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk,
@@ -182,16 +196,16 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
     if (mo) { p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
-    nec::vertex_load_engine<DistT, kMode><<<slots, nec::kEngineThreads, 0, ctx->stream>>>(p);
-    NEC_CUDA(ctx, cudaGetLastError());
+    const int rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512>(ctx, p, slots);
+    if (rc != NEC_OK) return rc;
     ctx->stats.kernel_launches++;
     return NEC_OK;
 }
 
 int engine_occupancy(nec_ctx *ctx) {
     int o8 = 0, o32 = 0;
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, 0>, nec::kEngineThreads, 0));
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0>, nec::kEngineThreads, 0));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, 0, 512>, 512, nec::engine_smem_bytes<uint8_t, 512>()));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0, 512>, 512, nec::engine_smem_bytes<uint32_t, 512>()));
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
     return NEC_OK;
@@ -223,10 +237,16 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
     // ---- pass 1: 8-bit distances -----------------------------------------------------
-    uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)(ctx->occ_u8 * ctx->prop.multiProcessorCount));
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)ctx->occ_u8 * sms);
     if (debug) want = 1;
     if ((rc = ensure_arena(ctx, n, 1, want)) != NEC_OK) return rc;
     uint32_t slots = std::min<uint32_t>(want, ctx->arena.n_slots);
+    // memory allows fewer than ~1.5 slots per SM although there is work for more: use 1024-thread CTAs,
+    // one per SM, so that every SM still runs 32 warps
+    ctx->wide_ctas = !debug && n_batches > slots && slots < sms + sms / 2;
+    if (getenv("NEC_BATCHED_WIDE")) ctx->wide_ctas = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
+    if (ctx->wide_ctas) slots = std::min<uint32_t>(slots, sms);
     const Arena &a = ctx->arena;
     NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * sizeof(uint32_t) * slots, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
@@ -277,6 +297,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         cudaMemcpyAsync(ctx->d_worklist, deep.data(), deep.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
         uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
         if (debug) want2 = 1;
+        ctx->wide_ctas = false;
         cudaStreamSynchronize(ctx->stream);  // arena may be reallocated below
         if ((rc = ensure_arena(ctx, n, 4, want2)) != NEC_OK) { cudaFree(d_keep); return rc; }
         const Arena &w = ctx->arena;

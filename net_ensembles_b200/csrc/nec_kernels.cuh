@@ -42,8 +42,8 @@
 namespace nec {
 
 constexpr int kLanes = 32;            // sources per batch
-constexpr int kEngineThreads = 512;   // 16 warps per CTA
-constexpr int kEngineMinBlocks = 2;   // CTAs per SM the register budget is sized for
+// CTA shape: 512 threads x 2 CTAs per SM when the workspace budget allows two slots per SM, else
+// 1024 threads x 1 CTA per SM (large graphs are slot-limited by memory; wider CTAs keep the SMs busy)
 constexpr int kUnroll = 8;            // neighbour rows in flight per warp step (backward)
 constexpr int kFwdUnroll = 4;         // flattened adjacency entries per lane and step (forward)
 
@@ -125,8 +125,13 @@ __device__ __forceinline__ int tile_owner(uint32_t incl, uint32_t t) {
 // kMode 0: vertex_load; 1: vertex_load + per-(vertex,lane) debug planes (nec_bfs_debug);
 // 2: distance measures only — the forward pass alone, per source eccentricity / sum of distances /
 //    reached count (diameter, closeness_centrality: reference generic_graph.rs:1116-1144, :1387-1403).
-template <typename DistT, int kMode>
-__global__ void __launch_bounds__(kEngineThreads, kEngineMinBlocks)
+template <typename DistT, int kThreads>
+constexpr size_t engine_smem_bytes() {
+    return (size_t)(kThreads / 32) * (2 * 32 * sizeof(uint2) + (sizeof(DistT) == 1 ? 2 * 32 * 32 : 0));
+}
+
+template <typename DistT, int kMode, int kEngineThreads>
+__global__ void __launch_bounds__(kEngineThreads, kEngineThreads == 512 ? 2 : 1)
 vertex_load_engine(const EngineParams p) {
     constexpr bool kDebug = kMode == 1;
     constexpr bool kMeasure = kMode == 2;
@@ -154,8 +159,10 @@ vertex_load_engine(const EngineParams p) {
     __shared__ uint32_t s_mreach[kLanes], s_mecc[kLanes];
     __shared__ unsigned long long s_cnt[3];
     constexpr bool kStageRows = sizeof(DistT) == 1;      // 32 B distance rows are staged through shared memory
-    __shared__ uint2 s_stage[kWarps][2][32];             // backward: (neighbour, owner's source mask) per flattened entry
-    __shared__ __align__(16) unsigned char s_rows[kStageRows ? kWarps : 1][2][32][32];   // backward: staged distance rows
+    extern __shared__ __align__(16) unsigned char engine_smem[];
+    // backward: (neighbour, owner's source mask) per flattened entry; staged distance rows
+    uint2 (*s_stage)[2][32] = reinterpret_cast<uint2 (*)[2][32]>(engine_smem);
+    unsigned char (*s_rows)[2][32][32] = reinterpret_cast<unsigned char (*)[2][32][32]>(engine_smem + (size_t)kWarps * 2 * 32 * sizeof(uint2));
 
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
