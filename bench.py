@@ -242,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
     n, nnz = len(rp) - 1, len(col)
     sample = args.sources
     if sample is None and args.workload in ("erm2p20", "ba2p22"):
-        sample = 6144 * world if args.workload == "erm2p20" else 1984 * world   # fills the memory-limited slots of one GPU
+        sample = 9472 * world if args.workload == "erm2p20" else 3072 * world   # two batches per CTA / one per memory-limited slot
     sources = step_sources(args.workload, n, sample)
     mine = sources[shard_sources(len(sources), rank, world)]
 

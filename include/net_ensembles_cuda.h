@@ -70,7 +70,7 @@ const char *nec_last_error(const nec_ctx *ctx);
 int nec_set_stream(nec_ctx *ctx, void *cuda_stream);
 
 /* Cap the scratch arena (bytes of HBM the engine may use for per-batch state);
- * 0 restores the default (60 % of free device memory at first use). */
+ * 0 restores the default (80 % of free device memory at first use). */
 int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
 /* Engine selection (tests and profiling; the default 0 chooses by graph size):

@@ -122,7 +122,7 @@ int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_sl
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     size_t free_b = 0, total_b = 0;
     NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + a.bytes) * 0.6);
+    size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + a.bytes) * 0.8);
     // queue capacity: every vertex can sit on at most 32 distinct levels of one batch
     size_t qcap = (size_t)n * nec::kLanes + nec::kLanes;
     uint32_t slots = want_slots;
@@ -130,8 +130,8 @@ int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_sl
     if (ps * slots > budget) {
         // prefer keeping one slot per SM; shrink the queue bound (overflow is detected) first
         const uint32_t floor_slots = std::min<uint32_t>(slots, (uint32_t)ctx->prop.multiProcessorCount);
-        while (ps * floor_slots > budget && qcap > (size_t)n * 16 + nec::kLanes) {
-            qcap = std::max((size_t)n * 16 + nec::kLanes, qcap / 2);
+        while (ps * floor_slots > budget && qcap > (size_t)n * 8 + nec::kLanes) {
+            qcap = std::max((size_t)n * 8 + nec::kLanes, qcap / 2);
             ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
         }
         slots = (uint32_t)std::min<size_t>(slots, budget / ps);
@@ -242,9 +242,10 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     if (debug) want = 1;
     if ((rc = ensure_arena(ctx, n, 1, want)) != NEC_OK) return rc;
     uint32_t slots = std::min<uint32_t>(want, ctx->arena.n_slots);
-    // memory allows fewer than ~1.5 slots per SM although there is work for more: use 1024-thread CTAs,
-    // one per SM, so that every SM still runs 32 warps
-    ctx->wide_ctas = !debug && n_batches > slots && slots < sms + sms / 2;
+    // large graphs (beyond the mid engine) and memory-limited slot counts: 1024-thread CTAs, one per SM.
+    // Same 32 warps per SM as 2 x 512, but half the resident slots (less HBM state in flight, smaller
+    // level-boundary imbalance): 1.3x faster on the N = 2^20 graph in a same-box A/B.
+    ctx->wide_ctas = !debug && (n > nec::kMidMaxN || (n_batches > slots && slots < sms + sms / 2));
     if (getenv("NEC_BATCHED_WIDE")) ctx->wide_ctas = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
     if (ctx->wide_ctas) slots = std::min<uint32_t>(slots, sms);
     const Arena &a = ctx->arena;
