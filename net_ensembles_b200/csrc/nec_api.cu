@@ -460,7 +460,7 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     std::vector<uint32_t> fallback;
     int rc = run_sources_mid(ctx, g, h_sources, n_sources, include_endpoints, d_out, fallback);
     if (rc != NEC_OK || fallback.empty()) return rc;
-    // the few sources the mid engine could not encode (depth > 253 or > 255 predecessors)
+    // the few sources the mid engine could not encode (depth > 126, > 62 predecessors, queue overflow)
     const nec_stats first = ctx->stats;
     double *d_tmp = nullptr;
     NEC_CUDA(ctx, cudaMalloc((void **)&d_tmp, (size_t)g->n * sizeof(double)));
@@ -738,7 +738,7 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     if (mid_ok) {
         std::vector<uint32_t> fb, fb_index;
         rc = run_sources_mid(ctx, g, sources, n_sources, 1, nullptr, fb, &mo, &fb_index);
-        if (rc == NEC_OK && !fb.empty()) {       // sources deeper than 253 levels: batched engine (32-bit distances), scattered back
+        if (rc == NEC_OK && !fb.empty()) {       // sources deeper than 126 levels: batched engine, scattered back
             const nec_stats first = ctx->stats;
             MeasureOut part{};
             const size_t k = fb.size();

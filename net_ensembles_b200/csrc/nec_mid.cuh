@@ -16,7 +16,7 @@
 //            order[n] u32  — BFS order = the level queues; written/read as a stream
 //            cls[n] u32    — per queue position: which slab neighbours are BFS successors and how
 //                            many neighbours are predecessors (see below); streamed
-//            npred[n] u8   — written once per vertex (backward), read by the sweep
+//            succ0/succ1   — per queue position: the vertex's first two BFS successors; streamed
 //            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
 //                            after each source (streams through HBM; evict-first hints)
 // Forward (thread per frontier vertex): one slab row (cp.async-staged one step ahead) gives the
@@ -26,8 +26,10 @@
 // <= l are final and every unreached neighbour is about to become l+1.  The classification
 // (successor mask, predecessor count) is stored per queue position, so the backward pass needs
 // no distance reads at all for slab neighbours and skips the row fetch of BFS leaves.
-// Backward (thread per vertex): bk = 1 + sum of q over the successor bits in CSR order,
-// q = bk / npred.  Then a coalesced sweep adds q[v] * npred[v] to the CTA's partial load.
+// Backward (thread per vertex): bk = 1 + sum of q over the successors in CSR order (the first two
+// come from the per-position successor slots, so most vertices need no row at all), q = bk / npred; the
+// vertex's distance byte is overwritten with a 'finished' mark that carries npred.  Then a coalesced
+// sweep adds q[v] * npred[v] to the CTA's partial load.
 // Claims are PLAIN STORES (no shared-memory atomics): every thread that reads a neighbour as unreached
 // stores the new distance and appends it.  Two threads racing for the same vertex inside the few
 // cycles between read and store both append it; such a duplicate queue entry is harmless — expanding
@@ -37,7 +39,8 @@
 // Vertices of degree > kMidHubDeg are expanded by a whole warp (forward: deferred list;
 // backward: lanes over adjacency entries, sum still in CSR order); rows longer than the slab
 // continue in the CSR arrays with distance-based classification.
-// Sources whose BFS is deeper than 253 levels or that meet a vertex with > 255 predecessors
+// Sources whose BFS is deeper than 126 levels, that meet a vertex with > 62 predecessors or whose queue
+// (2n entries) overflows
 // are reported back (status) and re-run by the batched engine; nothing is approximated.
 #pragma once
 #include <cuda_runtime.h>
