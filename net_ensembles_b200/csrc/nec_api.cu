@@ -377,7 +377,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
         if (v >= 1 && (uint32_t)v < slots) slots = (uint32_t)v;
     }
     const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
-    const size_t need = (q_stride * 8 * 2 + o_stride * 4 * 4) * slots;
+    const size_t need = (q_stride * 8 * 2 + o_stride * 4 + o_stride * 16) * slots;
     if (need > ctx->mid_bytes) {
         if (ctx->mid_base) cudaFree(ctx->mid_base);
         ctx->mid_base = nullptr; ctx->mid_bytes = 0;
@@ -391,8 +391,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     double *d_q = (double *)ctx->mid_base;
     double *d_bslot = d_q + q_stride * slots;
     uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
-    uint32_t *d_cls = d_order + o_stride * slots;
-    uint32_t *d_succ = d_cls + o_stride * slots;          // 2 * o_stride per slot
+    uint4 *d_pos4 = (uint4 *)(d_order + o_stride * slots);   // o_stride entries per slot; 256 B aligned since o_stride*4 is
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, n_sources, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -401,7 +400,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab;
     p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
-    p.cls_base = d_cls; p.succ_base = d_succ;
+    p.pos4_base = d_pos4;
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
     p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
     if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }

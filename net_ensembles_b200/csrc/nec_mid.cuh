@@ -14,9 +14,9 @@
 //                            read on level l, so only ~two levels' worth of sectors per CTA has
 //                            to survive in the 126 MB L2
 //            order[n] u32  — BFS order = the level queues; written/read as a stream
-//            cls[n] u32    — per queue position: which slab neighbours are BFS successors and how
-//                            many neighbours are predecessors (see below); streamed
-//            succ0/succ1   — per queue position: the vertex's first two BFS successors; streamed
+//            pos4[n] 16 B  — per queue position {cls, s0, s1, s2}: cls = which slab neighbours are BFS
+//                            successors + how many neighbours are predecessors (see below), s* = the
+//                            vertex's first three successors; one coalesced 16 B store / load; streamed
 //            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
 //                            after each source (streams through HBM; evict-first hints)
 // Forward (thread per frontier vertex): one slab row (cp.async-staged one step ahead) gives the
@@ -70,8 +70,7 @@ struct MidParams {
     int include_endpoints;
     double *q_base;        size_t q_stride;
     uint32_t *order_base;  size_t order_stride;   // stride == capacity of the per-CTA queue (>= n)
-    uint32_t *cls_base;                       // same stride as order
-    uint32_t *succ_base;                      // 2 x order_stride: first and second BFS successor per queue position
+    uint4 *pos4_base;                         // per queue position {cls, first three BFS successors}; same stride as order
     double *bslot_base;    size_t bslot_stride;
     // measure_only != 0: forward pass only; per source index eccentricity / sum of distances / reached
     // count (nec_distance_measures) — they fall out of the level offsets, no extra traversal work
@@ -149,10 +148,8 @@ mid_engine(const MidParams p) {
 
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
     uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
-    uint32_t *__restrict__ clsq = p.cls_base + (size_t)blockIdx.x * p.order_stride;
+    uint4 *__restrict__ pos4 = p.pos4_base + (size_t)blockIdx.x * p.order_stride;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
-    uint32_t *__restrict__ succ0 = p.succ_base + (size_t)blockIdx.x * 2 * p.order_stride;
-    uint32_t *__restrict__ succ1 = succ0 + p.order_stride;
 
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
@@ -282,7 +279,7 @@ mid_engine(const MidParams p) {
                 }
                 // read each slab neighbour's distance once: classify it, claim it if unreached.
                 // Branch-free (predicated shared-memory PTX): lanes differ per slot, branches would serialise.
-                uint32_t won = 0, s0 = 0, s1 = 0, nsucc = 0;
+                uint32_t won = 0, s0 = 0, s1 = 0, s2 = 0, nsucc = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
                     const bool valid = (uint32_t)(k - 1) < deg;
@@ -290,6 +287,7 @@ mid_engine(const MidParams p) {
                     const uint32_t d = lds_u8_if(valid, dist_s32 + x, 0xFFFFu);
                     const bool unreached = d == 0xFFu;
                     const bool is_succ = unreached || d == next_d;
+                    s2 = (is_succ && nsucc == 2) ? x : s2;
                     s1 = (is_succ && nsucc == 1) ? x : s1;
                     s0 = (is_succ && nsucc == 0) ? x : s0;
                     nsucc += is_succ ? 1u : 0u;
@@ -304,7 +302,7 @@ mid_engine(const MidParams p) {
                     cls |= (is_succ ? 1u : 0u) << (k - 1);
                     cls += (d == pred_d ? 1u : 0u) << 16;
                 }
-                if (u != kNone) { __stcs(&clsq[i], cls); __stcs(&succ0[i], s0); __stcs(&succ1[i], s1); }
+                if (u != kNone) __stcs(&pos4[i], make_uint4(cls, s0, s1, s2));
                 {   // append everything this warp found with ONE tail update
                     const uint32_t cnt = __popc(won);
                     const uint32_t incl = warp_inclusive_scan(cnt, lane);
@@ -378,8 +376,8 @@ mid_engine(const MidParams p) {
 
         // ---- backward: deepest level first; one thread per vertex, CSR-order sums -----------
         // Everything a vertex needs was recorded per queue position by the forward pass: cls (successor
-        // mask, npred) and its first two successors.  The four streams are read coalesced, one step
-        // ahead; only the q pulls are random.  Vertices with > 2 successors, rows longer than the slab
+        // mask, npred) and its first three successors, 16 B per position.  The streams are read coalesced, one step
+        // ahead; only the q pulls are random.  Vertices with > 3 successors, rows longer than the slab
         // and hubs (rare) read the slab row / CSR and classify by distance byte: a finished vertex
         // carries 0x80 | (its level's parity << 6) | npred; a neighbour of a level-l vertex is a
         // successor <=> it is finished with the parity of l+1 (finished same-level neighbours carry l's).
@@ -389,44 +387,42 @@ mid_engine(const MidParams p) {
             const uint32_t succ_tag = 0x80u | (((l + 1) & 1u) << 6), mark_tag = 0x80u | ((l & 1u) << 6);
             auto is_successor_byte = [&](uint32_t b) { return (b & 0xC0u) == succ_tag && b != 0xFFu; };
             const long long t_lvl = clock64();
-            // two-deep software pipeline: step t+2's four words are being loaded, step t+1's q pulls are
+            // two-deep software pipeline: step t+2's (vertex, pos4) are being loaded, step t+1's q pulls are
             // in flight, step t is consumed
             uint32_t i = b0 + threadIdx.x;
-            uint32_t v_c = kNone, c_c = 0, v_n = kNone, c_n = 0, a_n = 0, b_n = 0;
-            double q0_c = 0.0, q1_c = 0.0;
+            uint32_t v_c = kNone, c_c = 0, v_n = kNone;
+            uint4 p_n = make_uint4(0u, 0u, 0u, 0u);
+            double q0_c = 0.0, q1_c = 0.0, q2_c = 0.0;
             if (i < b1) {
-                v_c = __ldcs(&order[i]); c_c = __ldcs(&clsq[i]);
-                const uint32_t a = __ldcs(&succ0[i]), b = __ldcs(&succ1[i]);
+                v_c = __ldcs(&order[i]);
+                const uint4 t = __ldcs(&pos4[i]);
+                c_c = t.x;
                 const uint32_t ns = __popc(c_c & 0x7FFFu);
-                if (ns >= 1) q0_c = q[a];
-                if (ns >= 2) q1_c = q[b];
+                if (ns >= 1) q0_c = q[t.y];
+                if (ns >= 2) q1_c = q[t.z];
+                if (ns >= 3) q2_c = q[t.w];
             }
-            if (i + kStride < b1) {
-                v_n = __ldcs(&order[i + kStride]); c_n = __ldcs(&clsq[i + kStride]);
-                a_n = __ldcs(&succ0[i + kStride]); b_n = __ldcs(&succ1[i + kStride]);
-            }
+            if (i + kStride < b1) { v_n = __ldcs(&order[i + kStride]); p_n = __ldcs(&pos4[i + kStride]); }
             for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kStride, i += kStride) {
                 const uint32_t w = v_c, cls = c_c;
-                const double q0 = q0_c, q1 = q1_c;
+                const double q0 = q0_c, q1 = q1_c, q2 = q2_c;
                 // issue step t+1's pulls, then step t+2's loads
-                v_c = v_n; c_c = c_n; q0_c = 0.0; q1_c = 0.0;
+                v_c = v_n; c_c = p_n.x; q0_c = 0.0; q1_c = 0.0; q2_c = 0.0;
                 {
-                    const uint32_t ns = __popc(c_n & 0x7FFFu);
-                    if (ns >= 1) q0_c = q[a_n];
-                    if (ns >= 2) q1_c = q[b_n];
+                    const uint32_t ns = __popc(p_n.x & 0x7FFFu);
+                    if (ns >= 1) q0_c = q[p_n.y];
+                    if (ns >= 2) q1_c = q[p_n.z];
+                    if (ns >= 3) q2_c = q[p_n.w];
                 }
-                v_n = kNone; c_n = 0;
-                if (i + 2 * kStride < b1) {
-                    v_n = __ldcs(&order[i + 2 * kStride]); c_n = __ldcs(&clsq[i + 2 * kStride]);
-                    a_n = __ldcs(&succ0[i + 2 * kStride]); b_n = __ldcs(&succ1[i + 2 * kStride]);
-                }
+                v_n = kNone; p_n = make_uint4(0u, 0u, 0u, 0u);
+                if (i + 2 * kStride < b1) { v_n = __ldcs(&order[i + 2 * kStride]); p_n = __ldcs(&pos4[i + 2 * kStride]); }
                 const uint32_t smask = cls & 0x7FFFu;
                 const uint32_t nsucc = __popc(smask);
-                double acc = q0 + q1;                                          // successors in CSR order
+                double acc = (q0 + q1) + q2;                                   // successors in CSR order
                 uint32_t np = cls >> 16;
                 uint32_t deg = 0, rs = 0;
                 bool hub = false;
-                if (nsucc > 2 || (cls & kClsRowFlag)) {                        // rare: the row itself is needed
+                if (nsucc > 3 || (cls & kClsRowFlag)) {                        // rare: the row itself is needed
                     uint32_t row[W];
 #pragma unroll
                     for (int k = 0; k < W / 4; ++k) {
@@ -434,7 +430,7 @@ mid_engine(const MidParams p) {
                         row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
                     }
                     uint32_t rest = smask;
-                    rest &= rest - 1; rest &= rest - 1;                        // beyond the first two successors
+                    rest &= rest - 1; rest &= rest - 1; rest &= rest - 1;      // beyond the first three successors
 #pragma unroll
                     for (int k = 1; k < W; ++k)
                         if ((rest >> (k - 1)) & 1u) acc += q[row[k]];

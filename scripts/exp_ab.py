@@ -18,6 +18,7 @@ if len(sys.argv) > 1:
     st = ctx.stats()
     print("%-8s engine_ms %s -> full-run est %.1f ms  fwd %.3f bwd %.3f" % (sys.argv[1], ["%.2f" % t for t in ts], min(ts) * 4, st["frac_forward"], st["frac_backward"]), flush=True)
 else:
-    for slots in ("296", "260", "222", "200", "180", "148"):
-        env = dict(os.environ, NEC_MID_SLOTS=slots)
-        subprocess.run([sys.executable, __file__, "slots=" + slots], env=env)
+    for rep in range(2):
+        for tag in ("ab_old", "ab_new"):
+            env = dict(os.environ, NEC_LIB_PATH=os.path.join(ROOT, "net_ensembles_b200", "lib", tag + ".so"))
+            subprocess.run([sys.executable, __file__, tag], env=env)
