@@ -14,9 +14,9 @@
 //                            read on level l, so only ~two levels' worth of sectors per CTA has
 //                            to survive in the 126 MB L2
 //            order[n] u32  — BFS order = the level queues; written/read as a stream
-//            pos4[n] 16 B  — per queue position {cls, s0, s1, s2}: cls = which slab neighbours are BFS
-//                            successors + how many neighbours are predecessors (see below), s* = the
-//                            vertex's first three successors; one coalesced 16 B store / load; streamed
+//            pos4[n] 16 B  — per queue position: the vertex's first four BFS successors with its successor
+//                            count, predecessor count and "row needed" flag packed into the spare high
+//                            bits (ids < 2^18); one coalesced 16 B store / load; streamed
 //            bslot[n] f64  — this CTA's private partial load, updated by a coalesced sweep
 //                            after each source (streams through HBM; evict-first hints)
 // Forward (thread per frontier vertex): one slab row (cp.async-staged one step ahead) gives the
@@ -279,7 +279,7 @@ mid_engine(const MidParams p) {
                 }
                 // read each slab neighbour's distance once: classify it, claim it if unreached.
                 // Branch-free (predicated shared-memory PTX): lanes differ per slot, branches would serialise.
-                uint32_t won = 0, s0 = 0, s1 = 0, s2 = 0, nsucc = 0;
+                uint32_t won = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0, nsucc = 0;
 #pragma unroll
                 for (int k = 1; k < W; ++k) {
                     const bool valid = (uint32_t)(k - 1) < deg;
@@ -287,6 +287,7 @@ mid_engine(const MidParams p) {
                     const uint32_t d = lds_u8_if(valid, dist_s32 + x, 0xFFFFu);
                     const bool unreached = d == 0xFFu;
                     const bool is_succ = unreached || d == next_d;
+                    s3 = (is_succ && nsucc == 3) ? x : s3;
                     s2 = (is_succ && nsucc == 2) ? x : s2;
                     s1 = (is_succ && nsucc == 1) ? x : s1;
                     s0 = (is_succ && nsucc == 0) ? x : s0;
@@ -302,7 +303,8 @@ mid_engine(const MidParams p) {
                     cls |= (is_succ ? 1u : 0u) << (k - 1);
                     cls += (d == pred_d ? 1u : 0u) << 16;
                 }
-                if (u != kNone) __stcs(&pos4[i], make_uint4(cls, s0, s1, s2));
+                if (u != kNone)                       // {s0 | npred<<26, s1 | min(nsucc,7)<<28 | rowflag<<31, s2, s3}; ids < 2^18
+                    __stcs(&pos4[i], make_uint4(s0 | ((cls >> 16) << 26), s1 | (min(nsucc, 7u) << 28) | ((cls & kClsRowFlag) << 16), s2, s3));
                 {   // append everything this warp found with ONE tail update
                     const uint32_t cnt = __popc(won);
                     const uint32_t incl = warp_inclusive_scan(cnt, lane);
@@ -375,9 +377,9 @@ mid_engine(const MidParams p) {
         }
 
         // ---- backward: deepest level first; one thread per vertex, CSR-order sums -----------
-        // Everything a vertex needs was recorded per queue position by the forward pass: cls (successor
-        // mask, npred) and its first three successors, 16 B per position.  The streams are read coalesced, one step
-        // ahead; only the q pulls are random.  Vertices with > 3 successors, rows longer than the slab
+        // Everything a vertex needs was recorded per queue position by the forward pass: its first four
+        // successors, successor count and npred, 16 B per position.  The streams are read coalesced, one step
+        // ahead; only the q pulls are random.  Vertices with > 4 successors, rows longer than the slab
         // and hubs (rare) read the slab row / CSR and classify by distance byte: a finished vertex
         // carries 0x80 | (its level's parity << 6) | npred; a neighbour of a level-l vertex is a
         // successor <=> it is finished with the parity of l+1 (finished same-level neighbours carry l's).
@@ -387,58 +389,57 @@ mid_engine(const MidParams p) {
             const uint32_t succ_tag = 0x80u | (((l + 1) & 1u) << 6), mark_tag = 0x80u | ((l & 1u) << 6);
             auto is_successor_byte = [&](uint32_t b) { return (b & 0xC0u) == succ_tag && b != 0xFFu; };
             const long long t_lvl = clock64();
-            // two-deep software pipeline: step t+2's (vertex, pos4) are being loaded, step t+1's q pulls are
-            // in flight, step t is consumed
+            // two-deep software pipeline: step t+2's (vertex, record) are being loaded, step t+1's q pulls
+            // are in flight, step t is consumed
             uint32_t i = b0 + threadIdx.x;
-            uint32_t v_c = kNone, c_c = 0, v_n = kNone;
+            uint32_t v_c = kNone, m_c = 0, v_n = kNone;        // m: np<<8 | nsucc<<1 | rowflag of the step
             uint4 p_n = make_uint4(0u, 0u, 0u, 0u);
-            double q0_c = 0.0, q1_c = 0.0, q2_c = 0.0;
+            double q0_c = 0.0, q1_c = 0.0, q2_c = 0.0, q3_c = 0.0;
+            auto issue_pulls = [&](const uint4 &r, double &a0, double &a1, double &a2, double &a3) -> uint32_t {
+                const uint32_t ns = (r.y >> 28) & 7u;
+                a0 = ns >= 1 ? q[r.x & 0x3FFFFFFu] : 0.0;
+                a1 = ns >= 2 ? q[r.y & 0xFFFFFFFu] : 0.0;
+                a2 = ns >= 3 ? q[r.z] : 0.0;
+                a3 = ns >= 4 ? q[r.w] : 0.0;
+                return ((r.x >> 26) << 8) | (ns << 1) | (r.y >> 31);
+            };
             if (i < b1) {
                 v_c = __ldcs(&order[i]);
                 const uint4 t = __ldcs(&pos4[i]);
-                c_c = t.x;
-                const uint32_t ns = __popc(c_c & 0x7FFFu);
-                if (ns >= 1) q0_c = q[t.y];
-                if (ns >= 2) q1_c = q[t.z];
-                if (ns >= 3) q2_c = q[t.w];
+                m_c = issue_pulls(t, q0_c, q1_c, q2_c, q3_c);
             }
             if (i + kStride < b1) { v_n = __ldcs(&order[i + kStride]); p_n = __ldcs(&pos4[i + kStride]); }
             for (uint32_t wbase = b0 + warp * 32; wbase < b1; wbase += kStride, i += kStride) {
-                const uint32_t w = v_c, cls = c_c;
-                const double q0 = q0_c, q1 = q1_c, q2 = q2_c;
+                const uint32_t w = v_c, meta = m_c;
+                double acc = ((q0_c + q1_c) + q2_c) + q3_c;                      // successors in CSR order
                 // issue step t+1's pulls, then step t+2's loads
-                v_c = v_n; c_c = p_n.x; q0_c = 0.0; q1_c = 0.0; q2_c = 0.0;
-                {
-                    const uint32_t ns = __popc(p_n.x & 0x7FFFu);
-                    if (ns >= 1) q0_c = q[p_n.y];
-                    if (ns >= 2) q1_c = q[p_n.z];
-                    if (ns >= 3) q2_c = q[p_n.w];
-                }
+                v_c = v_n;
+                m_c = issue_pulls(p_n, q0_c, q1_c, q2_c, q3_c);
                 v_n = kNone; p_n = make_uint4(0u, 0u, 0u, 0u);
                 if (i + 2 * kStride < b1) { v_n = __ldcs(&order[i + 2 * kStride]); p_n = __ldcs(&pos4[i + 2 * kStride]); }
-                const uint32_t smask = cls & 0x7FFFu;
-                const uint32_t nsucc = __popc(smask);
-                double acc = (q0 + q1) + q2;                                   // successors in CSR order
-                uint32_t np = cls >> 16;
+                const uint32_t nsucc = (meta >> 1) & 7u;
+                uint32_t np = meta >> 8;
                 uint32_t deg = 0, rs = 0;
                 bool hub = false;
-                if (nsucc > 3 || (cls & kClsRowFlag)) {                        // rare: the row itself is needed
+                if (nsucc > 4 || (meta & 1u)) {                               // rare: the row itself is needed
                     uint32_t row[W];
 #pragma unroll
                     for (int k = 0; k < W / 4; ++k) {
                         const uint4 t = __ldg(p.slab + (size_t)w * (W / 4) + k);
                         row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w;
                     }
-                    uint32_t rest = smask;
-                    rest &= rest - 1; rest &= rest - 1; rest &= rest - 1;      // beyond the first three successors
+                    deg = row[0];
+                    hub = deg > kMidHubDeg;
+                    if (!hub) {
+                        // recompute the whole sum in CSR order, classifying by distance byte
+                        acc = 0.0;
 #pragma unroll
-                    for (int k = 1; k < W; ++k)
-                        if ((rest >> (k - 1)) & 1u) acc += q[row[k]];
-                    if (cls & kClsRowFlag) {
-                        deg = row[0];
-                        hub = deg > kMidHubDeg;
-                        rs = __ldg(p.row_ptr + w);
-                        if (!hub) {
+                        for (int k = 1; k < W; ++k) {
+                            const uint32_t b = (uint32_t)(k - 1) < deg ? (uint32_t)dist[row[k]] : 0xFFu;
+                            if (is_successor_byte(b)) acc += q[row[k]];
+                        }
+                        if (deg > kSlabNbrs) {
+                            rs = __ldg(p.row_ptr + w);
                             for (uint32_t k0 = kSlabNbrs; k0 < deg; k0 += 4) {
                                 uint32_t xs[4], dy[4];
                                 double qy[4];
@@ -452,6 +453,8 @@ mid_engine(const MidParams p) {
                                 for (int j = 0; j < 4; ++j) { acc += qy[j]; np += dy[j] == d_pred ? 1u : 0u; }
                             }
                         }
+                    } else {
+                        rs = __ldg(p.row_ptr + w);
                     }
                 }
                 // hubs of this warp's 32 vertices: all lanes cooperate, one hub at a time; the sum over
