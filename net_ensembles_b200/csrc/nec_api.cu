@@ -46,6 +46,7 @@ struct nec_graph {
     uint32_t *d_col_idx = nullptr;   // nnz
     uint32_t max_degree = 0;
     uint4 *d_slab = nullptr;         // n rows of slab_w u32 (mid engine), nullptr if n > kMidMaxN
+    uint8_t *d_deg8 = nullptr;       // min(degree, 255) per vertex (mid engine)
     int slab_w = 0;
 };
 
@@ -397,7 +398,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(d_bslot, 0, q_stride * 8 * slots, ctx->stream));
     nec::MidParams p{};
-    p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab;
+    p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab; p.deg8 = g->d_deg8;
     p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
     p.pos4_base = d_pos4;
@@ -608,6 +609,7 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, rp32.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     std::vector<uint32_t> slab;
+    std::vector<uint8_t> deg8;
     if (e == cudaSuccess && n > 0 && n <= nec::kMidMaxN) {
         // slab rows: [degree, first W-1 neighbours]; W = 8 unless more than 10 % of the rows would overflow
         size_t over8 = 0;
@@ -620,8 +622,12 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
             slab[(size_t)v * W] = (uint32_t)deg;
             for (uint64_t k = 0; k < deg && k < (uint64_t)(W - 1); ++k) slab[(size_t)v * W + 1 + k] = col_idx[rs + k];
         }
+        deg8.resize((size_t)n + 2);
+        for (uint32_t v = 0; v < n; ++v) deg8[v] = (uint8_t)std::min<uint64_t>(row_ptr[v + 1] - row_ptr[v], 255);
         e = cudaMallocAsync((void **)&g->d_slab, slab.size() * sizeof(uint32_t), ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_slab, slab.data(), slab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_deg8, deg8.size(), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_deg8, deg8.data(), deg8.size(), cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -639,6 +645,7 @@ void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
         if (g->d_row_ptr) cudaFreeAsync(g->d_row_ptr, ctx->stream);
         if (g->d_col_idx) cudaFreeAsync(g->d_col_idx, ctx->stream);
         if (g->d_slab) cudaFreeAsync(g->d_slab, ctx->stream);
+        if (g->d_deg8) cudaFreeAsync(g->d_deg8, ctx->stream);
     }
     delete g;
 }

@@ -65,6 +65,7 @@ struct MidParams {
     const uint32_t *__restrict__ row_ptr;
     const uint32_t *__restrict__ col_idx;
     const uint4 *__restrict__ slab;           // n rows of W u32: [degree, first W-1 neighbours] (see nec_graph)
+    const uint8_t *__restrict__ deg8;         // min(degree, 255) per vertex (255: look at row_ptr)
     const uint32_t *__restrict__ sources;
     uint32_t n_sources;
     int include_endpoints;
@@ -354,7 +355,11 @@ mid_engine(const MidParams p) {
             uint32_t cnt = 0;
             for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
                 const uint32_t d = dist[v];
-                if (d != 0xFFu) { sum += d; cnt += 1; t_edges += __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v); }
+                if (d != 0xFFu) {
+                    sum += d; cnt += 1;
+                    const uint32_t dg = __ldg(p.deg8 + v);
+                    t_edges += dg != 0xFFu ? dg : __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
+                }
             }
             t_reached = cnt;
 #pragma unroll
@@ -501,18 +506,46 @@ mid_engine(const MidParams p) {
             continue;
         }
         // ---- sweep: this source's contribution, coalesced ------------------------------------
+        // two vertices per 16-byte access, four accesses in flight per thread: q (L2) and the partial
+        // load (HBM stream) are the long-latency loads here
         {
             const double sub = p.include_endpoints ? 0.0 : 1.0;
-            for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
-                const uint32_t d = dist[v];
+            auto one = [&](uint32_t v, uint32_t d, uint32_t dg, double qv, double &b) {      // exact stats + load term
                 if (d != 0xFFu) {
                     t_reached += 1;                                   // exact (the queue may hold duplicates)
-                    t_edges += __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
-                    if (d != 0u) {
-                        const double bk = q[v] * (double)(d & 0x3Fu);           // finished mark carries npred
-                        __stcs(&bslot[v], __ldcs(&bslot[v]) + (bk - sub));
+                    t_edges += dg != 0xFFu ? dg : __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
+                    // finished mark carries npred; no FMA contraction: a BFS leaf must give exactly bk - 1 = 0
+                    if (d != 0u) b += __dsub_rn(__dmul_rn(qv, (double)(d & 0x3Fu)), sub);
+                }
+            };
+            const uint32_t n2 = n & ~1u;
+            for (uint32_t base = 2 * threadIdx.x; base < n2; base += 8 * kMidThreads) {
+                double2 qq[4], bb[4];
+                uint32_t dd[4], gg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t v = base + u * 2 * kMidThreads;
+                    dd[u] = v < n2 ? (uint32_t)*reinterpret_cast<const uint16_t *>(dist + v) : 0xFFFFu;
+                    const bool any = dd[u] != 0xFFFFu;
+                    qq[u] = any ? *reinterpret_cast<const double2 *>(q + v) : make_double2(0.0, 0.0);
+                    bb[u] = any ? __ldcs(reinterpret_cast<const double2 *>(bslot + v)) : make_double2(0.0, 0.0);
+                    gg[u] = any ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(p.deg8 + v)) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t v = base + u * 2 * kMidThreads;
+                    if (dd[u] != 0xFFFFu) {
+                        one(v, dd[u] & 0xFFu, gg[u] & 0xFFu, qq[u].x, bb[u].x);
+                        one(v + 1, dd[u] >> 8, gg[u] >> 8, qq[u].y, bb[u].y);
+                        __stcs(reinterpret_cast<double2 *>(bslot + v), bb[u]);
                     }
                 }
+            }
+            if ((n & 1u) && threadIdx.x == 0) {
+                const uint32_t v = n - 1;
+                double b = bslot[v];
+                one(v, dist[v], p.deg8[v], q[v], b);
+                bslot[v] = b;
             }
         }
         if (depth > my_depth) my_depth = depth;
