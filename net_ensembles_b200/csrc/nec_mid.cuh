@@ -145,14 +145,14 @@ mid_engine(const MidParams p) {
     __shared__ uint32_t s_mreach;
     const uint32_t qcap = (uint32_t)p.order_stride;
     __shared__ uint32_t s_hub[kMidHubCap];
-    __shared__ unsigned long long s_cnt[2];
+    __shared__ unsigned long long s_cnt[3];      // reached, edge pairs, queue entries (incl. duplicates)
 
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
     uint32_t *__restrict__ order = p.order_base + (size_t)blockIdx.x * p.order_stride;
     uint4 *__restrict__ pos4 = p.pos4_base + (size_t)blockIdx.x * p.order_stride;
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
 
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0, cyc_small = 0;
 
@@ -553,14 +553,14 @@ mid_engine(const MidParams p) {
             const uint32_t wr = __reduce_add_sync(0xFFFFFFFFu, t_reached), we = __reduce_add_sync(0xFFFFFFFFu, t_edges);
             if (lane == 0) { atomicAdd(&s_cnt[0], (unsigned long long)wr); atomicAdd(&s_cnt[1], (unsigned long long)we); }
         }
-        if (threadIdx.x == 0) { p.source_status[si] = kMidDone; cyc_bwd += clock64() - t_phase; }
+        if (threadIdx.x == 0) { p.source_status[si] = kMidDone; cyc_bwd += clock64() - t_phase; s_cnt[2] += s_lvl[depth + 1]; }
         __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         atomicAdd(&p.counters[0], s_cnt[0]);
         atomicAdd(&p.counters[1], s_cnt[1]);
-        atomicAdd(&p.counters[2], s_cnt[0]);
+        atomicAdd(&p.counters[2], s_cnt[2] ? s_cnt[2] : s_cnt[0]);
         atomicMax(&p.counters[3], (unsigned long long)my_depth);
         atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
         atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
