@@ -377,7 +377,12 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
         const int v = atoi(env);
         if (v >= 1 && (uint32_t)v < slots) slots = (uint32_t)v;
     }
-    const size_t q_stride = align_up((size_t)n * 8, 256) / 8, o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
+    const size_t q_stride = align_up((size_t)n * 8, 256) / 8;
+    size_t o_stride = align_up((size_t)n * 2 * 4, 256) / 4;   // queue: room for duplicates
+    if (const char *env = getenv("NEC_MID_QUEUE_CAP")) {          // test hook: force the overflow hand-back path
+        const long v = atol(env);
+        if (v >= 64 && (size_t)v < o_stride) o_stride = align_up((size_t)v * 4, 256) / 4;
+    }
     const size_t need = (q_stride * 8 * 2 + o_stride * 4 + o_stride * 16) * slots;
     if (need > ctx->mid_bytes) {
         if (ctx->mid_base) cudaFree(ctx->mid_base);

@@ -243,6 +243,8 @@ mid_engine(const MidParams p) {
                 if (threadIdx.x == 0) s_hub_n = 0;
                 continue;                                 // re-sample the tail
             }
+            if (s_qfull) break;                           // queue overflowed: some slots below the tail were never
+                                                          // written, so nothing behind this point may be expanded
             lb = le;
             le = tail_now;
             if (threadIdx.x == 0) s_lvl[level] = lb;

@@ -231,6 +231,24 @@ def test_many_predecessors_and_hubs(engine_ctx, oracle):
     dg.free()
 
 
+def test_mid_engine_queue_overflow_hands_sources_back(ctx, oracle, monkeypatch):
+    """The mid engine's queue holds 2n entries (plain-store claims may append a vertex twice); a source
+    that overflows it must be handed back to the batched engine, not expanded past the hole."""
+    e = ne.SwEnsemble(3000, 0.2, 21)
+    rp, col = e.export_csr()
+    want = oracle.vertex_load(rp, col, True, threads=0)
+    monkeypatch.setenv("NEC_MID_QUEUE_CAP", "1024")          # far below n: every source overflows
+    dg = ctx.upload(rp, col)
+    got = dg.vertex_load(True)
+    st = ctx.stats()
+    assert st["wide_batches"] == 3000 and (st["engine"] >> 4) == 2
+    assert close(got, want, REL)
+    monkeypatch.delenv("NEC_MID_QUEUE_CAP")
+    assert close(dg.vertex_load(True), want, REL)
+    assert ctx.stats()["engine"] == 2
+    dg.free()
+
+
 def test_mid_engine_is_the_default_for_mid_size_graphs(ctx, oracle):
     e = ne.SwEnsemble(4096, 0.1, 3)
     rp, col = e.export_csr()
