@@ -330,9 +330,12 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev_mid);
         ctx->stats.engine_ms += ms2;
         ctx->stats.workspace_bytes = std::max<uint64_t>(ctx->stats.workspace_bytes, ctx->arena.bytes);
-        for (uint32_t b : deep)
+        for (uint32_t b : deep) {
+            if (status[b] == nec::kQueueOverflow)
+                return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (32-bit distance pass, capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
             if (status[b] != nec::kDone)
                 return fail(ctx, NEC_EINTERNAL, "batch %u failed in the 32-bit distance pass (status %u)", b, (unsigned)status[b]);
+        }
     }
     ctx->stats.engine = 1;
     ctx->stats.reached_pairs = counters[0];

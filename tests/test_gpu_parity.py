@@ -231,6 +231,25 @@ def test_many_predecessors_and_hubs(engine_ctx, oracle):
     dg.free()
 
 
+def test_batched_engine_reports_queue_overflow_loudly(ctx, oracle):
+    """With a starved workspace the batched engine shrinks its level-queue bound from 32n to 8n entries per
+    slot; a path graph puts every vertex on 32 distinct levels of a 32-source batch, which must be reported
+    (NEC_EINTERNAL), never silently truncated — and the context must stay usable."""
+    n = 6000
+    rp, col = csr_from_adj(adj_from_edges(n, [(i, i + 1) for i in range(n - 1)]))
+    dg = ctx.upload(rp, col)
+    ctx.set_engine(1)
+    ctx.set_workspace_limit(3 * 1000 * 1000)                    # one slot, and only with the shrunken queue
+    with pytest.raises(ne.NecError) as ei:
+        dg.vertex_load_sources(np.arange(64, dtype=np.uint32), True)
+    assert ei.value.code == -5 and "queue overflow" in str(ei.value)
+    ctx.set_workspace_limit(0)
+    src = np.arange(0, n, 97, dtype=np.uint32)
+    assert close(dg.vertex_load_sources(src, True), oracle.vertex_load(rp, col, True, sources=src), REL)
+    ctx.set_engine(0)
+    dg.free()
+
+
 def test_mid_engine_queue_overflow_hands_sources_back(ctx, oracle, monkeypatch):
     """The mid engine's queue holds 2n entries (plain-store claims may append a vertex twice); a source
     that overflows it must be handed back to the batched engine, not expanded past the hole."""
