@@ -296,3 +296,75 @@ def test_sampled_parity_on_larger_graph(ctx, oracle):
     src = np.arange(0, 1 << 14, 251, dtype=np.uint32)
     assert close(dg2.vertex_load_sources(src, True), oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
     dg.free(), dg2.free()
+
+
+def _random_graph(rng, n, m):
+    """Simple undirected graph with ~m distinct edges, adjacency in insertion order."""
+    adj = [[] for _ in range(n)]
+    seen = set()
+    if n < 2:
+        return adj
+    for _ in range(m):
+        a, b = int(rng.integers(n)), int(rng.integers(n))
+        if a == b or (min(a, b), max(a, b)) in seen:
+            continue
+        seen.add((min(a, b), max(a, b)))
+        adj[a].append(b)
+        adj[b].append(a)
+    return adj
+
+
+def test_differential_fuzz_all_engines(ctx, oracle):
+    """Random small graphs of every density (isolated vertices, many components, near-complete), both
+    traversal engines, both endpoint conventions, the small-graph batch kernel and the distance measures."""
+    rng = np.random.default_rng(20261019)
+    graphs = []
+    for trial in range(120):
+        n = int(rng.integers(1, 220))
+        dens = float(rng.choice([0.0, 0.3, 0.6, 1.0, 2.0, 4.0, 12.0]))
+        graphs.append(_random_graph(rng, n, int(dens * n)))
+    csr = [csr_from_adj(a) for a in graphs]
+    want_t = [oracle.vertex_load(rp, col, True) for rp, col in csr]
+    want_f = [oracle.vertex_load(rp, col, False) for rp, col in csr]
+    for engine in (1, 2):
+        ctx.set_engine(engine)
+        for (rp, col), wt, wf in zip(csr, want_t, want_f):
+            dg = ctx.upload(rp, col)
+            assert close(dg.vertex_load(True), wt, REL) and close(dg.vertex_load(False), wf, REL)
+            ecc, sumd, reached = dg.distance_measures()
+            recc, rsum, rreach = oracle.distance_measures(rp, col)
+            assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
+            dg.free()
+    ctx.set_engine(0)
+    outs = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in csr], False)
+    for got, wf in zip(outs, want_f):
+        assert close(got, wf, REL)
+
+
+def test_mid_engine_hub_list_overflow_and_hub_heavy_graphs(ctx, oracle):
+    """600 vertices of degree 71 on one BFS level: more hubs than the shared hub list holds (512), so some
+    are expanded inline; plus a root of degree 600 and a Barabasi-Albert graph with hubs of degree ~1000."""
+    edges = [(0, 1 + h) for h in range(600)]
+    nxt = 601
+    for h in range(600):
+        for _ in range(70):
+            edges.append((1 + h, nxt))
+            nxt += 1
+    adj = adj_from_edges(nxt, edges)
+    rp, col = csr_from_adj(adj)
+    dg = ctx.upload(rp, col)
+    src = np.concatenate([np.arange(0, 8), np.arange(601, nxt, 997)]).astype(np.uint32)
+    ctx.set_engine(2)
+    for incl in (True, False):
+        assert close(dg.vertex_load_sources(src, incl), oracle.vertex_load(rp, col, incl, sources=src), REL)
+    assert ctx.stats()["engine"] == 2
+    ctx.set_engine(0)
+    dg.free()
+    b = ne.ba_scalable(60000, 4, 5, 3)
+    rp, col = b.export_csr()
+    assert int(np.diff(rp.astype(np.int64)).max()) > 500
+    dg = ctx.upload(rp, col)
+    src = np.arange(0, 60000, 1201, dtype=np.uint32)
+    assert close(dg.vertex_load_sources(src, True), oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
+    assert ctx.stats()["engine"] & 15 in (1, 2)
+    dg.free()
