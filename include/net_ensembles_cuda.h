@@ -145,7 +145,7 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
 /* Counters of the last nec_vertex_load* call on this context. */
 typedef struct nec_stats {
     uint64_t n_sources;       /* sources processed */
-    uint64_t n_batches;       /* 32-source batches */
+    uint64_t n_batches;       /* batches (of batch_width sources) */
     uint64_t reached_pairs;   /* sum_s |R_s|  (vertices reached, source included) */
     uint64_t edge_pairs;      /* sum_s E_s    (directed adjacency entries in s's component) */
     uint64_t vertex_visits;   /* (vertex, level, batch) queue entries expanded, forward pass */
@@ -161,7 +161,7 @@ typedef struct nec_stats {
     uint64_t workspace_bytes; /* scratch arena in use */
     uint32_t engine;          /* traversal kernel that ran: 1 batched (vertex_load_engine), 2 mid (mid_engine),
                                  3 small-graph batch (small_graph_kernel); batched|mid<<4 if mid handed sources back */
-    uint32_t reserved;
+    uint32_t batch_width;     /* sources per batch of the batched engine in this call: 32 or 64 (0: engine not used) */
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);
 

@@ -14,6 +14,7 @@ ORACLE_PATH = os.path.join(ROOT, "oracle", "build", "liboracle.so")
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "nec_api.cu"), os.path.join(PKG, "csrc", "host", "host_api.cpp")]
 CUDA_DEPS = CUDA_SOURCES + [
     os.path.join(PKG, "csrc", "nec_kernels.cuh"), os.path.join(PKG, "csrc", "nec_small.cuh"),
+    os.path.join(PKG, "csrc", "nec_mid.cuh"),
     os.path.join(PKG, "csrc", "host", "nec_graphs.hpp"), os.path.join(PKG, "csrc", "host", "nec_rand.hpp"),
     os.path.join(ROOT, "include", "net_ensembles_cuda.h"),
 ]

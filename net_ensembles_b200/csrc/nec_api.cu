@@ -26,14 +26,14 @@ struct Arena {                       // per-slot scratch of the batched engine
     void *base = nullptr;
     size_t bytes = 0;
     // layout parameters the arena was built for
-    uint32_t n = 0, n_slots = 0, dist_bytes = 0, max_levels = 0;
+    uint32_t n = 0, n_slots = 0, dist_bytes = 0, max_levels = 0, ksrc = 0;
     size_t qcap = 0;
     // carved pointers
     uint8_t *dist = nullptr; size_t dist_stride = 0;
     double *q = nullptr;     size_t q_stride = 0;
-    uint32_t *mask = nullptr; size_t mask_stride = 0;
+    uint8_t *mask = nullptr; size_t mask_stride = 0;    // bytes per slot
     double *bslot = nullptr; size_t bslot_stride = 0;
-    uint2 *queue = nullptr;  size_t queue_stride = 0;
+    uint32_t *queue_v = nullptr; uint8_t *queue_m = nullptr; size_t queue_stride = 0;   // entries per slot
     uint32_t *lvl = nullptr; size_t lvl_stride = 0;
 };
 
@@ -106,54 +106,71 @@ int grow(nec_ctx *ctx, T *&ptr, size_t &cap, size_t need) {
     return NEC_OK;
 }
 
-size_t per_slot_bytes(uint32_t n, uint32_t dist_bytes, size_t qcap, uint32_t max_levels) {
+size_t per_slot_bytes(uint32_t n, uint32_t dist_bytes, size_t qcap, uint32_t max_levels, uint32_t ksrc) {
+    const size_t mask_b = ksrc / 8;
+    const size_t qpitch = align_up(qcap, 64);
     size_t b = 0;
-    b += align_up((size_t)n * nec::kLanes * dist_bytes, 256);
-    b += align_up((size_t)n * nec::kLanes * sizeof(double), 256);
-    b += align_up((size_t)n * 3 * sizeof(uint32_t), 256);
+    b += align_up((size_t)n * ksrc * dist_bytes, 256);
+    b += align_up((size_t)n * ksrc * sizeof(double), 256);
+    b += align_up((size_t)n * 4 * mask_b, 256);
     b += align_up((size_t)n * sizeof(double), 256);
-    b += align_up(qcap * sizeof(uint2), 256);
+    b += qpitch * 4 + qpitch * mask_b;
     b += align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);
     return b;
 }
 
-// Build (or reuse) the arena for (n, distance width, wanted slots).
-int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots) {
-    Arena &a = ctx->arena;
+// Slots and queue capacity the workspace budget allows for (n, distance width, batch width, wanted slots).
+struct ArenaPlan { uint32_t slots; size_t qcap, per_slot, budget; };
+int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc, ArenaPlan &out) {
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     size_t free_b = 0, total_b = 0;
     NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + a.bytes) * 0.8);
-    // queue capacity: every vertex can sit on at most 32 distinct levels of one batch
-    size_t qcap = (size_t)n * nec::kLanes + nec::kLanes;
+    const size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + ctx->arena.bytes) * 0.8);
+    // queue capacity: every vertex can sit on at most 32 (64) distinct levels of one batch
+    size_t qcap = (size_t)n * ksrc + ksrc;
     uint32_t slots = want_slots;
-    size_t ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
+    size_t ps = per_slot_bytes(n, dist_bytes, qcap, max_levels, ksrc);
     if (ps * slots > budget) {
         // prefer keeping one slot per SM; shrink the queue bound (overflow is detected) first
         const uint32_t floor_slots = std::min<uint32_t>(slots, (uint32_t)ctx->prop.multiProcessorCount);
-        while (ps * floor_slots > budget && qcap > (size_t)n * 8 + nec::kLanes) {
-            qcap = std::max((size_t)n * 8 + nec::kLanes, qcap / 2);
-            ps = per_slot_bytes(n, dist_bytes, qcap, max_levels);
+        while (ps * floor_slots > budget && qcap > (size_t)n * 8 + ksrc) {
+            qcap = std::max((size_t)n * 8 + ksrc, qcap / 2);
+            ps = per_slot_bytes(n, dist_bytes, qcap, max_levels, ksrc);
         }
         slots = (uint32_t)std::min<size_t>(slots, budget / ps);
-        if (slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one batch slot (%zu B) for n=%u", budget, ps, n);
     }
-    const bool reuse = a.base && a.n == n && a.dist_bytes == dist_bytes && a.n_slots >= slots && a.qcap == qcap;
+    out = ArenaPlan{slots, qcap, ps, budget};
+    return NEC_OK;
+}
+
+// Build (or reuse) the arena for (n, distance width, wanted slots).
+int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc = nec::kLanes) {
+    Arena &a = ctx->arena;
+    const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
+    ArenaPlan plan{};
+    int prc = plan_arena(ctx, n, dist_bytes, want_slots, ksrc, plan);
+    if (prc != NEC_OK) return prc;
+    const uint32_t slots = plan.slots;
+    const size_t qcap = plan.qcap, ps = plan.per_slot;
+    if (slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one batch slot (%zu B) for n=%u", plan.budget, ps, n);
+    const bool reuse = a.base && a.n == n && a.dist_bytes == dist_bytes && a.ksrc == ksrc && a.n_slots >= slots && a.qcap == qcap;
     if (!reuse) {
         if (a.base) cudaFree(a.base);
         a = Arena{};
         const size_t bytes = ps * slots;
         cudaError_t e = cudaMalloc(&a.base, bytes);
         if (e != cudaSuccess) { a = Arena{}; return fail(ctx, NEC_ENOMEM, "cudaMalloc(%zu B workspace) failed: %s", bytes, cudaGetErrorString(e)); }
-        a.bytes = bytes; a.n = n; a.n_slots = slots; a.dist_bytes = dist_bytes; a.qcap = qcap; a.max_levels = max_levels;
+        a.bytes = bytes; a.n = n; a.n_slots = slots; a.dist_bytes = dist_bytes; a.qcap = qcap; a.max_levels = max_levels; a.ksrc = ksrc;
         // planes are grouped by kind so that one memset clears all slots' masks / partial loads
         uint8_t *p = (uint8_t *)a.base;
         auto carve = [&](size_t per_slot) { uint8_t *r = p; p += align_up(per_slot, 256) * slots; return r; };
-        a.dist = carve((size_t)n * nec::kLanes * dist_bytes);      a.dist_stride = align_up((size_t)n * nec::kLanes * dist_bytes, 256);
-        a.q = (double *)carve((size_t)n * nec::kLanes * 8);         a.q_stride = align_up((size_t)n * nec::kLanes * 8, 256) / 8;
-        a.mask = (uint32_t *)carve((size_t)n * 3 * 4);              a.mask_stride = align_up((size_t)n * 3 * 4, 256) / 4;
+        const size_t mask_b = ksrc / 8, qpitch = align_up(qcap, 64);
+        a.dist = carve((size_t)n * ksrc * dist_bytes);              a.dist_stride = align_up((size_t)n * ksrc * dist_bytes, 256);
+        a.q = (double *)carve((size_t)n * ksrc * 8);                a.q_stride = align_up((size_t)n * ksrc * 8, 256) / 8;
+        a.mask = carve((size_t)n * 4 * mask_b);                     a.mask_stride = align_up((size_t)n * 4 * mask_b, 256);
         a.bslot = (double *)carve((size_t)n * 8);                   a.bslot_stride = align_up((size_t)n * 8, 256) / 8;
-        a.queue = (uint2 *)carve(qcap * 8);                         a.queue_stride = align_up(qcap * 8, 256) / 8;  // pitch; >= qcap
+        a.queue_v = (uint32_t *)carve(qpitch * 4);                  a.queue_stride = qpitch;
+        a.queue_m = carve(qpitch * mask_b);
         a.lvl = (uint32_t *)carve(((size_t)max_levels + 2) * 4);    a.lvl_stride = align_up(((size_t)max_levels + 2) * 4, 256) / 4;
     }
     return NEC_OK;
@@ -165,20 +182,20 @@ struct MeasureOut {                  // device outputs of the distance-measure m
     uint32_t *reached;
 };
 
-template <typename DistT, int kMode, int kThreads>
+template <typename DistT, int kMode, int kThreads, int kSrc>
 int launch_engine_t(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots) {
-    constexpr size_t smem = nec::engine_smem_bytes<DistT, kThreads>();
+    constexpr size_t smem = nec::engine_smem_bytes<DistT, kThreads, kSrc>();
     static bool attr_done = false;                      // per instantiation
     if (!attr_done && smem > 48 * 1024) {
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::vertex_load_engine<DistT, kMode, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::vertex_load_engine<DistT, kMode, kThreads, kSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    nec::vertex_load_engine<DistT, kMode, kThreads><<<slots, kThreads, smem, ctx->stream>>>(p);
+    nec::vertex_load_engine<DistT, kMode, kThreads, kSrc><<<slots, kThreads, smem, ctx->stream>>>(p);
     NEC_CUDA(ctx, cudaGetLastError());
     return NEC_OK;
 }
 
-template <typename DistT, int kMode>
+template <typename DistT, int kMode, int kSrc = 32>
 int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
                   uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk,
                   const MeasureOut *mo = nullptr) {
@@ -191,13 +208,13 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.q_base = a.q; p.q_stride = a.q_stride;
     p.mask_base = a.mask; p.mask_stride = a.mask_stride;
     p.bslot_base = a.bslot; p.bslot_stride = a.bslot_stride;
-    p.queue_base = a.queue; p.queue_stride = a.queue_stride;   // pitch doubles as capacity
+    p.queue_v_base = a.queue_v; p.queue_m_base = a.queue_m; p.queue_stride = a.queue_stride; p.queue_cap = a.qcap;
     p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride;
     p.max_levels = a.max_levels;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
     if (mo) { p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
-    const int rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512>(ctx, p, slots);
+    const int rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024, kSrc>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512, kSrc>(ctx, p, slots);
     if (rc != NEC_OK) return rc;
     ctx->stats.kernel_launches++;
     return NEC_OK;
@@ -205,8 +222,8 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
 
 int engine_occupancy(nec_ctx *ctx) {
     int o8 = 0, o32 = 0;
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, 0, 512>, 512, nec::engine_smem_bytes<uint8_t, 512>()));
-    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0, 512>, 512, nec::engine_smem_bytes<uint32_t, 512>()));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o8, nec::vertex_load_engine<uint8_t, 0, 512, 32>, 512, nec::engine_smem_bytes<uint8_t, 512, 32>()));
+    NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0, 512, 32>, 512, nec::engine_smem_bytes<uint32_t, 512, 32>()));
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
     return NEC_OK;
@@ -228,20 +245,34 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     for (uint32_t k = 0; k < n_sources; ++k)
         if (h_sources[k] >= n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, n);
 
-    const uint32_t n_batches = (n_sources + nec::kLanes - 1) / nec::kLanes;
+    // batch width: 64 sources per batch once there is at least one such batch per SM (the bit-parallel
+    // forward pass costs the same per adjacency entry at either width), else 32 for more parallelism
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    // -- provided the workspace budget holds one 64-wide slot per SM (a slot's state doubles with the
+    // width; with fewer slots than SMs the narrower batches win: same sources in flight, more CTAs)
+    uint32_t ksrc = 32u;
+    if (!debug && (n_sources + 63) / 64 >= sms) {
+        ArenaPlan plan64{};
+        int prc = plan_arena(ctx, n, 1, sms, 64u, plan64);
+        if (prc != NEC_OK) return prc;
+        if (plan64.slots >= sms) ksrc = 64u;
+    }
+    if (!debug && getenv("NEC_BATCH_WIDTH")) ksrc = atoi(getenv("NEC_BATCH_WIDTH")) == 64 ? 64u : 32u;
+    const uint32_t n_batches32 = (n_sources + 31) / 32;
+    const uint32_t n_batches = (n_sources + ksrc - 1) / ksrc;
     ctx->stats.n_batches = n_batches;
+    ctx->stats.batch_width = ksrc;
     int rc;
     if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
-    if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches32)) != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, n_batches, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
     // ---- pass 1: 8-bit distances -----------------------------------------------------
-    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
     uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)ctx->occ_u8 * sms);
     if (debug) want = 1;
-    if ((rc = ensure_arena(ctx, n, 1, want)) != NEC_OK) return rc;
+    if ((rc = ensure_arena(ctx, n, 1, want, ksrc)) != NEC_OK) return rc;
     uint32_t slots = std::min<uint32_t>(want, ctx->arena.n_slots);
     // large graphs (beyond the mid engine) and memory-limited slot counts: 1024-thread CTAs, one per SM.
     // Same 32 warps per SM as 2 x 512, but half the resident slots (less HBM state in flight, smaller
@@ -250,12 +281,16 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     if (getenv("NEC_BATCHED_WIDE")) ctx->wide_ctas = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
     if (ctx->wide_ctas) slots = std::min<uint32_t>(slots, sms);
     const Arena &a = ctx->arena;
-    NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * sizeof(uint32_t) * slots, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * slots, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = mo    ? launch_engine<uint8_t, 2>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr, mo)
-       : debug ? launch_engine<uint8_t, 1>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
-               : launch_engine<uint8_t, 0>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
+    if (ksrc == 64)
+        rc = mo ? launch_engine<uint8_t, 2, 64>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr, mo)
+                : launch_engine<uint8_t, 0, 64>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
+    else
+        rc = mo    ? launch_engine<uint8_t, 2>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr, mo)
+           : debug ? launch_engine<uint8_t, 1>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, dbg_npred, dbg_bk)
+                   : launch_engine<uint8_t, 0>(ctx, g, n_sources, nullptr, n_batches, include_endpoints, slots, nullptr, nullptr);
     if (rc != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     if (!mo) {
@@ -279,10 +314,12 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
     ctx->stats.engine_ms = ms;
 
-    std::vector<uint32_t> deep;
+    std::vector<uint32_t> deep;                     // 32-source batch ids for the 32-bit distance pass
     for (uint32_t b = 0; b < n_batches; ++b) {
-        if (status[b] == nec::kTooDeep) deep.push_back(b);
-        else if (status[b] == nec::kQueueOverflow)
+        if (status[b] == nec::kTooDeep) {
+            if (ksrc == 32) deep.push_back(b);
+            else { deep.push_back(2 * b); if (2 * b + 1 < n_batches32) deep.push_back(2 * b + 1); }
+        } else if (status[b] == nec::kQueueOverflow)
             return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
         else if (status[b] != nec::kDone)
             return fail(ctx, NEC_EINTERNAL, "batch %u was not processed (status %u)", b, (unsigned)status[b]);
@@ -297,6 +334,8 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         if (!mo) cudaMemcpyAsync(d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
         if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, deep.size())) != NEC_OK) { cudaFree(d_keep); return rc; }
         cudaMemcpyAsync(ctx->d_worklist, deep.data(), deep.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemsetAsync(ctx->d_status, 0, n_batches32, ctx->stream);
+        status.assign(n_batches32, 0);
         uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
         if (debug) want2 = 1;
         ctx->wide_ctas = false;
@@ -304,7 +343,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         if ((rc = ensure_arena(ctx, n, 4, want2)) != NEC_OK) { cudaFree(d_keep); return rc; }
         const Arena &w = ctx->arena;
         uint32_t slots2 = std::min<uint32_t>(want2, w.n_slots);
-        cudaMemsetAsync(w.mask, 0, w.mask_stride * sizeof(uint32_t) * slots2, ctx->stream);
+        cudaMemsetAsync(w.mask, 0, w.mask_stride * slots2, ctx->stream);
         cudaMemsetAsync(w.bslot, 0, w.bslot_stride * sizeof(double) * slots2, ctx->stream);
         cudaEventRecord(ctx->ev0, ctx->stream);
         rc = mo    ? launch_engine<uint32_t, 2>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr, mo)
@@ -319,7 +358,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
             ctx->stats.kernel_launches += 2;
         }
         cudaEventRecord(ctx->ev1, ctx->stream);
-        cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(status.data(), ctx->d_status, n_batches32, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         cudaFree(d_keep);

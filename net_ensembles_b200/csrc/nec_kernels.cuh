@@ -63,9 +63,12 @@ struct EngineParams {
     // per-slot arenas (slot = blockIdx.x)
     uint8_t *dist_base;   size_t dist_stride;   // bytes per slot
     double *q_base;       size_t q_stride;      // doubles per slot
-    uint32_t *mask_base;  size_t mask_stride;   // u32 per slot (3n: seen, next[even], next[odd])
+    uint8_t *mask_base;   size_t mask_stride;   // bytes per slot (n records of 4 masks: seen, next[even], next[odd], -; u32 or u64 each)
     double *bslot_base;   size_t bslot_stride;  // doubles per slot (n)
-    uint2 *queue_base;    size_t queue_stride;  // entries per slot (= capacity)
+    uint32_t *queue_v_base;                     // level queues: vertex ids ...
+    uint8_t *queue_m_base;                      // ... and their source masks (u32 or u64 per entry)
+    size_t queue_stride;                        // entries per slot (pitch)
+    size_t queue_cap;                           // usable entries per slot
     uint32_t *lvl_base;   size_t lvl_stride;    // u32 per slot (max_levels + 2)
     uint32_t max_levels;                        // deepest level index the slot can record
     // outputs
@@ -121,22 +124,57 @@ __device__ __forceinline__ int tile_owner(uint32_t incl, uint32_t t) {
     return lo;
 }
 
+// Batch width: 32 sources (one per lane) or 64 (two per lane: sources `lane` and `lane + 32`).  The
+// forward pass is bit-parallel, so its cost per adjacency entry does not depend on the width; the
+// backward pass reads one distance row per adjacency entry whatever the width (a 64 B row is one full
+// DRAM transaction where a 32 B row wastes half of one).  Wide batches double the per-slot state.
+template <int kSrc> struct SrcTraits;
+template <> struct SrcTraits<32> {
+    using Mask = uint32_t;
+    using Stage = uint2;                                  // (neighbour id, owner's source mask)
+    static __device__ __forceinline__ Stage stage(uint32_t x, Mask m) { return make_uint2(x, m); }
+    static __device__ __forceinline__ uint32_t half(const Stage &e, int) { return e.y; }
+    static __device__ __forceinline__ bool any(const Stage &e) { return e.y != 0; }
+    static __device__ __forceinline__ uint32_t popc(Mask m) { return (uint32_t)__popc(m); }
+};
+template <> struct SrcTraits<64> {
+    using Mask = unsigned long long;
+    using Stage = uint4;                                  // (neighbour id, mask low, mask high, -)
+    static __device__ __forceinline__ Stage stage(uint32_t x, Mask m) { return make_uint4(x, (uint32_t)m, (uint32_t)(m >> 32), 0u); }
+    static __device__ __forceinline__ uint32_t half(const Stage &e, int h) { return h ? e.z : e.y; }
+    static __device__ __forceinline__ bool any(const Stage &e) { return (e.y | e.z) != 0; }
+    static __device__ __forceinline__ uint32_t popc(Mask m) { return (uint32_t)__popcll(m); }
+};
+
+__device__ __forceinline__ unsigned long long atom_or_if(bool pred, unsigned long long *addr, unsigned long long val) {
+    unsigned long long old = ~0ull;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.global.or.b64 %0, [%1], %2;\n\t}"
+                 : "+l"(old) : "l"(addr), "l"(val), "r"((uint32_t)pred) : "memory");
+    return old;
+}
+
 // The engine.  One CTA = one slot; loops over its batches.
 // kMode 0: vertex_load; 1: vertex_load + per-(vertex,lane) debug planes (nec_bfs_debug);
 // 2: distance measures only — the forward pass alone, per source eccentricity / sum of distances /
 //    reached count (diameter, closeness_centrality: reference generic_graph.rs:1116-1144, :1387-1403).
-template <typename DistT, int kThreads>
+template <typename DistT, int kThreads, int kSrc>
 constexpr size_t engine_smem_bytes() {
-    return (size_t)(kThreads / 32) * (2 * 32 * sizeof(uint2) + (sizeof(DistT) == 1 ? 2 * 32 * 32 : 0));
+    return (size_t)(kThreads / 32) * (2 * 32 * sizeof(typename SrcTraits<kSrc>::Stage) + (sizeof(DistT) == 1 ? 2 * 32 * kSrc : 0));
 }
 
-template <typename DistT, int kMode, int kEngineThreads>
+template <typename DistT, int kMode, int kEngineThreads, int kSrc>
 __global__ void __launch_bounds__(kEngineThreads, kEngineThreads == 512 ? 2 : 1)
 vertex_load_engine(const EngineParams p) {
+    using ST = SrcTraits<kSrc>;
+    using Mask = typename ST::Mask;
+    using Stage = typename ST::Stage;
+    constexpr int kH = kSrc / 32;                        // sources per lane
+    constexpr int kUnrollB = kUnroll / kH;               // neighbour rows per backward step (kUnroll loads in flight per lane)
     constexpr bool kDebug = kMode == 1;
     constexpr bool kMeasure = kMode == 2;
     constexpr uint32_t kInf = DistTraits<DistT>::kInf;
     constexpr int kWarps = kEngineThreads / 32;
+    static_assert(!kDebug || kSrc == 32, "debug planes are 32 sources wide");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
@@ -144,25 +182,26 @@ vertex_load_engine(const EngineParams p) {
 
     DistT *__restrict__ dist = reinterpret_cast<DistT *>(p.dist_base + (size_t)blockIdx.x * p.dist_stride);
     double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
-    uint32_t *seen = p.mask_base + (size_t)blockIdx.x * p.mask_stride;
-    uint32_t *next_even = seen + n;
-    uint32_t *next_odd = next_even + n;
+    // per-vertex mask record {seen, next[even level], next[odd level], -}: one 16 B / 32 B sector, so the
+    // atomics that follow the `seen` test of a neighbour hit the sector that test just fetched
+    Mask *rec = reinterpret_cast<Mask *>(p.mask_base + (size_t)blockIdx.x * p.mask_stride);
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
-    uint2 *__restrict__ queue = p.queue_base + (size_t)blockIdx.x * p.queue_stride;
+    uint32_t *__restrict__ queue_v = p.queue_v_base + (size_t)blockIdx.x * p.queue_stride;
+    Mask *__restrict__ queue_m = reinterpret_cast<Mask *>(p.queue_m_base + (size_t)blockIdx.x * p.queue_stride * sizeof(Mask));
     uint32_t *__restrict__ lvl = p.lvl_base + (size_t)blockIdx.x * p.lvl_stride;
-    const uint32_t qcap = (uint32_t)p.queue_stride;
+    const uint32_t qcap = (uint32_t)p.queue_cap;
     const uint32_t level_limit = p.max_levels < DistTraits<DistT>::kMaxLevel ? p.max_levels : DistTraits<DistT>::kMaxLevel;
 
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
-    __shared__ unsigned long long s_msum[kLanes];        // kMode 2: per source of the batch
-    __shared__ uint32_t s_mreach[kLanes], s_mecc[kLanes];
+    __shared__ unsigned long long s_msum[kSrc];          // kMode 2: per source of the batch
+    __shared__ uint32_t s_mreach[kSrc], s_mecc[kSrc];
     __shared__ unsigned long long s_cnt[3];
-    constexpr bool kStageRows = sizeof(DistT) == 1;      // 32 B distance rows are staged through shared memory
+    constexpr bool kStageRows = sizeof(DistT) == 1;      // byte distance rows are staged through shared memory
     extern __shared__ __align__(16) unsigned char engine_smem[];
     // backward: (neighbour, owner's source mask) per flattened entry; staged distance rows
-    uint2 (*s_stage)[2][32] = reinterpret_cast<uint2 (*)[2][32]>(engine_smem);
-    unsigned char (*s_rows)[2][32][32] = reinterpret_cast<unsigned char (*)[2][32][32]>(engine_smem + (size_t)kWarps * 2 * 32 * sizeof(uint2));
+    Stage (*s_stage)[2][32] = reinterpret_cast<Stage (*)[2][32]>(engine_smem);
+    unsigned char (*s_rows)[2][32][kSrc] = reinterpret_cast<unsigned char (*)[2][32][kSrc]>(engine_smem + (size_t)kWarps * 2 * 32 * sizeof(Stage));
 
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
@@ -175,26 +214,35 @@ vertex_load_engine(const EngineParams p) {
         long long t_phase = clock64();
         // ---- reset: only `seen` (next[] cleans itself; stale dist/q are never read because the
         //      backward pass touches lane k of a row only if source k reached that vertex) -----
-        for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) __stcg(&seen[v], 0u);
+        // (whole records are cleared: full-sector stores; the next[] words are zero already)
+        {
+            uint4 *r16 = reinterpret_cast<uint4 *>(rec);
+            const size_t n16 = (size_t)n * 4 * sizeof(Mask) / 16;
+            for (size_t i = threadIdx.x; i < n16; i += kEngineThreads) __stcg(&r16[i], make_uint4(0u, 0u, 0u, 0u));
+        }
         if (kDebug) {
-            const size_t n16 = ((size_t)n * kLanes * sizeof(DistT)) / 16;
+            const size_t n16 = ((size_t)n * kSrc * sizeof(DistT)) / 16;
             uint4 *d16 = reinterpret_cast<uint4 *>(dist);
             const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             for (size_t i = threadIdx.x; i < n16; i += kEngineThreads) d16[i] = inf4;
         }
         if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; }
-        if (kMeasure && threadIdx.x < kLanes) { s_msum[threadIdx.x] = 0; s_mreach[threadIdx.x] = 0; s_mecc[threadIdx.x] = 0; }
+        if (kMeasure && threadIdx.x < kSrc) { s_msum[threadIdx.x] = 0; s_mreach[threadIdx.x] = 0; s_mecc[threadIdx.x] = 0; }
         __syncthreads();
 
         // ---- seed level 0: bit k <-> source k of the batch ------------------------------
         if (warp == 0) {
-            const uint32_t sidx = batch * kLanes + lane;
-            if (sidx < p.n_sources) {
-                const uint32_t s = p.sources[sidx];
-                dist[(size_t)s * kLanes + lane] = (DistT)0;
-                atomicOr(&seen[s], 1u << lane);
-                const uint32_t old = atomicOr(&next_even[s], 1u << lane);
-                if (old == 0) queue[atomicAdd(&s_tail, 1u)].x = s;
+#pragma unroll
+            for (int h = 0; h < kH; ++h) {
+                const uint32_t k = h * 32 + lane;
+                const uint32_t sidx = batch * kSrc + k;
+                if (sidx < p.n_sources) {
+                    const uint32_t s = p.sources[sidx];
+                    dist[(size_t)s * kSrc + k] = (DistT)0;
+                    atomicOr(&rec[(size_t)s * 4], (Mask)1 << k);
+                    const Mask old = atomicOr(&rec[(size_t)s * 4 + 1], (Mask)1 << k);
+                    if (old == 0) queue_v[atomicAdd(&s_tail, 1u)] = s;
+                }
             }
         }
 
@@ -212,46 +260,57 @@ vertex_load_engine(const EngineParams p) {
             if (threadIdx.x == 0) lvl[level] = qbeg;
             if (qend == qbeg) break;                 // level `level` is empty: done
             if (level >= level_limit) { too_deep = true; break; }
-            uint32_t *next_cur = (level & 1) ? next_odd : next_even;
-            uint32_t *next_nxt = (level & 1) ? next_even : next_odd;
+            Mask *next_cur = rec + 1 + (level & 1);          // word of the record, indexed [4 * vertex]
+            Mask *next_nxt = rec + 2 - (level & 1);
             const DistT cur_d = (DistT)level;
 
             for (uint32_t tile = qbeg + warp * 32; tile < qend; tile += kWarps * 32) {
                 const uint32_t idx = tile + lane;
-                uint32_t m = 0, rs = 0, deg = 0, u = 0;
+                Mask m = 0;
+                uint32_t rs = 0, deg = 0, u = 0;
                 if (idx < qend) {
-                    u = queue[idx].x;
-                    m = __ldcg(&next_cur[u]);
-                    __stcg(&next_cur[u], 0u);        // self-cleaning: this parity is reused at level+2
-                    if (!kMeasure) queue[idx].y = m; // the backward pass reads (vertex, mask)
+                    u = queue_v[idx];
+                    m = __ldcg(&next_cur[(size_t)u * 4]);
+                    __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // self-cleaning: this parity is reused at level+2
+                    if (!kMeasure) queue_m[idx] = m; // the backward pass reads (vertex, mask)
                     rs = __ldg(p.row_ptr + u);
                     deg = __ldg(p.row_ptr + u + 1) - rs;
-                    const uint32_t pc = __popc(m);
+                    const uint32_t pc = ST::popc(m);
                     b_reached += pc;
                     b_edges += pc * deg;
                     b_visits += 1;
                 }
                 // distance rows of the dequeued entries: the mask is final now, so each row's bytes are
-                // written by ONE store instruction (lane k = source k) instead of bit by bit at discovery
+                // written by ONE store instruction per 32 sources (lane k = sources k, k+32) instead of
+                // bit by bit at discovery
                 if (kMeasure) {
                     // source k has popc(ballot(bit k)) vertices of this tile on the current level
-                    uint32_t mine_cnt = 0;
+                    uint32_t mine_cnt[kH];
 #pragma unroll
-                    for (int k = 0; k < kLanes; ++k) {
-                        const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, (m >> k) & 1u));
-                        if (lane == k) mine_cnt = c;
+                    for (int h = 0; h < kH; ++h) mine_cnt[h] = 0;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) {
+                            const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, (uint32_t)(m >> (h * 32 + k)) & 1u));
+                            if (lane == k) mine_cnt[h] = c;
+                        }
                     }
-                    if (mine_cnt) {
-                        atomicAdd(&s_msum[lane], (unsigned long long)mine_cnt * level);
-                        atomicAdd(&s_mreach[lane], mine_cnt);
-                        atomicMax(&s_mecc[lane], level);
-                    }
+#pragma unroll
+                    for (int h = 0; h < kH; ++h)
+                        if (mine_cnt[h]) {
+                            atomicAdd(&s_msum[h * 32 + lane], (unsigned long long)mine_cnt[h] * level);
+                            atomicAdd(&s_mreach[h * 32 + lane], mine_cnt[h]);
+                            atomicMax(&s_mecc[h * 32 + lane], level);
+                        }
                 } else {
                     const uint32_t n_ent = min(32u, qend - tile);
                     for (uint32_t e = 0; e < n_ent; ++e) {
                         const uint32_t u_e = __shfl_sync(0xFFFFFFFFu, u, e);
-                        const uint32_t m_e = __shfl_sync(0xFFFFFFFFu, m, e);
-                        if ((m_e >> lane) & 1u) dist[(size_t)u_e * kLanes + lane] = cur_d;
+                        const Mask m_e = __shfl_sync(0xFFFFFFFFu, m, e);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h)
+                            if ((uint32_t)(m_e >> (h * 32 + lane)) & 1u) dist[(size_t)u_e * kSrc + h * 32 + lane] = cur_d;
                     }
                 }
                 const uint32_t incl = warp_inclusive_scan(deg, lane);
@@ -260,14 +319,15 @@ vertex_load_engine(const EngineParams p) {
                 // kFwdUnroll flattened entries per lane and step: every stage below is a batch of
                 // independent memory operations (col -> seen -> atomicOr(seen) -> atomicOr(next)).
                 for (uint32_t t0 = 0; t0 < total; t0 += 32 * kFwdUnroll) {
-                    uint32_t x[kFwdUnroll], fresh[kFwdUnroll];
+                    uint32_t x[kFwdUnroll];
+                    Mask fresh[kFwdUnroll];
 #pragma unroll
                     for (int j = 0; j < kFwdUnroll; ++j) {
                         const uint32_t t = t0 + j * 32 + lane;
                         const int o = tile_owner(incl, t);
                         const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
                         const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
-                        const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o);
+                        const Mask m_o = __shfl_sync(0xFFFFFFFFu, m, o);
                         x[j] = 0; fresh[j] = 0;
                         if (t < total) { x[j] = __ldg(p.col_idx + rs_o + (t - off_o)); fresh[j] = m_o; }
                     }
@@ -275,24 +335,24 @@ vertex_load_engine(const EngineParams p) {
                     // atomics of a stage are issued before any result is consumed (predicated PTX, no
                     // branches, so the compiler cannot serialise the round trips)
                     {
-                        uint32_t sv[kFwdUnroll];
+                        Mask sv[kFwdUnroll];
 #pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) sv[j] = fresh[j] ? __ldcg(&seen[x[j]]) : 0xFFFFFFFFu;
+                        for (int j = 0; j < kFwdUnroll; ++j) sv[j] = fresh[j] ? __ldcg(&rec[(size_t)x[j] * 4]) : ~(Mask)0;
 #pragma unroll
                         for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~sv[j];
                     }
                     {   // exact filter: racing lanes each keep disjoint bits
-                        uint32_t old[kFwdUnroll];
+                        Mask old[kFwdUnroll];
 #pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &seen[x[j]], fresh[j]);
+                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &rec[(size_t)x[j] * 4], fresh[j]);
 #pragma unroll
                         for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~old[j];
                     }
                     uint32_t enq_bits = 0;
                     {
-                        uint32_t old[kFwdUnroll];
+                        Mask old[kFwdUnroll];
 #pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &next_nxt[x[j]], fresh[j]);
+                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &next_nxt[(size_t)x[j] * 4], fresh[j]);
 #pragma unroll
                         for (int j = 0; j < kFwdUnroll; ++j) enq_bits |= (fresh[j] != 0 && old[j] == 0 ? 1u : 0u) << j;
                     }
@@ -307,7 +367,7 @@ vertex_load_engine(const EngineParams p) {
                             base = __shfl_sync(0xFFFFFFFFu, base, leader);
                             if (enqueue) {
                                 const uint32_t pos = base + __popc(bal & lane_lt);
-                                if (pos < qcap) queue[pos].x = x[j];
+                                if (pos < qcap) queue_v[pos] = x[j];
                                 else s_fail = 1;
                             }
                         }
@@ -323,7 +383,7 @@ vertex_load_engine(const EngineParams p) {
 
         if (too_deep || failed) {
             // leave the slot clean for the next batch: drop pending mask bits (rare path)
-            for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) { __stcg(&next_even[v], 0u); __stcg(&next_odd[v], 0u); }
+            for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) { __stcg(&rec[(size_t)v * 4 + 1], (Mask)0); __stcg(&rec[(size_t)v * 4 + 2], (Mask)0); }
             if (threadIdx.x == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
             __syncthreads();
             continue;
@@ -335,8 +395,8 @@ vertex_load_engine(const EngineParams p) {
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
         if (kMeasure) {
             if (depth > my_depth) my_depth = depth;
-            if (threadIdx.x < kLanes) {
-                const uint32_t sidx = batch * kLanes + threadIdx.x;
+            if (threadIdx.x < kSrc) {
+                const uint32_t sidx = batch * kSrc + threadIdx.x;
                 if (sidx < p.n_sources) {
                     if (p.out_ecc) p.out_ecc[sidx] = s_mecc[threadIdx.x];
                     if (p.out_sumdist) p.out_sumdist[sidx] = s_msum[threadIdx.x];
@@ -355,10 +415,10 @@ vertex_load_engine(const EngineParams p) {
             const uint32_t d_succ = l + 1, d_pred = l - 1;
             for (uint32_t tile = lb + warp * 32; tile < le; tile += kWarps * 32) {
                 const uint32_t idx = tile + lane;
-                uint32_t w = 0, m = 0, rs = 0, deg = 0;
+                uint32_t w = 0, rs = 0, deg = 0;
+                Mask m = 0;
                 if (idx < le) {
-                    const uint2 ent = queue[idx];
-                    w = ent.x; m = ent.y;
+                    w = queue_v[idx]; m = queue_m[idx];
                     rs = __ldg(p.row_ptr + w);
                     deg = __ldg(p.row_ptr + w + 1) - rs;
                 }
@@ -367,20 +427,25 @@ vertex_load_engine(const EngineParams p) {
                 const uint32_t off = incl - deg;
                 // running state of the entry whose row is being consumed (warp-uniform `cur`)
                 int cur = -1;
-                uint32_t cur_end = 0, npred = 0;
-                double acc = 0.0, my_total = 0.0;
+                uint32_t cur_end = 0, npred[kH];
+                double acc[kH], my_total = 0.0;
+#pragma unroll
+                for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; }
 
                 auto finish_entry = [&]() {
                     const uint32_t w_c = __shfl_sync(0xFFFFFFFFu, w, cur);
-                    const uint32_t m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
-                    const double bk = 1.0 + acc;
+                    const Mask m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
                     double contrib = 0.0;
-                    if ((m_c >> lane) & 1u) {
-                        q[(size_t)w_c * kLanes + lane] = bk / (double)npred;
-                        contrib = p.include_endpoints ? bk : bk - 1.0;
-                        if (kDebug) {
-                            p.dbg_npred[(size_t)w_c * kLanes + lane] = npred;
-                            p.dbg_bk[(size_t)w_c * kLanes + lane] = bk;
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) {
+                        const double bk = 1.0 + acc[h];
+                        if ((uint32_t)(m_c >> (h * 32 + lane)) & 1u) {
+                            q[(size_t)w_c * kSrc + h * 32 + lane] = bk / (double)npred[h];
+                            contrib += p.include_endpoints ? bk : bk - 1.0;
+                            if (kDebug) {
+                                p.dbg_npred[(size_t)w_c * kSrc + h * 32 + lane] = npred[h];
+                                p.dbg_bk[(size_t)w_c * kSrc + h * 32 + lane] = bk;
+                            }
                         }
                     }
                     const double tot = warp_sum(contrib);
@@ -389,25 +454,27 @@ vertex_load_engine(const EngineParams p) {
 
                 // Flattened adjacency entries are consumed in chunks of 32.  Two-deep pipeline per warp:
                 // chunk s+2's neighbour ids are being loaded (registers), chunk s+1's distance rows are
-                // in flight to shared memory (cp.async, 32 rows x 32 B per chunk, two lanes per row),
-                // chunk s is consumed: one LDS byte per (row, lane), then the predicated q loads.
-                auto edge_of = [&](uint32_t t0) -> uint2 {        // (neighbour id, owner's source mask) of flattened entry t0+lane
+                // in flight to shared memory (cp.async, 32 rows x kSrc B per chunk, 16 B pieces),
+                // chunk s is consumed: one LDS byte per (row, source), then the predicated q loads.
+                auto edge_of = [&](uint32_t t0) -> Stage {        // (neighbour id, owner's source mask) of flattened entry t0+lane
                     const uint32_t t = t0 + lane;
                     const int o = tile_owner(incl, t);
                     const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
                     const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
-                    const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o);
-                    return t < total ? make_uint2(__ldg(p.col_idx + rs_o + (t - off_o)), m_o) : make_uint2(0u, 0u);
+                    const Mask m_o = __shfl_sync(0xFFFFFFFFu, m, o);
+                    return t < total ? ST::stage(__ldg(p.col_idx + rs_o + (t - off_o)), m_o) : ST::stage(0u, (Mask)0);
                 };
                 auto stage_rows = [&](int buf) {                  // rows of the chunk whose edges sit in s_stage[warp][buf]
                     if constexpr (kStageRows) {
+                        constexpr int kPieces = kSrc / 16;        // 16 B pieces per row
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int r = h * 16 + (lane >> 1);
-                            const uint2 e = s_stage[warp][buf][r];
-                            if (e.y) {
-                                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rows[warp][buf][r][(lane & 1) * 16]);
-                                const unsigned char *src = reinterpret_cast<const unsigned char *>(dist) + (size_t)e.x * kLanes + (lane & 1) * 16;
+                        for (int it = 0; it < kPieces; ++it) {
+                            const int r = it * (32 / kPieces) + lane / kPieces;
+                            const int part = lane % kPieces;
+                            const Stage e = s_stage[warp][buf][r];
+                            if (ST::any(e)) {
+                                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rows[warp][buf][r][part * 16]);
+                                const unsigned char *src = reinterpret_cast<const unsigned char *>(dist) + (size_t)e.x * kSrc + part * 16;
                                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                             }
                         }
@@ -415,49 +482,62 @@ vertex_load_engine(const EngineParams p) {
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 };
                 const uint32_t n_chunks = (total + 31) / 32;
-                uint2 st_next = edge_of(0);
+                Stage st_next = edge_of(0);
                 __syncwarp();
                 s_stage[warp][0][lane] = st_next;
                 __syncwarp();
                 stage_rows(0);
-                st_next = n_chunks > 1 ? edge_of(32) : make_uint2(0u, 0u);
+                st_next = n_chunks > 1 ? edge_of(32) : ST::stage(0u, (Mask)0);
                 for (uint32_t sc = 0; sc < n_chunks; ++sc) {
                     const int buf = sc & 1;
                     const uint32_t t0 = sc * 32;
                     s_stage[warp][buf ^ 1][lane] = st_next;       // chunk sc+1 (zeros past the end); buffer was drained at sc-1
                     __syncwarp();
                     stage_rows(buf ^ 1);
-                    st_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : make_uint2(0u, 0u);
+                    st_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : ST::stage(0u, (Mask)0);
                     asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk sc's rows have landed (this lane's copies)
                     __syncwarp();                                          // ... and every other lane's
                     const uint32_t cnt = min(32u, total - t0);
-                    for (uint32_t c0 = 0; c0 < cnt; c0 += kUnroll) {
-                        uint32_t dx[kUnroll];
-                        double qv[kUnroll];
+                    for (uint32_t c0 = 0; c0 < cnt; c0 += kUnrollB) {
+                        uint32_t dx[kUnrollB][kH];
+                        double qv[kUnrollB][kH];
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj) {
-                            const uint2 e = s_stage[warp][buf][(c0 + jj) & 31];   // broadcast read; mask 0 past the end
-                            const bool act = (e.y >> lane) & 1u;
-                            if constexpr (kStageRows) dx[jj] = act ? (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][lane] : kInf;
-                            else dx[jj] = act ? (uint32_t)dist[(size_t)e.x * kLanes + lane] : kInf;
+                        for (int jj = 0; jj < kUnrollB; ++jj) {
+                            const Stage e = s_stage[warp][buf][(c0 + jj) & 31];   // broadcast read; mask 0 past the end
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) {
+                                const bool act = (ST::half(e, h) >> lane) & 1u;
+                                if constexpr (kStageRows) dx[jj][h] = act ? (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][h * 32 + lane] : kInf;
+                                else dx[jj][h] = act ? (uint32_t)dist[(size_t)e.x * kSrc + h * 32 + lane] : kInf;
+                            }
                         }
-                        uint32_t pred_bits = 0;                                  // bit jj: neighbour jj is a predecessor
+                        uint32_t pred_bits[kH];                                  // bit jj: neighbour jj is a predecessor
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj) {
-                            qv[jj] = (dx[jj] == d_succ) ? q[(size_t)s_stage[warp][buf][(c0 + jj) & 31].x * kLanes + lane] : 0.0;
-                            pred_bits |= (dx[jj] == d_pred ? 1u : 0u) << jj;
+                        for (int h = 0; h < kH; ++h) pred_bits[h] = 0;
+#pragma unroll
+                        for (int jj = 0; jj < kUnrollB; ++jj) {
+                            const uint32_t xj = s_stage[warp][buf][(c0 + jj) & 31].x;
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) {
+                                qv[jj][h] = (dx[jj][h] == d_succ) ? q[(size_t)xj * kSrc + h * 32 + lane] : 0.0;
+                                pred_bits[h] |= (dx[jj][h] == d_pred ? 1u : 0u) << jj;
+                            }
                         }
 #pragma unroll
-                        for (int jj = 0; jj < kUnroll; ++jj) {   // CSR order: fixes the rounding
+                        for (int jj = 0; jj < kUnrollB; ++jj) {  // CSR order: fixes the rounding
                             const uint32_t tt = t0 + c0 + jj;
                             if (c0 + jj < cnt) {
                                 if (tt >= cur_end) {              // warp-uniform: next entry's row starts
                                     if (cur >= 0) finish_entry();
                                     do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
-                                    acc = 0.0; npred = 0;
+#pragma unroll
+                                    for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; }
                                 }
-                                acc += qv[jj];
-                                npred += (pred_bits >> jj) & 1u;
+#pragma unroll
+                                for (int h = 0; h < kH; ++h) {
+                                    acc[h] += qv[jj][h];
+                                    npred[h] += (pred_bits[h] >> jj) & 1u;
+                                }
                             }
                         }
                     }
@@ -473,17 +553,17 @@ vertex_load_engine(const EngineParams p) {
             // the sources themselves (level 0) get bk but no load contribution
             const uint32_t lb = lvl[0], le = lvl[1];
             for (uint32_t idx = lb + warp; idx < le; idx += kWarps) {
-                const uint2 ent = queue[idx];
-                const bool active = (ent.y >> lane) & 1u;
-                const uint32_t rs = p.row_ptr[ent.x], re = p.row_ptr[ent.x + 1];
+                const uint32_t ex = queue_v[idx];
+                const bool active = (uint32_t)(queue_m[idx] >> lane) & 1u;
+                const uint32_t rs = p.row_ptr[ex], re = p.row_ptr[ex + 1];
                 double acc = 0.0;
                 for (uint32_t e = rs; e < re; ++e) {
                     const uint32_t x = p.col_idx[e];
-                    if (active && (uint32_t)dist[(size_t)x * kLanes + lane] == 1u) acc += q[(size_t)x * kLanes + lane];
+                    if (active && (uint32_t)dist[(size_t)x * kSrc + lane] == 1u) acc += q[(size_t)x * kSrc + lane];
                 }
                 if (active) {
-                    p.dbg_npred[(size_t)ent.x * kLanes + lane] = 0;
-                    p.dbg_bk[(size_t)ent.x * kLanes + lane] = 1.0 + acc;
+                    p.dbg_npred[(size_t)ex * kSrc + lane] = 0;
+                    p.dbg_bk[(size_t)ex * kSrc + lane] = 1.0 + acc;
                 }
             }
         }

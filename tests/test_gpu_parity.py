@@ -3,6 +3,8 @@ identical inputs.  Integer state (distances, predecessor counts) must be exact; 
 exact while they fit in f64; load values agree within relative 1e-9 (absolute floor 1e-9 for
 |x| < 1) — the tolerance BASELINE.json's north_star states, because the GPU summation order
 (pull, lane tree, per-slot partials) differs from the crate's push order."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,10 +16,13 @@ REL = 1e-9
 ENGINES = {"auto": 0, "batched": 1, "mid": 2}
 
 
-@pytest.fixture(params=["batched", "mid"])
-def engine_ctx(ctx, request):
-    """Runs a test once per traversal engine (the C ABI picks by graph size by default)."""
-    ctx.set_engine(ENGINES[request.param])
+@pytest.fixture(params=["batched", "batched64", "mid"])
+def engine_ctx(ctx, request, monkeypatch):
+    """Runs a test once per traversal engine and batch width (the C ABI picks by graph size and source
+    count by default; NEC_BATCH_WIDTH pins the batched engine's 32 / 64 sources per batch)."""
+    ctx.set_engine(ENGINES[request.param.rstrip("64")])
+    if request.param.startswith("batched"):
+        monkeypatch.setenv("NEC_BATCH_WIDTH", "64" if request.param.endswith("64") else "32")
     yield ctx
     ctx.set_engine(0)
 
@@ -326,8 +331,9 @@ def test_differential_fuzz_all_engines(ctx, oracle):
     csr = [csr_from_adj(a) for a in graphs]
     want_t = [oracle.vertex_load(rp, col, True) for rp, col in csr]
     want_f = [oracle.vertex_load(rp, col, False) for rp, col in csr]
-    for engine in (1, 2):
+    for engine, width in ((1, "32"), (1, "64"), (2, "32")):
         ctx.set_engine(engine)
+        os.environ["NEC_BATCH_WIDTH"] = width
         for (rp, col), wt, wf in zip(csr, want_t, want_f):
             dg = ctx.upload(rp, col)
             assert close(dg.vertex_load(True), wt, REL) and close(dg.vertex_load(False), wf, REL)
@@ -336,6 +342,7 @@ def test_differential_fuzz_all_engines(ctx, oracle):
             assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
             dg.free()
     ctx.set_engine(0)
+    del os.environ["NEC_BATCH_WIDTH"]
     outs = ne.vertex_load_batch(ctx, [(rp.astype(np.uint32), col) for rp, col in csr], False)
     for got, wf in zip(outs, want_f):
         assert close(got, wf, REL)
@@ -367,4 +374,28 @@ def test_mid_engine_hub_list_overflow_and_hub_heavy_graphs(ctx, oracle):
     src = np.arange(0, 60000, 1201, dtype=np.uint32)
     assert close(dg.vertex_load_sources(src, True), oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
     assert ctx.stats()["engine"] & 15 in (1, 2)
+    dg.free()
+
+
+def test_wide_batches_are_the_default_for_many_sources(ctx, oracle):
+    """>= 64 sources per SM's worth of batches: the batched engine runs 64 sources per batch (two per
+    lane); a ragged tail batch and sources that repeat are covered."""
+    g = ne.ErEnsembleC(3000, 3.0, 11)                        # many components, isolated vertices
+    rp, col = g.export_csr()
+    dg = ctx.upload(rp, col)
+    ctx.set_engine(1)
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 3000, 64 * 148 + 37).astype(np.uint32)   # with repeats; 37-source tail
+    got = dg.vertex_load_sources(src, True)
+    st = ctx.stats()
+    assert st["batch_width"] == 64 and st["n_batches"] == 149
+    assert close(got, oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
+    ecc, sumd, reached = dg.distance_measures(src)
+    assert ctx.stats()["batch_width"] == 64
+    recc, rsum, rreach = oracle.distance_measures(rp, col, src)
+    assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
+    got = dg.vertex_load_sources(src[:2000], True)
+    assert ctx.stats()["batch_width"] == 32
+    assert close(got, oracle.vertex_load(rp, col, True, sources=src[:2000], threads=0), REL)
+    ctx.set_engine(0)
     dg.free()
