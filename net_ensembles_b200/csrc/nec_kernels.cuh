@@ -212,9 +212,9 @@ vertex_load_engine(const EngineParams p) {
         uint32_t b_reached = 0, b_edges = 0, b_visits = 0;   // per lane, per batch; counted only if the batch completes
 
         long long t_phase = clock64();
-        // ---- reset: only `seen` (next[] cleans itself; stale dist/q are never read because the
-        //      backward pass touches lane k of a row only if source k reached that vertex) -----
-        // (whole records are cleared: full-sector stores; the next[] words are zero already)
+        // ---- reset: only the mask records (whole records: full-sector stores; the next[] words are zero
+        //      already).  Stale dist/q are never used: the backward pass selects source k of a row only if
+        //      k reached that vertex in this batch. -----
         {
             uint4 *r16 = reinterpret_cast<uint4 *>(rec);
             const size_t n16 = (size_t)n * 4 * sizeof(Mask) / 16;
@@ -507,8 +507,11 @@ vertex_load_engine(const EngineParams p) {
 #pragma unroll
                             for (int h = 0; h < kH; ++h) {
                                 const bool act = (ST::half(e, h) >> lane) & 1u;
-                                if constexpr (kStageRows) dx[jj][h] = act ? (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][h * 32 + lane] : kInf;
-                                else dx[jj][h] = act ? (uint32_t)dist[(size_t)e.x * kSrc + h * 32 + lane] : kInf;
+                                if constexpr (kStageRows) {
+                                    // unconditional shared-memory read, then select: faster than a predicated read
+                                    const uint32_t raw = (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][h * 32 + lane];
+                                    dx[jj][h] = act ? raw : kInf;
+                                } else dx[jj][h] = act ? (uint32_t)dist[(size_t)e.x * kSrc + h * 32 + lane] : kInf;
                             }
                         }
                         uint32_t pred_bits[kH];                                  // bit jj: neighbour jj is a predecessor

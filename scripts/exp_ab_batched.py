@@ -24,7 +24,7 @@ if len(sys.argv) > 2:
         st["edge_pairs"] / 2 / (min(ts) * 1e-3) / 1e9), flush=True)
 else:
     which = sys.argv[1] if len(sys.argv) > 1 else "erm"
-    for rep in range(2):
-        for tag in ("ab_old", "ab_new"):
+    for rep in range(int(os.environ.get("AB_REPS", "2"))):
+        for tag in os.environ.get("AB_TAGS", "ab_old,ab_new").split(","):
             env = dict(os.environ, NEC_LIB_PATH=os.path.join(ROOT, "net_ensembles_b200", "lib", tag + ".so"))
             subprocess.run([sys.executable, __file__, which, tag], env=env)
