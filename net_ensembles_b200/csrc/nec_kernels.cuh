@@ -239,7 +239,6 @@ vertex_load_engine(const EngineParams p) {
                 if (sidx < p.n_sources) {
                     const uint32_t s = p.sources[sidx];
                     dist[(size_t)s * kSrc + k] = (DistT)0;
-                    atomicOr(&rec[(size_t)s * 4], (Mask)1 << k);
                     const Mask old = atomicOr(&rec[(size_t)s * 4 + 1], (Mask)1 << k);
                     if (old == 0) queue_v[atomicAdd(&s_tail, 1u)] = s;
                 }
@@ -264,15 +263,27 @@ vertex_load_engine(const EngineParams p) {
             Mask *next_nxt = rec + 2 - (level & 1);
             const DistT cur_d = (DistT)level;
 
+            // mark: the level's vertices become `seen` for their sources BEFORE anything is expanded, so the
+            // expansion needs no atomic on `seen` (a plain test suffices: bits of this and earlier levels are
+            // final, and a source discovered twice on the level being built is caught by the atomic on next[]).
+            // The entry's mask moves to the queue (the backward pass wants it there) and next[] cleans itself.
+            for (uint32_t idx = qbeg + threadIdx.x; idx < qend; idx += kEngineThreads) {
+                const uint32_t u = queue_v[idx];
+                const Mask m = __ldcg(&next_cur[(size_t)u * 4]);
+                const Mask sn = __ldcg(&rec[(size_t)u * 4]);
+                __stcg(&rec[(size_t)u * 4], sn | m);
+                __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // this parity is reused at level+2
+                queue_m[idx] = m;
+            }
+            __syncthreads();
+
             for (uint32_t tile = qbeg + warp * 32; tile < qend; tile += kWarps * 32) {
                 const uint32_t idx = tile + lane;
                 Mask m = 0;
                 uint32_t rs = 0, deg = 0, u = 0;
                 if (idx < qend) {
                     u = queue_v[idx];
-                    m = __ldcg(&next_cur[(size_t)u * 4]);
-                    __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // self-cleaning: this parity is reused at level+2
-                    if (!kMeasure) queue_m[idx] = m; // the backward pass reads (vertex, mask)
+                    m = queue_m[idx];
                     rs = __ldg(p.row_ptr + u);
                     deg = __ldg(p.row_ptr + u + 1) - rs;
                     const uint32_t pc = ST::popc(m);
@@ -340,13 +351,6 @@ vertex_load_engine(const EngineParams p) {
                         for (int j = 0; j < kFwdUnroll; ++j) sv[j] = fresh[j] ? __ldcg(&rec[(size_t)x[j] * 4]) : ~(Mask)0;
 #pragma unroll
                         for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~sv[j];
-                    }
-                    {   // exact filter: racing lanes each keep disjoint bits
-                        Mask old[kFwdUnroll];
-#pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) old[j] = atom_or_if(fresh[j] != 0, &rec[(size_t)x[j] * 4], fresh[j]);
-#pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~old[j];
                     }
                     uint32_t enq_bits = 0;
                     {
