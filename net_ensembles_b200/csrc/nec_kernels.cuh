@@ -345,12 +345,16 @@ vertex_load_engine(const EngineParams p) {
                     // every stage is a batch of kFwdUnroll INDEPENDENT operations per lane: all loads /
                     // atomics of a stage are issued before any result is consumed (predicated PTX, no
                     // branches, so the compiler cannot serialise the round trips)
-                    {
-                        Mask sv[kFwdUnroll];
+                    {   // sources that already reached x, or are already noted for the level being built (a
+                        // snapshot: the atomic below is exact, this only spares most of the redundant ones)
+                        Mask sv[kFwdUnroll], nv[kFwdUnroll];
 #pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) sv[j] = fresh[j] ? __ldcg(&rec[(size_t)x[j] * 4]) : ~(Mask)0;
+                        for (int j = 0; j < kFwdUnroll; ++j) {
+                            sv[j] = fresh[j] ? __ldcg(&rec[(size_t)x[j] * 4]) : ~(Mask)0;
+                            nv[j] = fresh[j] ? __ldcg(&next_nxt[(size_t)x[j] * 4]) : (Mask)0;
+                        }
 #pragma unroll
-                        for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~sv[j];
+                        for (int j = 0; j < kFwdUnroll; ++j) fresh[j] &= ~(sv[j] | nv[j]);
                     }
                     uint32_t enq_bits = 0;
                     {
