@@ -242,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
     n, nnz = len(rp) - 1, len(col)
     sample = args.sources
     if sample is None and args.workload in ("erm2p20", "ba2p22"):
-        sample = 9472 * world if args.workload == "erm2p20" else 3072 * world   # two batches per CTA / one per memory-limited slot
+        sample = 9472 * world if args.workload == "erm2p20" else 3072 * world   # one 64-source batch per SM / one 32-source batch per memory-limited slot
     sources = step_sources(args.workload, n, sample)
     mine = sources[shard_sources(len(sources), rank, world)]
 
@@ -336,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "no explicit flush: one step streams %.1f GB of per-source state (%.2f GB of arenas on rank 0, "
                              "> 126 MB L2) and ends with different data in L2 than it starts with; the 2 MB adjacency slab is "
                              "L2-resident by design" % (16e-6 * len(mine), st0["workspace_bytes"] / 1e9),
-                       "slots": st0["n_slots"], "max_depth": st0["max_depth"],
+                       "slots": st0["n_slots"], "batch_width": st0.get("batch_width"), "max_depth": st0["max_depth"],
                        "queue_entries_per_vertex_per_batch": st0["vertex_visits"] / max(1, st0["n_batches"] * n),
                        "phase_share": {"reset": st0["frac_reset"], "forward": st0["frac_forward"], "backward": st0["frac_backward"]}},
             "clocks": clocks,
@@ -344,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload),
-                         "kernel": {1: "vertex_load_engine<u8> (batched, 32 sources per CTA)", 2: "mid_engine (one source per CTA)"}.get(st0["engine"] & 15, "?"),
+                         "kernel": {1: "vertex_load_engine<u8> (batched, %d sources per CTA)" % (st0.get("batch_width") or 32), 2: "mid_engine (one source per CTA)"}.get(st0["engine"] & 15, "?"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg, "kernel_ms_per_launch": eng_s * 1e3},
         }
