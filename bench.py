@@ -112,11 +112,12 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def profiled_traffic(workload, sources_per_launch):
+    """dram bytes per launch of the dominant kernel: the committed ncu capture's bytes per source (traffic
+    is proportional to the sources a launch processes) times this launch's sources; None if not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            return json.load(fh).get(workload)
+            return json.load(fh)[workload]["dram_bytes_per_source"] * sources_per_launch
     except Exception:
         return None
 
@@ -343,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload),
+                         "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload, len(mine)),
                          "kernel": {1: "vertex_load_engine<u8> (batched, %d sources per CTA)" % (st0.get("batch_width") or 32), 2: "mid_engine (one source per CTA)"}.get(st0["engine"] & 15, "?"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg, "kernel_ms_per_launch": eng_s * 1e3},
