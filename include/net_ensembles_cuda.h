@@ -75,7 +75,7 @@ int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
 /* Engine selection (tests and profiling; the default 0 chooses by graph size):
  *   NEC_ENGINE_AUTO    0  n in [2048, 100000]: one source per CTA, per-source state in shared
- *                         memory; otherwise the batched 32-source engine
+ *                         memory; otherwise the batched engine (32 or 64 sources per CTA)
  *   NEC_ENGINE_BATCHED 1  always the batched engine
  *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 100000 */
 #define NEC_ENGINE_AUTO 0
@@ -131,7 +131,7 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
  *   sum_dist[i] = sum of the distances to every vertex it reaches (closeness_centrality, :1387-1403:
  *                 count[v] = sum_s d(s,v), which equals this sum for source v in an undirected graph)
  *   reached[i]  = number of vertices it reaches, itself included (connectivity test of diameter, :1116-1136)
- * Integer results, exact.  Forward (bit-parallel, 32 sources per pass) only; any output may be NULL. */
+ * Integer results, exact.  Forward (bit-parallel, 32 or 64 sources per pass) only; any output may be NULL. */
 int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
                           uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached);
 

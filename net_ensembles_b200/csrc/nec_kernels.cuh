@@ -6,28 +6,33 @@
 // b[v] = sum_{s != v, s reaches v} (bk_s(v) - [!include_endpoints]).
 //
 // How it is laid out for the GPU — "batched multi-source, source-minor":
-//   * 32 sources form a BATCH; source k of the batch is bit k / lane k everywhere.
+//   * B = 32 or 64 sources form a BATCH (template parameter kSrc; the host picks 64 when the call has
+//     at least one such batch per SM and the workspace holds one 64-wide slot per SM).  Source k of
+//     the batch is bit k of every mask and byte / element k of every row; lane k of a warp owns
+//     source k (and k + 32 at B = 64).
 //   * one CTA owns one batch SLOT (its arena of state) and walks the batch level by level
 //     with __syncthreads only; CTAs are persistent and take batches round-robin (static
 //     batch -> slot mapping, so every floating-point sum is reproducible run to run).
-//   * per-slot state: seen[v] (u32: sources that have reached v), next[2][v] (u32: sources
-//     that reach v on the level being built; double-buffered by level parity, self-cleaning),
-//     dist[v][32] (u8, one 32 B sector per vertex; u32 rows for graphs deeper than 253
-//     levels), q[v][32] (f64, 256 B per vertex), the level queues of (vertex, source-mask)
-//     entries, and a private partial load vector.
-//   * FORWARD pass, bit-parallel, one LANE PER ADJACENCY ENTRY: a warp takes a tile of 32 queue
-//     entries, writes their distance rows (the entry's source mask is final when it is dequeued:
-//     lane k stores byte k, one store instruction per row), flattens their adjacency lists (warp
-//     scan + per-lane owner search) and every lane handles (u -> x) entries for all 32 sources at
-//     once, four per step, each stage a batch of independent memory operations:
-//     new = mask(u) & ~seen[x]; atomicOr(seen[x]) filters races exactly; the truly new bits are
-//     ORed into next[x]; the lane that turns next[x] non-zero appends x to the next level's queue
+//   * per-slot state: one mask record per vertex {seen, next[even], next[odd], -} (u32 or u64
+//     words; seen = sources that have reached v, next = sources that reach v on the level being
+//     built, double-buffered by level parity, self-cleaning), dist[v][B] (u8; a 64 B row is one
+//     DRAM burst; u32 rows for graphs deeper than 253 levels), q[v][B] (f64), the level queues
+//     (vertex ids and their source masks) and a private partial load vector.
+//   * FORWARD pass, bit-parallel.  Per level: (1) MARK - every queue entry's mask moves from its
+//     next[] word into the queue and is ORed into seen (plain read-modify-write: one owner per
+//     vertex and level), so that (2) EXPAND needs no atomic on seen: one LANE PER ADJACENCY ENTRY,
+//     a warp takes a tile of 32 queue entries, writes their distance rows (lane k stores byte k,
+//     one store instruction per row and 32 sources), flattens their adjacency lists (warp scan +
+//     per-lane owner search) and every lane handles (u -> x) entries for all B sources at once,
+//     four per step, each stage a batch of independent memory operations:
+//     new = mask(u) & ~(seen[x] | next[x]) (a snapshot), atomicOr(next[x], new) merges racing
+//     lanes exactly, and the lane that turns next[x] non-zero appends x to the next level's queue
 //     (warp-aggregated shared-memory tail).
 //   * BACKWARD pass (pull, atomic-free, deterministic), one LANE PER SOURCE: levels deepest
 //     -> 1 over the same queues, again in tiles of 32 entries with flattened adjacency entries
 //     consumed in chunks of 32 through a two-deep pipeline: chunk s+2's neighbour ids are being
-//     loaded, chunk s+1's 32 distance rows (32 B each) are in flight to shared memory (cp.async,
-//     two lanes per row), chunk s is consumed.  For entry (w, mask) and neighbour x, lane k reads
+//     loaded, chunk s+1's 32 distance rows are in flight to shared memory (cp.async, 16 B pieces),
+//     chunk s is consumed.  For entry (w, mask) and neighbour x, lane k reads
 //     byte k of x's staged row; lanes with dist == level+1 pull q[x][k], lanes count
 //     dist == level-1 as predecessors; at the end of w's row bk = 1 + sum, q[w][k] = bk / npred
 //     and the lane-sum of bk goes to the slot's private b[] (exactly one writer per vertex per
@@ -41,7 +46,7 @@
 
 namespace nec {
 
-constexpr int kLanes = 32;            // sources per batch
+constexpr int kLanes = 32;            // lanes per warp = sources per narrow batch (debug planes, small-graph kernel)
 // CTA shape: 512 threads x 2 CTAs per SM when the workspace budget allows two slots per SM, else
 // 1024 threads x 1 CTA per SM (large graphs are slot-limited by memory; wider CTAs keep the SMs busy)
 constexpr int kUnroll = 8;            // neighbour rows in flight per warp step (backward)
@@ -328,7 +333,7 @@ vertex_load_engine(const EngineParams p) {
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 const uint32_t off = incl - deg;
                 // kFwdUnroll flattened entries per lane and step: every stage below is a batch of
-                // independent memory operations (col -> seen -> atomicOr(seen) -> atomicOr(next)).
+                // independent memory operations (col -> seen/next snapshot -> atomicOr(next)).
                 for (uint32_t t0 = 0; t0 < total; t0 += 32 * kFwdUnroll) {
                     uint32_t x[kFwdUnroll];
                     Mask fresh[kFwdUnroll];
