@@ -180,6 +180,7 @@ def run_markov(args, rank, world, local_rank):
     mine = [g for g in range(4096) if g % world == rank]
     chains = [ne.ErEnsembleC(256, 4.0, SEED + g) for g in mine]
     ctx = ne.Context(local_rank)
+    batch = ne.ChainBatch(chains)
 
     def sync():
         if world > 1:
@@ -187,13 +188,13 @@ def run_markov(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        ne.chains_step_and_load(ctx, chains, 1, True)
+        batch.step_and_load(ctx, 1, True)
     sync()
     t0 = time.perf_counter()
     kernel_ms, te, launches = 0.0, 0.0, 0
     for _ in range(args.steps):
-        outs = ne.chains_step_and_load(ctx, chains, 1, True)
-        st = ctx.stats()
+        outs = batch.step_and_load(ctx, 1, True)      # (chains, 256) loads in host memory
+        st = batch.stats
         kernel_ms += st["kernel_ms"]; te += st["edge_pairs"] / 2; launches += st["kernel_launches"]
     sync()
     vals = torch.tensor([time.perf_counter() - t0, kernel_ms], dtype=torch.float64, device="cuda")

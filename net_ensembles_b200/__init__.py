@@ -5,8 +5,8 @@ package is the Python host side: a ctypes binding (`_lib`) and a mirror of the r
 operator interface for this path (`Graph`, `SwGraph`-backed `SwEnsemble`, `ErEnsembleC`,
 `ErEnsembleM`, `BAensemble`, each with `vertex_load(include_endpoints)`).
 """
-from .api import (BAensemble, Context, DeviceGraph, ErEnsembleC, ErEnsembleM, Graph, NecError,  # noqa: F401
+from .api import (BAensemble, ChainBatch, Context, DeviceGraph, ErEnsembleC, ErEnsembleM, Graph, NecError,  # noqa: F401
                   SwEnsemble, chains_step_and_load, default_context, gnm_scalable, ba_scalable, vertex_load_batch)
 
 __all__ = ["Context", "DeviceGraph", "Graph", "ErEnsembleC", "ErEnsembleM", "SwEnsemble", "BAensemble",
-           "NecError", "chains_step_and_load", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch"]
+           "NecError", "ChainBatch", "chains_step_and_load", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch"]

@@ -64,6 +64,7 @@ NECH_SYMBOLS = {
     "nech_rng_state": (c_int, [c_vp, c_vp]),
     "nech_vertex_load_cuda": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nech_chains_step_and_load_cuda": (c_int, [c_vp, c_u32, c_u64, c_vp, c_int, c_vp]),
+    "nech_last_chain_stats": (None, [ctypes.POINTER(NecStats)]),
     "nech_pcg64_draws": (None, [c_u64, c_u64, c_vp]),
 }
 

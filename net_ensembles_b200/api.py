@@ -168,18 +168,45 @@ def vertex_load_batch(ctx, graphs, include_endpoints):
     return np.split(out, np.cumsum(ns)[:-1]) if len(graphs) else []
 
 
+class ChainBatch:
+    """A fixed set of Markov chains measured together (benches/common/mod.rs:79-90 run on many chains):
+    holds the handle table, the result buffer and the vertex counts so that a measurement step costs one
+    C call — `m_steps` Markov steps on every chain (all host cores), CSR export, and vertex_load of all the
+    graphs through the one-CTA-per-graph kernel, pipelined with the copies."""
+
+    def __init__(self, chains):
+        self.chains = list(chains)
+        self._handles = (c_vp * len(self.chains))(*[c._h for c in self.chains])
+        self._ns = np.array([c.vertex_count() for c in self.chains], dtype=np.int64)
+        self._out = np.empty(int(self._ns.sum()), dtype=np.float64)
+        self._uniform = len(self.chains) > 0 and bool((self._ns == self._ns[0]).all())
+        self._cuts = np.cumsum(self._ns)[:-1]
+        self.stats = None
+
+    def step_and_load(self, ctx, m_steps, include_endpoints):
+        """Returns the load vectors: a (chains, n) array when all graphs have the same size, else a list of
+        views.  The buffer is reused by the next call."""
+        lib = _lib.load()
+        if not self.chains:
+            return []
+        rc = lib.nech_chains_step_and_load_cuda(self._handles, len(self.chains), int(m_steps), ctx._h,
+                                                int(bool(include_endpoints)), _ptr(self._out))
+        if rc != 0:
+            raise NecError(rc, lib.nech_last_error().decode())
+        st = _lib.NecStats()
+        lib.nech_last_chain_stats(ctypes.byref(st))
+        self.stats = st.as_dict()          # counters of this step
+        if self._uniform:
+            return self._out.reshape(len(self.chains), int(self._ns[0]))
+        return np.split(self._out, self._cuts)
+
+
 def chains_step_and_load(ctx, chains, m_steps, include_endpoints):
     """Markov-chain measurement (benches/common/mod.rs:79-90): `m_steps` Markov steps on every
-    chain, then vertex_load of all their graphs in ONE launch (export + call happen in C++).
-    Returns a list of load vectors (views into one array)."""
-    lib = _lib.load()
-    handles = (c_vp * len(chains))(*[c._h for c in chains])
-    ns = [c.vertex_count() for c in chains]
-    out = np.empty(int(sum(ns)), dtype=np.float64)
-    rc = lib.nech_chains_step_and_load_cuda(handles, len(chains), int(m_steps), ctx._h, int(bool(include_endpoints)), _ptr(out))
-    if rc != 0:
-        raise NecError(rc, lib.nech_last_error().decode())
-    return np.split(out, np.cumsum(ns)[:-1]) if chains else []
+    chain, then vertex_load of all their graphs (export + call happen in C++).  Convenience form of
+    ChainBatch for a one-off call; returns a list of load vectors (copies)."""
+    res = ChainBatch(chains).step_and_load(ctx, m_steps, include_endpoints)
+    return [np.array(r) for r in res]
 
 
 class _HostGraph:

@@ -2,10 +2,14 @@
 // harness (ctypes).  `nech_` = net_ensembles_cuda host.  These build the INPUT graphs of the
 // hot path and call it through the public C ABI; they contain no load arithmetic and no CPU
 // implementation of vertex_load.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../../include/net_ensembles_cuda.h"
 #include "nec_graphs.hpp"
@@ -182,53 +186,87 @@ int nech_vertex_load_cuda(const void *p, nec_ctx *ctx, int include_endpoints, do
 }
 
 // Markov-chain shape (benches/common/mod.rs:79-90): `count` m_steps on every chain, then
-// vertex_load(include_endpoints) of ALL chains' graphs in one launch (one CTA per graph).
-// out receives the load vectors back to back.  count == 0 measures without stepping.
+// vertex_load(include_endpoints) of ALL chains' graphs (one CTA per graph).  out receives the load
+// vectors back to back.  count == 0 measures without stepping.
+//
+// Stepping and export run on all host cores; nec_vertex_load_batch is itself a copy-in / kernel / copy-out
+// pipeline.  (Stepping the next group of chains on a helper thread while the GPU works was tried and lost:
+// two OpenMP teams on the same cores stall each other for longer than the 3 ms they would hide.)
+namespace {
+struct ChainGroup {                          // one group's exported CSRs (buffers reused across calls)
+    std::vector<uint32_t> n_per, rp, col;
+    std::vector<uint64_t> rp_off, col_off;
+    uint64_t out_count = 0;
+    int bad = 0;
+};
+thread_local ChainGroup g_group;
+thread_local nec_stats g_chain_stats;
+
+void prepare_group(ChainGroup &grp, void *const *handles, uint32_t g0, uint32_t g1, uint64_t m_steps) {
+    const uint32_t cnt = g1 - g0;
+    grp.n_per.resize(cnt); grp.rp_off.resize(cnt); grp.col_off.resize(cnt);
+    int bad = 0;
+    // chains are independent: step them on all host cores (each chain owns its generator)
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int64_t g = g0; g < (int64_t)g1; ++g) {
+        Handle *h = static_cast<Handle *>(handles[g]);
+        for (uint64_t k = 0; k < m_steps; ++k) switch (h->kind) {
+            case Kind::ErC: h->erc->m_step(); break;
+            case Kind::ErM: h->erm->m_step(); break;
+            case Kind::Sw: h->sw->m_step(); break;
+            default: bad += 1; k = m_steps; break;
+        }
+    }
+    grp.bad = bad;
+    uint64_t rp_total = 0, col_total = 0, out_count = 0;
+    for (uint32_t g = g0; g < g1; ++g)
+        with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
+            grp.n_per[g - g0] = (uint32_t)gr.vertex_count();
+            grp.rp_off[g - g0] = rp_total; grp.col_off[g - g0] = col_total;
+            rp_total += gr.vertex_count() + 1; col_total += gr.nnz(); out_count += gr.vertex_count();
+            return 0;
+        });
+    grp.out_count = out_count;
+    if (grp.rp.size() < rp_total) grp.rp.resize(rp_total + rp_total / 8);
+    if (grp.col.size() < col_total + 1) grp.col.resize(col_total + col_total / 8 + 1);
+    uint32_t *const rp_buf = grp.rp.data(), *const col_buf = grp.col.data();
+    const uint64_t *const rp_off = grp.rp_off.data(), *const col_off = grp.col_off.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t g = g0; g < (int64_t)g1; ++g)
+        with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
+            uint32_t *r = rp_buf + rp_off[g - g0];
+            uint32_t *c = col_buf + col_off[g - g0];
+            uint32_t at = 0;
+            for (size_t v = 0; v < gr.vertices.size(); ++v) {
+                r[v] = at;
+                for (auto &e : gr.vertices[v].adj) c[at++] = e.to;
+            }
+            r[gr.vertices.size()] = at;
+            return 0;
+        });
+}
+}  // namespace
+
 int nech_chains_step_and_load_cuda(void *const *handles, uint32_t n_chains, uint64_t m_steps, nec_ctx *ctx,
                                    int include_endpoints, double *out) {
     return guarded([&]() -> int {
-        std::vector<uint32_t> n_per(n_chains);
-        std::vector<uint64_t> rp_off(n_chains), col_off(n_chains);
-        // chains are independent: step them on all host cores (each chain owns its generator)
-        int bad = 0;
-#pragma omp parallel for schedule(static) reduction(+ : bad)
-        for (int64_t g = 0; g < (int64_t)n_chains; ++g) {
-            Handle *h = static_cast<Handle *>(handles[g]);
-            for (uint64_t k = 0; k < m_steps; ++k) switch (h->kind) {
-                case Kind::ErC: h->erc->m_step(); break;
-                case Kind::ErM: h->erm->m_step(); break;
-                case Kind::Sw: h->sw->m_step(); break;
-                default: bad += 1; k = m_steps; break;
-            }
-        }
-        if (bad) { g_err = "chain has no Markov step"; return NEC_EINVAL; }
-        uint64_t rp_total = 0, col_total = 0;
-        for (uint32_t g = 0; g < n_chains; ++g)
-            with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
-                n_per[g] = (uint32_t)gr.vertex_count();
-                rp_off[g] = rp_total; col_off[g] = col_total;
-                rp_total += gr.vertex_count() + 1; col_total += gr.nnz();
-                return 0;
-            });
-        std::vector<uint32_t> rp(rp_total), col(col_total ? col_total : 1);
-#pragma omp parallel for schedule(static)
-        for (int64_t g = 0; g < (int64_t)n_chains; ++g)
-            with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
-                uint32_t *r = rp.data() + rp_off[g];
-                uint32_t *c = col.data() + col_off[g];
-                uint32_t at = 0;
-                for (size_t v = 0; v < gr.vertices.size(); ++v) {
-                    r[v] = at;
-                    for (auto &e : gr.vertices[v].adj) c[at++] = e.to;
-                }
-                r[gr.vertices.size()] = at;
-                return 0;
-            });
-        int rc = nec_vertex_load_batch(ctx, n_chains, n_per.data(), rp_off.data(), rp.data(), col_off.data(), col.data(),
-                                       include_endpoints, out);
+        const bool verbose = getenv("NEC_SMALL_VERBOSE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
+        g_chain_stats = nec_stats{};
+        ChainGroup &grp = g_group;
+        prepare_group(grp, handles, 0, n_chains, m_steps);
+        if (grp.bad) { g_err = "chain has no Markov step"; return NEC_EINVAL; }
+        const double t1 = now();
+        const int rc = nec_vertex_load_batch(ctx, n_chains, grp.n_per.data(), grp.rp_off.data(), grp.rp.data(),
+                                             grp.col_off.data(), grp.col.data(), include_endpoints, out);
         if (rc != NEC_OK) g_err = nec_last_error(ctx);
+        else nec_get_stats(ctx, &g_chain_stats);
+        if (verbose) fprintf(stderr, "[nech chains] step+export %.2f ms, batch call %.2f ms\n", t1 - t0, now() - t1);
         return rc; }, NEC_EINVAL);
 }
+// Counters of the last nech_chains_step_and_load_cuda call of this thread.
+void nech_last_chain_stats(nec_stats *out) { *out = g_chain_stats; }
 
 // raw generator access, for the known-answer tests of the rand restatement
 void nech_pcg64_draws(uint64_t seed, uint64_t count, uint64_t *out_u64) {

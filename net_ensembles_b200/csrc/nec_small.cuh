@@ -16,6 +16,10 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -200,112 +204,230 @@ small_graph_kernel(const SmallParams p) {
     }
 }
 
-// Device staging for nec_vertex_load_batch, owned by the context and grown on demand.
+// Staging for nec_vertex_load_batch, owned by the context and grown on demand: a device arena, a pinned
+// host mirror of it, and the three streams of the copy-in / kernel / copy-out pipeline.
+constexpr int kSmallMaxChunks = 8;
 struct SmallWorkspace {
-    void *base = nullptr;
+    void *base = nullptr;            // device arena
     size_t cap = 0;
+    void *h_base = nullptr;          // pinned host staging (same layout)
+    size_t h_cap = 0;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr;
+    cudaEvent_t ev_entry = nullptr, ev_in[kSmallMaxChunks] = {}, ev_k0[kSmallMaxChunks] = {}, ev_k1[kSmallMaxChunks] = {}, ev_out[kSmallMaxChunks] = {};
     bool attr_set = false;
-    void release() { if (base) cudaFree(base); base = nullptr; cap = 0; }
+    cudaError_t init_pipeline() {
+        if (s_in) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_k2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int c = 0; c < kSmallMaxChunks; ++c) {
+            if ((e = cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&ev_k0[c])) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&ev_k1[c])) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev_out[c], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        if (h_base) cudaFreeHost(h_base);
+        base = h_base = nullptr; cap = h_cap = 0;
+        if (s_in) {
+            cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_k2); cudaStreamDestroy(s_out); cudaEventDestroy(ev_entry);
+            for (int c = 0; c < kSmallMaxChunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_k0[c]); cudaEventDestroy(ev_k1[c]); cudaEventDestroy(ev_out[c]); }
+            s_in = s_k = s_k2 = s_out = nullptr;
+        }
+    }
 };
 
 inline int small_fail(std::string *err, int code, const std::string &msg) { if (err) *err = msg; return code; }
 
-inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, std::string *err,
+// The call is synchronous (host pointers in, host pointers out) but pipelined inside: the graphs are cut
+// into up to 8 chunks; while the kernel works on chunk c, chunk c+1 is validated and packed into pinned
+// memory by all host cores and copied in, and chunk c-1's loads are copied out and handed to the caller.
+inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t, cudaEvent_t, std::string *err,
                            nec_stats *stats, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *rp_off,
                            const uint32_t *rp, const uint64_t *col_off, const uint32_t *col, int include_endpoints, double *out) {
     if (n_graphs == 0) return NEC_OK;
-    // ---- validate + size ------------------------------------------------------------------
+    const bool verbose = getenv("NEC_SMALL_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_pack = 0.0, t_wait = 0.0, t_copy = 0.0;
+    // ---- sizes; compact offsets of the packed copy ---------------------------------------------
     uint64_t rp_total = 0, col_total = 0, out_total = 0;
     uint32_t max_n = 0;
     size_t max_csr = 0;
-    std::vector<uint64_t> out_off(n_graphs);
+    std::vector<uint64_t> c_rp_off(n_graphs + 1), c_col_off(n_graphs + 1), out_off(n_graphs + 1);
     for (uint32_t g = 0; g < n_graphs; ++g) {
         const uint32_t n = n_per_graph[g];
         if (n == 0 || n > NEC_BATCH_MAX_N)
             return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: graph " + std::to_string(g) + " has n=" + std::to_string(n) +
                                                    " (allowed 1.." + std::to_string(NEC_BATCH_MAX_N) + "; use nec_vertex_load for larger graphs)");
-        const uint32_t *r = rp + rp_off[g];
-        rp_total = std::max<uint64_t>(rp_total, rp_off[g] + n + 1);
-        col_total = std::max<uint64_t>(col_total, col_off[g] + r[n]);
-        out_off[g] = out_total;
-        out_total += n;
+        const uint32_t nnz = (rp + rp_off[g])[n];
+        if (nnz > (uint64_t)n * n)
+            return small_fail(err, NEC_EINVAL, "nec_vertex_load_batch: row_ptr not monotone (graph " + std::to_string(g) + ")");
+        c_rp_off[g] = rp_total; c_col_off[g] = col_total; out_off[g] = out_total;
+        rp_total += n + 1; col_total += nnz; out_total += n;
         max_n = std::max(max_n, n);
-        max_csr = std::max(max_csr, (size_t)(n + 1) * 4 + (size_t)r[n] * 2);
+        max_csr = std::max(max_csr, (size_t)(n + 1) * 4 + (size_t)nnz * 2);
         stats->n_sources += n;
         stats->n_batches += (n + kLanes - 1) / kLanes;
     }
-    // structural validation of every graph, on all host cores (graphs are independent)
-    int bad_graph = -1, bad_kind = 0;
-#pragma omp parallel for schedule(static)
-    for (int64_t g = 0; g < (int64_t)n_graphs; ++g) {
-        const uint32_t n = n_per_graph[g];
-        const uint32_t *r = rp + rp_off[g];
-        const uint32_t *c = col + col_off[g];
-        int kind = r[0] != 0 ? 1 : 0;
-        for (uint32_t v = 0; v < n && !kind; ++v)
-            if (r[v + 1] < r[v]) kind = 2;
-        for (uint32_t e = 0; !kind && e < r[n]; ++e)
-            if (c[e] >= n) kind = 3;
-        if (kind) {
-#pragma omp critical
-            { if (bad_graph < 0 || g < bad_graph) { bad_graph = (int)g; bad_kind = kind; } }
-        }
+    c_rp_off[n_graphs] = rp_total; c_col_off[n_graphs] = col_total; out_off[n_graphs] = out_total;
+
+    // ---- staging: one device arena + its pinned mirror -----------------------------------------
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_n = up((size_t)n_graphs * 4), b_off = up((size_t)(n_graphs + 1) * 8);
+    const size_t b_rp = up(rp_total * 4), b_col = up(std::max<uint64_t>(col_total, 1) * 4), b_out = up(out_total * 8);
+    const size_t need = b_n + 3 * b_off + b_rp + b_col + b_out + 256;
+    cudaError_t e = ws.init_pipeline();
+    if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: stream/event setup failed: ") + cudaGetErrorString(e));
+    if (need > ws.cap) {
+        if (ws.base) cudaFree(ws.base);
+        ws.base = nullptr; ws.cap = 0;
+        e = cudaMalloc(&ws.base, need + need / 4);
+        if (e != cudaSuccess) return small_fail(err, NEC_ENOMEM, std::string("nec_vertex_load_batch: cudaMalloc failed: ") + cudaGetErrorString(e));
+        ws.cap = need + need / 4;
     }
+    if (need > ws.h_cap) {
+        if (ws.h_base) cudaFreeHost(ws.h_base);
+        ws.h_base = nullptr; ws.h_cap = 0;
+        e = cudaHostAlloc(&ws.h_base, need + need / 4, cudaHostAllocDefault);
+        if (e != cudaSuccess) return small_fail(err, NEC_ENOMEM, std::string("nec_vertex_load_batch: cudaHostAlloc failed: ") + cudaGetErrorString(e));
+        ws.h_cap = need + need / 4;
+    }
+    struct Planes { uint32_t *n; uint64_t *rp_off, *col_off, *out_off; uint32_t *rp, *col; double *out; unsigned long long *cnt; };
+    auto carve = [&](void *base) {
+        uint8_t *d = (uint8_t *)base;
+        Planes pl{};
+        pl.n = (uint32_t *)d; d += b_n;
+        pl.rp_off = (uint64_t *)d; d += b_off;
+        pl.col_off = (uint64_t *)d; d += b_off;
+        pl.out_off = (uint64_t *)d; d += b_off;
+        pl.rp = (uint32_t *)d; d += b_rp;
+        pl.col = (uint32_t *)d; d += b_col;
+        pl.out = (double *)d; d += b_out;
+        pl.cnt = (unsigned long long *)d;
+        return pl;
+    };
+    const Planes D = carve(ws.base), H = carve(ws.h_base);
+
+    // work issued earlier on the context's stream stays ahead of this call
+    cudaEventRecord(ws.ev_entry, stream);
+    cudaStreamWaitEvent(ws.s_in, ws.ev_entry, 0);
+    cudaStreamWaitEvent(ws.s_k, ws.ev_entry, 0);
+    cudaStreamWaitEvent(ws.s_k2, ws.ev_entry, 0);
+    std::memcpy(H.n, n_per_graph, (size_t)n_graphs * 4);
+    std::memcpy(H.rp_off, c_rp_off.data(), (size_t)n_graphs * 8);
+    std::memcpy(H.col_off, c_col_off.data(), (size_t)n_graphs * 8);
+    std::memcpy(H.out_off, out_off.data(), (size_t)n_graphs * 8);
+    cudaMemcpyAsync(D.n, H.n, b_n + 3 * b_off, cudaMemcpyHostToDevice, ws.s_in);      // the four planes are contiguous
+    cudaMemsetAsync(D.cnt, 0, 4 * sizeof(unsigned long long), ws.s_in);    // ordered before every kernel via ev_in[]
+
+    const uint32_t csr_budget = (uint32_t)std::min<size_t>((max_csr + 255) / 256 * 256, kSmallCsrBytes);   // larger CSRs are read from L1/L2
+    const size_t smem = small_smem_bytes(max_n, csr_budget);
+    if (!ws.attr_set) {
+        e = cudaFuncSetAttribute(small_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
+        if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        ws.attr_set = true;
+    }
+
+    const uint32_t n_chunks = std::max<uint32_t>(1, std::min<uint32_t>(kSmallMaxChunks, n_graphs / 256));
+    int bad_graph = -1, bad_kind = 0;
+    uint32_t launched = 0;
+    for (uint32_t c = 0; c < n_chunks && bad_graph < 0; ++c) {
+        const uint32_t g0 = (uint32_t)((uint64_t)n_graphs * c / n_chunks), g1 = (uint32_t)((uint64_t)n_graphs * (c + 1) / n_chunks);
+        // validate + pack this chunk's graphs on all host cores (graphs are independent)
+        const double t_p0 = now();
+#pragma omp parallel for schedule(static)
+        for (int64_t g = g0; g < (int64_t)g1; ++g) {
+            const uint32_t n = n_per_graph[g];
+            const uint32_t *r = rp + rp_off[g];
+            const uint32_t *cc = col + col_off[g];
+            int kind = r[0] != 0 ? 1 : 0;
+            for (uint32_t v = 0; v < n && !kind; ++v)
+                if (r[v + 1] < r[v]) kind = 2;
+            for (uint32_t k = 0; !kind && k < r[n]; ++k)
+                if (cc[k] >= n) kind = 3;
+            if (kind) {
+#pragma omp critical
+                { if (bad_graph < 0 || g < bad_graph) { bad_graph = (int)g; bad_kind = kind; } }
+            } else {
+                std::memcpy(H.rp + c_rp_off[g], r, (size_t)(n + 1) * 4);
+                std::memcpy(H.col + c_col_off[g], cc, (size_t)r[n] * 4);
+            }
+        }
+        t_pack += now() - t_p0;
+        if (bad_graph >= 0) break;
+        cudaMemcpyAsync(D.rp + c_rp_off[g0], H.rp + c_rp_off[g0], (c_rp_off[g1] - c_rp_off[g0]) * 4, cudaMemcpyHostToDevice, ws.s_in);
+        if (c_col_off[g1] > c_col_off[g0])
+            cudaMemcpyAsync(D.col + c_col_off[g0], H.col + c_col_off[g0], (c_col_off[g1] - c_col_off[g0]) * 4, cudaMemcpyHostToDevice, ws.s_in);
+        cudaEventRecord(ws.ev_in[c], ws.s_in);
+        // consecutive chunks' kernels go to alternating streams: the next chunk's CTAs fill the SMs that the
+        // previous chunk's last wave leaves idle
+        cudaStream_t sk = (c & 1) ? ws.s_k2 : ws.s_k;
+        cudaStreamWaitEvent(sk, ws.ev_in[c], 0);
+        SmallParams p{};
+        p.n_graphs = g1 - g0; p.n_per_graph = D.n + g0; p.rp_off = D.rp_off + g0; p.rp = D.rp; p.col_off = D.col_off + g0; p.col = D.col;
+        p.out_off = D.out_off + g0; p.include_endpoints = include_endpoints; p.out = D.out; p.counters = D.cnt;
+        p.csr_budget = csr_budget;
+        cudaEventRecord(ws.ev_k0[c], sk);
+        small_graph_kernel<<<g1 - g0, kSmallThreads, smem, sk>>>(p);
+        cudaEventRecord(ws.ev_k1[c], sk);
+        cudaStreamWaitEvent(ws.s_out, ws.ev_k1[c], 0);
+        cudaMemcpyAsync(H.out + out_off[g0], D.out + out_off[g0], (out_off[g1] - out_off[g0]) * 8, cudaMemcpyDeviceToHost, ws.s_out);
+        cudaEventRecord(ws.ev_out[c], ws.s_out);
+        launched = c + 1;
+    }
+    e = cudaGetLastError();
+    const double t_issued = now();
+    // ---- hand the results over chunk by chunk while later chunks are still in flight ----------
+    for (uint32_t c = 0; c < launched && e == cudaSuccess; ++c) {
+        const uint32_t g0 = (uint32_t)((uint64_t)n_graphs * c / n_chunks), g1 = (uint32_t)((uint64_t)n_graphs * (c + 1) / n_chunks);
+        const double t_w0 = now();
+        e = cudaEventSynchronize(ws.ev_out[c]);
+        const double t_w1 = now();
+        t_wait += t_w1 - t_w0;
+        if (e != cudaSuccess || bad_graph >= 0) continue;
+        const uint64_t o0 = out_off[g0], o1 = out_off[g1];
+        const int64_t n_blk = (int64_t)((o1 - o0 + 16383) / 16384);
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < n_blk; ++b) {
+            const uint64_t lo = o0 + (uint64_t)b * 16384, hi = std::min<uint64_t>(o1, lo + 16384);
+            std::memcpy(out + lo, H.out + lo, (hi - lo) * 8);
+        }
+        t_copy += now() - t_w1;
+    }
+    if (verbose)
+        fprintf(stderr, "[nec small] %u graphs %u chunks: setup+issue %.2f ms (pack %.2f) wait %.2f copy-out %.2f total %.2f\n",
+                n_graphs, n_chunks, t_issued - t_begin, t_pack, t_wait, t_copy, now() - t_begin);
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) {                       // every kernel has finished: its copy-out was waited for above
+        cudaMemcpyAsync(H.cnt, D.cnt, sizeof cnt, cudaMemcpyDeviceToHost, ws.s_out);
+        e = cudaStreamSynchronize(ws.s_out);
+        std::memcpy(cnt, H.cnt, sizeof cnt);
+    }
+    cudaStreamSynchronize(ws.s_in);
+    cudaStreamSynchronize(ws.s_k);
+    cudaStreamSynchronize(ws.s_k2);
+    cudaStreamSynchronize(ws.s_out);
     if (bad_graph >= 0)
         return small_fail(err, NEC_EINVAL, std::string("nec_vertex_load_batch: ") +
                                                (bad_kind == 1 ? "local row_ptr must start at 0" : bad_kind == 2 ? "row_ptr not monotone" : "neighbour id out of range") +
                                                " (graph " + std::to_string(bad_graph) + ")");
-    // ---- device staging: one arena -----------------------------------------------------------
-    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    const size_t b_n = up((size_t)n_graphs * 4), b_off = up((size_t)n_graphs * 8);
-    const size_t b_rp = up(rp_total * 4), b_col = up(std::max<uint64_t>(col_total, 1) * 4), b_out = up(out_total * 8);
-    const size_t need = b_n + 3 * b_off + b_rp + b_col + b_out + 256;
-    if (need > ws.cap) {
-        ws.release();
-        cudaError_t e = cudaMalloc(&ws.base, need);
-        if (e != cudaSuccess) return small_fail(err, NEC_ENOMEM, std::string("nec_vertex_load_batch: cudaMalloc failed: ") + cudaGetErrorString(e));
-        ws.cap = need;
-    }
-    uint8_t *d = (uint8_t *)ws.base;
-    uint32_t *d_n = (uint32_t *)d; d += b_n;
-    uint64_t *d_rp_off = (uint64_t *)d; d += b_off;
-    uint64_t *d_col_off = (uint64_t *)d; d += b_off;
-    uint64_t *d_out_off = (uint64_t *)d; d += b_off;
-    uint32_t *d_rp = (uint32_t *)d; d += b_rp;
-    uint32_t *d_col = (uint32_t *)d; d += b_col;
-    double *d_out = (double *)d; d += b_out;
-    unsigned long long *d_cnt = (unsigned long long *)d;
-    cudaMemcpyAsync(d_n, n_per_graph, (size_t)n_graphs * 4, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_rp_off, rp_off, (size_t)n_graphs * 8, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_col_off, col_off, (size_t)n_graphs * 8, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_out_off, out_off.data(), (size_t)n_graphs * 8, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_rp, rp, rp_total * 4, cudaMemcpyHostToDevice, stream);
-    if (col_total) cudaMemcpyAsync(d_col, col, col_total * 4, cudaMemcpyHostToDevice, stream);
-    cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), stream);
-
-    const uint32_t csr_budget = (uint32_t)std::min<size_t>((max_csr + 255) / 256 * 256, kSmallCsrBytes);   // larger CSRs are read from L1/L2
-    const size_t smem = small_smem_bytes(max_n, csr_budget);
-    cudaError_t e = cudaFuncSetAttribute(small_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
-    if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    SmallParams p{};
-    p.n_graphs = n_graphs; p.n_per_graph = d_n; p.rp_off = d_rp_off; p.rp = d_rp; p.col_off = d_col_off; p.col = d_col;
-    p.out_off = d_out_off; p.include_endpoints = include_endpoints; p.out = d_out; p.counters = d_cnt;
-    p.csr_budget = csr_budget;
-    cudaEventRecord(ev0, stream);
-    small_graph_kernel<<<n_graphs, kSmallThreads, smem, stream>>>(p);
-    cudaEventRecord(ev1, stream);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: launch failed: ") + cudaGetErrorString(e));
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    cudaMemcpyAsync(out, d_out, out_total * 8, cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, stream);
-    e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: ") + cudaGetErrorString(e));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    stats->kernel_ms = ms;
-    stats->engine_ms = ms;
-    stats->kernel_launches = 1;
+    float ms_span = 0.f;                          // first kernel's start to the last kernel's end (chunks overlap)
+    for (uint32_t c = 0; c < launched; ++c) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ws.ev_k0[0], ws.ev_k1[c]);
+        ms_span = std::max(ms_span, ms);
+    }
+    stats->kernel_ms = ms_span;
+    stats->engine_ms = ms_span;
+    stats->kernel_launches = launched;
     stats->engine = 3;
     stats->reached_pairs = cnt[0]; stats->edge_pairs = cnt[1]; stats->vertex_visits = cnt[2]; stats->max_depth = (uint32_t)cnt[3];
     stats->n_slots = n_graphs;

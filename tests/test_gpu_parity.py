@@ -399,3 +399,39 @@ def test_wide_batches_are_the_default_for_many_sources(ctx, oracle):
     assert close(got, oracle.vertex_load(rp, col, True, sources=src[:2000], threads=0), REL)
     ctx.set_engine(0)
     dg.free()
+
+
+def test_chain_batch_pipeline_many_chunks(ctx, oracle):
+    """> 256 graphs per call: the batch call runs as a pipeline of chunks (pack -> copy in -> kernel -> copy
+    out); mixed sizes, uniform sizes (2-D result), and a malformed graph in a late chunk."""
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(20, 70, 1100)
+    chains = [ne.ErEnsembleC(int(n), 3.0, 9000 + g) for g, n in enumerate(sizes)]
+    twins = [ne.ErEnsembleC(int(n), 3.0, 9000 + g) for g, n in enumerate(sizes)]
+    batch = ne.ChainBatch(chains)
+    for step in range(2):
+        outs = batch.step_and_load(ctx, 3, True)
+        assert batch.stats["kernel_launches"] == 4 and batch.stats["engine"] == 3   # 1100 graphs -> 4 chunks and batch.stats["n_sources"] == int(sizes.sum())
+        for t in twins:
+            t.m_steps(3)
+        for g in list(range(0, 1100, 37)) + [1099]:
+            rp, col = twins[g].export_csr()
+            assert close(outs[g], oracle.vertex_load(rp, col, True), REL), g
+    uni = ne.ChainBatch([ne.ErEnsembleC(40, 4.0, 70 + g) for g in range(600)])
+    res = uni.step_and_load(ctx, 0, False)
+    assert res.shape == (600, 40)
+    rp, col = uni.chains[599].export_csr()
+    assert close(res[599], oracle.vertex_load(rp, col, False), REL)
+    # malformed input in the last chunk: loud error, nothing half-written, context still usable
+    graphs = [c.export_csr() for c in chains[:700]]
+    graphs = [(rp.astype(np.uint32), col.copy()) for rp, col in graphs]
+    bad = next(g for g in range(650, 700) if len(graphs[g][1]))
+    graphs[bad][1][0] = 10_000
+    with pytest.raises(ne.NecError, match="out of range"):
+        ne.vertex_load_batch(ctx, graphs, True)
+    graphs[bad][1][0] = 0
+    outs = ne.vertex_load_batch(ctx, graphs[:600], True)
+    assert ctx.stats()["kernel_launches"] == 2
+    for g in (0, 299, 300, 599):
+        rp, col = chains[g].export_csr()
+        assert close(outs[g], oracle.vertex_load(rp, col, True), REL)
