@@ -74,10 +74,10 @@ int nec_set_stream(nec_ctx *ctx, void *cuda_stream);
 int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
 /* Engine selection (tests and profiling; the default 0 chooses by graph size):
- *   NEC_ENGINE_AUTO    0  n in [2048, 100000]: one source per CTA, per-source state in shared
+ *   NEC_ENGINE_AUTO    0  n in [64, 180000]: one source per CTA, per-source state in shared
  *                         memory; otherwise the batched engine (32 or 64 sources per CTA)
  *   NEC_ENGINE_BATCHED 1  always the batched engine
- *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 100000 */
+ *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 180000 */
 #define NEC_ENGINE_AUTO 0
 #define NEC_ENGINE_BATCHED 1
 #define NEC_ENGINE_MID 2

@@ -52,7 +52,7 @@ class Context:
         self._check(self._lib.nec_set_workspace_limit(self._h, int(nbytes)))
 
     def set_engine(self, engine):
-        """0 auto, 1 batched (32 or 64 sources per CTA), 2 mid (one source per CTA, 2048 <= n <= 180000)."""
+        """0 auto, 1 batched (32 or 64 sources per CTA), 2 mid (one source per CTA, default for 64 <= n <= 180000)."""
         self._check(self._lib.nec_set_engine(self._h, int(engine)))
 
     def stats(self):

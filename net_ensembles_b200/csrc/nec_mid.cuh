@@ -50,7 +50,7 @@ namespace nec {
 
 constexpr int kMidThreads = 512;          // two CTAs per SM: one source's narrow levels overlap another's wide ones
 constexpr uint32_t kMidMaxN = 180000;     // 1.125 B/vertex of shared memory + staging + bookkeeping <= 227 KB
-constexpr uint32_t kMidMinN = 2048;       // below this the batched engine's 32-source rows are cheap
+constexpr uint32_t kMidMinN = 64;         // one source per CTA wins down to tiny graphs (3.5x at n = 300..2048, scripts/exp_small_n.py)
 constexpr uint32_t kMidHubDeg = 64;
 constexpr int kMidHubCap = 512;
 constexpr uint32_t kMidMaxLevel = 126;    // distance bytes < 0x80; the backward pass overwrites them with a 'finished' mark

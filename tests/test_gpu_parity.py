@@ -411,7 +411,8 @@ def test_chain_batch_pipeline_many_chunks(ctx, oracle):
     batch = ne.ChainBatch(chains)
     for step in range(2):
         outs = batch.step_and_load(ctx, 3, True)
-        assert batch.stats["kernel_launches"] == 4 and batch.stats["engine"] == 3   # 1100 graphs -> 4 chunks and batch.stats["n_sources"] == int(sizes.sum())
+        assert batch.stats["kernel_launches"] == 4 and batch.stats["engine"] == 3    # 1100 graphs -> 4 chunks
+        assert batch.stats["n_sources"] == int(sizes.sum())
         for t in twins:
             t.m_steps(3)
         for g in list(range(0, 1100, 37)) + [1099]:
