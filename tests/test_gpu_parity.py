@@ -436,3 +436,50 @@ def test_chain_batch_pipeline_many_chunks(ctx, oracle):
     for g in (0, 299, 300, 599):
         rp, col = chains[g].export_csr()
         assert close(outs[g], oracle.vertex_load(rp, col, True), REL)
+
+
+def _full_size_properties(ctx, oracle, rp, col, src, want_engine, want_width):
+    """Size-independent properties at BASELINE's full sizes (the oracle only sees a handful of sources there):
+    with S the source set, R_s the vertices s reaches and d_s the BFS distances,
+      sum_v (load_true - load_false)(v) = sum_{s in S} (|R_s| - 1)       (an endpoint adds exactly 1),
+      sum_v load_true(v)               = sum_{s in S} sum_v d_s(v)       (a unit from v crosses d_s(v) vertices),
+    the right-hand sides being the exact integers of nec_distance_measures (forward pass alone)."""
+    dg = ctx.upload(rp, col)
+    lt = dg.vertex_load_sources(src, True)
+    st = ctx.stats()
+    assert st["engine"] & 15 == want_engine and (want_width is None or st["batch_width"] == want_width)
+    lf = dg.vertex_load_sources(src, False)
+    ecc, sumd, reached = dg.distance_measures(src)
+    assert st["reached_pairs"] == int(reached.astype(np.int64).sum())
+    ends = int((reached.astype(np.int64) - 1).sum())
+    assert abs(float((lt - lf).sum()) - ends) <= 1e-9 * ends
+    dtot = int(sumd.astype(object).sum())
+    assert abs(float(lt.sum()) - dtot) <= 1e-9 * dtot
+    diff = lt - lf                                          # per vertex: how many sources other than v reach it
+    assert np.all(np.abs(diff - np.rint(diff)) <= 1e-9 * np.maximum(1.0, diff)) and diff.min() >= -1e-6 and diff.max() <= len(src) * (1 + 1e-9)
+    sub = src[:: max(1, len(src) // 6)][:6]
+    assert close(dg.vertex_load_sources(sub, True), oracle.vertex_load(rp, col, True, sources=sub, threads=0), REL)
+    dg.free()
+    return st
+
+
+def test_full_size_properties_config2_small_world(ctx, oracle):
+    e = ne.SwEnsemble(1 << 16, 0.1, 123_239_010, 2)          # BASELINE configs[1], every source
+    rp, col = e.export_csr()
+    st = _full_size_properties(ctx, oracle, rp, col, np.arange(1 << 16, dtype=np.uint32), 2, None)
+    assert st["reached_pairs"] == (1 << 32)                  # connected
+
+
+def test_full_size_properties_config4_gnm(ctx, oracle):
+    g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)          # BASELINE configs[3] (scalable generator), sampled sources
+    rp, col = g.export_csr()
+    src = (np.arange(9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
+    _full_size_properties(ctx, oracle, rp, col, src, 1, 64)
+
+
+def test_full_size_properties_config5_barabasi_albert(ctx, oracle):
+    g = ne.ba_scalable(1 << 22, 4, 5, 20261020)              # BASELINE configs[4] (scalable generator), sampled sources
+    rp, col = g.export_csr()
+    src = (np.arange(1536, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
+    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)
+    assert st["reached_pairs"] == 1536 * (1 << 22)           # a BA graph is connected
