@@ -94,6 +94,12 @@ int fail(nec_ctx *ctx, int code, const char *fmt, ...) {
                         "%s failed: %s", #call, cudaGetErrorString(e__));                        \
     } while (0)
 
+
+// No C++ exception may cross the C ABI: host allocations inside an entry point report NEC_ENOMEM instead.
+#define NEC_CATCH_ALL(ctx)                                                                        \
+    catch (const std::bad_alloc &) { return fail(ctx, NEC_ENOMEM, "out of host memory"); }        \
+    catch (const std::exception &ex) { return fail(ctx, NEC_EINTERNAL, "unexpected exception: %s", ex.what()); }
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <class T>
@@ -627,7 +633,7 @@ int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes) {
     return NEC_OK;
 }
 
-int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr, const uint32_t *col_idx, nec_graph **out) {
+int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr, const uint32_t *col_idx, nec_graph **out) try {
     if (!ctx) return NEC_EINVAL;
     if (!out) return fail(ctx, NEC_EINVAL, "nec_graph_upload: out is NULL");
     *out = nullptr;
@@ -683,7 +689,7 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     }
     *out = g;
     return NEC_OK;
-}
+} NEC_CATCH_ALL(ctx)
 
 void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
     if (!g) return;
@@ -698,14 +704,14 @@ void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
 }
 
 int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
-                                   int include_endpoints, double *d_out) {
+                                   int include_endpoints, double *d_out) try {
     if (!ctx) return NEC_EINVAL;
     if (!g || (g->n && !d_out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources_device: NULL argument");
     return run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, d_out, false, nullptr, nullptr);
-}
+} NEC_CATCH_ALL(ctx)
 
 int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
-                            int include_endpoints, double *out) {
+                            int include_endpoints, double *out) try {
     if (!ctx) return NEC_EINVAL;
     if (!g || (g->n && !out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources: NULL argument");
     if (g->n == 0) { ctx->stats = nec_stats{}; return NEC_OK; }
@@ -716,17 +722,17 @@ int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *so
     NEC_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, (size_t)g->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NEC_OK;
-}
+} NEC_CATCH_ALL(ctx)
 
-int nec_vertex_load(nec_ctx *ctx, const nec_graph *g, int include_endpoints, double *out) {
+int nec_vertex_load(nec_ctx *ctx, const nec_graph *g, int include_endpoints, double *out) try {
     if (!ctx) return NEC_EINVAL;
     if (!g) return fail(ctx, NEC_EINVAL, "nec_vertex_load: graph is NULL");
     std::vector<uint32_t> all(g->n);
     for (uint32_t v = 0; v < g->n; ++v) all[v] = v;   // generic_graph.rs:1321 — every vertex is a source
     return nec_vertex_load_sources(ctx, g, all.data(), g->n, include_endpoints, out);
-}
+} NEC_CATCH_ALL(ctx)
 
-int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *dist, uint32_t *npred, double *sigma, double *bk) {
+int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *dist, uint32_t *npred, double *sigma, double *bk) try {
     if (!ctx) return NEC_EINVAL;
     if (!g) return fail(ctx, NEC_EINVAL, "nec_bfs_debug: graph is NULL");
     const uint32_t n = g->n;
@@ -768,10 +774,10 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
     cleanup();
     if (e != cudaSuccess) return fail(ctx, NEC_ECUDA, "nec_bfs_debug: %s", cudaGetErrorString(e));
     return NEC_OK;
-}
+} NEC_CATCH_ALL(ctx)
 
 int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
-                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) {
+                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) try {
     if (!ctx) return NEC_EINVAL;
     if (!g || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_distance_measures: NULL argument");
     ctx->stats = nec_stats{};
@@ -829,11 +835,11 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     }
     cleanup();
     return rc;
-}
+} NEC_CATCH_ALL(ctx)
 
 int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,
                           const uint32_t *row_ptr_concat, const uint64_t *col_offsets, const uint32_t *col_idx_concat,
-                          int include_endpoints, double *out_concat) {
+                          int include_endpoints, double *out_concat) try {
     if (!ctx) return NEC_EINVAL;
     if (n_graphs && (!n_per_graph || !row_ptr_offsets || !row_ptr_concat || !col_offsets || !out_concat))
         return fail(ctx, NEC_EINVAL, "nec_vertex_load_batch: NULL argument");
@@ -841,7 +847,7 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
     cudaSetDevice(ctx->device);
     return nec::small_batch_run(ctx->small, ctx->stream, ctx->ev0, ctx->ev1, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
                                 row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
-}
+} NEC_CATCH_ALL(ctx)
 
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out) {
     if (!ctx || !out) return NEC_EINVAL;
