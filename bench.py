@@ -253,6 +253,15 @@ def run_ours(args, rank, world, local_rank):
     dg = ctx.upload(rp, col)
     out = torch.empty(n, dtype=torch.float64, device="cuda")
 
+    if args.sources is None and args.workload in ("erm2p20", "ba2p22"):
+        # the sample is ONE resident wave of the engine as it plans the whole job (all n sources) for this graph
+        # on this GPU: slots x sources per batch (nec_wave_size); the whole job is that wave repeated
+        wave = dg.wave_size(n)
+        if wave * world != len(sources):
+            sample = wave * world
+            sources = step_sources(args.workload, n, sample)
+            mine = sources[shard_sources(len(sources), rank, world)]
+
     def step():
         dg.vertex_load_sources_device(mine, True, out.data_ptr())
         st = ctx.stats()

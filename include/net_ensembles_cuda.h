@@ -135,6 +135,12 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
 int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
                           uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached);
 
+/* How many sources the engine works on concurrently ("one resident wave": batch slots x sources per batch,
+ * as planned for this graph, this device's free memory and a job of n_sources_total sources).  Callers that
+ * sample sources or cut a job into calls should use multiples of it: a call with fewer sources leaves CTAs
+ * idle, a call with slightly more runs a second, nearly empty wave. */
+int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, uint32_t *sources_per_wave);
+
 /* Intermediate state of one source, for exactness checks: dist[n] (UINT32_MAX =
  * unreached), npred[n] (number of BFS predecessors), sigma[n] (f64 shortest-path
  * counts; NOT used by the load), bk[n] (accumulated value b_k after the backward

@@ -40,6 +40,7 @@ NEC_SYMBOLS = {
     "nec_vertex_load_batch": (c_int, [c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "nec_distance_measures": (c_int, [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp]),
     "nec_bfs_debug": (c_int, [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]),
+    "nec_wave_size": (c_int, [c_vp, c_vp, c_u64, c_vp]),
     "nec_get_stats": (c_int, [c_vp, ctypes.POINTER(NecStats)]),
 }
 NECH_SYMBOLS = {

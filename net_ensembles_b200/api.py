@@ -112,6 +112,13 @@ class DeviceGraph:
         self.ctx._check(self.ctx._lib.nec_vertex_load_sources_device(self.ctx._h, self._h, _ptr(src), src.shape[0],
                                                                      int(bool(include_endpoints)), c_vp(d_out_ptr)))
 
+    def wave_size(self, n_sources_total=None):
+        """Sources the engine works on concurrently for a job of `n_sources_total` (default: all vertices)."""
+        w = ctypes.c_uint32(0)
+        total = self.n if n_sources_total is None else int(n_sources_total)
+        self.ctx._check(self.ctx._lib.nec_wave_size(self.ctx._h, self._h, total, ctypes.byref(w)))
+        return int(w.value)
+
     def distance_measures(self, sources=None):
         """(ecc, sum_dist, reached) per listed source (all vertices by default); exact integers."""
         src = np.arange(self.n, dtype=np.uint32) if sources is None else np.ascontiguousarray(sources, dtype=np.uint32)

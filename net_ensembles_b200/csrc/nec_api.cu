@@ -70,6 +70,7 @@ struct nec_ctx {
     bool mid_attr_set = false;
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
     bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
+    uint32_t team_size = 1;                           // batched engine: CTAs per slot (thread-block cluster), set per call
     nec::SmallWorkspace small;
     nec_stats stats{};
 };
@@ -201,6 +202,40 @@ int launch_engine_t(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots) {
     return NEC_OK;
 }
 
+// Cluster teams: `team` CTAs of 512 threads per slot (grid = slots x team, cluster dimension = team).
+template <typename DistT, int kSrc>
+cudaLaunchConfig_t team_config(cudaLaunchAttribute *attr, uint32_t slots, uint32_t team, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(slots * team);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = nec::engine_smem_bytes<DistT, 512, kSrc>();
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+// How many teams of `team` CTAs can be resident at once (0 on error).
+template <typename DistT, int kSrc>
+int team_capacity(uint32_t team) {
+    auto kern = nec::vertex_load_engine<DistT, 0, 512, kSrc, true>;
+    constexpr size_t smem = nec::engine_smem_bytes<DistT, 512, kSrc>();
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = team_config<DistT, kSrc>(attr, 1, team, nullptr);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+template <typename DistT, int kSrc>
+int launch_engine_team(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots, uint32_t team) {
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = team_config<DistT, kSrc>(attr, slots, team, ctx->stream);
+    NEC_CUDA(ctx, cudaLaunchKernelEx(&cfg, nec::vertex_load_engine<DistT, 0, 512, kSrc, true>, p));
+    return NEC_OK;
+}
+
 template <typename DistT, int kMode, int kSrc = 32>
 int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
                   uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk,
@@ -220,7 +255,12 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
     if (mo) { p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
-    const int rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024, kSrc>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512, kSrc>(ctx, p, slots);
+    int rc;
+    if constexpr (kMode == 0 && sizeof(DistT) == 1) {
+        if (ctx->team_size > 1) rc = launch_engine_team<DistT, kSrc>(ctx, p, slots, ctx->team_size);
+        else rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024, kSrc>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512, kSrc>(ctx, p, slots);
+    } else
+        rc = ctx->wide_ctas ? launch_engine_t<DistT, kMode, 1024, kSrc>(ctx, p, slots) : launch_engine_t<DistT, kMode, 512, kSrc>(ctx, p, slots);
     if (rc != NEC_OK) return rc;
     ctx->stats.kernel_launches++;
     return NEC_OK;
@@ -232,6 +272,58 @@ int engine_occupancy(nec_ctx *ctx) {
     NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0, 512, 32>, 512, nec::engine_smem_bytes<uint32_t, 512, 32>()));
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
+    return NEC_OK;
+}
+
+// How the batched engine runs a call: batch width, resident slots, CTA shape.  Shared by the run itself and
+// by nec_wave_size.
+struct BatchedPlan { uint32_t ksrc, want, slots, team; bool wide; };
+int plan_batched(nec_ctx *ctx, uint32_t n, uint32_t n_sources, bool debug, bool measure, BatchedPlan &out) {
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    // batch width: 64 sources per batch once there is at least one such batch per SM (the bit-parallel
+    // forward pass costs the same per adjacency entry at either width), else 32 for more parallelism
+    // -- provided the workspace budget holds one 64-wide slot per SM (a slot's state doubles with the
+    // width; with fewer slots than SMs the narrower batches win: same sources in flight, more CTAs)
+    uint32_t ksrc = 32u;
+    if (!debug && (n_sources + 63) / 64 >= sms) {
+        ArenaPlan plan64{};
+        int prc = plan_arena(ctx, n, 1, sms, 64u, plan64);
+        if (prc != NEC_OK) return prc;
+        if (plan64.slots >= sms) ksrc = 64u;
+    }
+    if (!debug && getenv("NEC_BATCH_WIDTH")) ksrc = atoi(getenv("NEC_BATCH_WIDTH")) == 64 ? 64u : 32u;
+    const uint32_t n_batches = (n_sources + ksrc - 1) / ksrc;
+    uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)ctx->occ_u8 * sms);
+    if (debug) want = 1;
+    ArenaPlan ap{};
+    int prc = plan_arena(ctx, n, 1, want, ksrc, ap);
+    if (prc != NEC_OK) return prc;
+    uint32_t slots = std::min<uint32_t>(want, ap.slots);
+    // large graphs (beyond the mid engine) and memory-limited slot counts: 1024-thread CTAs, one per SM.
+    // Same 32 warps per SM as 2 x 512, but half the resident slots (less HBM state in flight, smaller
+    // level-boundary imbalance): 1.3x faster on the N = 2^20 graph in a same-box A/B.
+    bool wide = !debug && (n > nec::kMidMaxN || (n_batches > slots && slots < sms + sms / 2));
+    if (getenv("NEC_BATCHED_WIDE")) wide = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
+    if (wide) slots = std::min<uint32_t>(slots, sms);
+    // fewer slots than SMs can keep busy (memory-limited: config 5 gets 96 slots on 148 SMs): several 512-thread
+    // CTAs per slot as a thread-block cluster, as many as fit two per SM
+    uint32_t team_size = 1;
+    if (wide && !measure && slots > 0 && n_batches >= slots) {
+        uint32_t team = std::min<uint32_t>(8u, 2u * sms / slots);
+        if (getenv("NEC_TEAM_SIZE")) team = (uint32_t)atoi(getenv("NEC_TEAM_SIZE"));
+        if (team >= 3 && team <= 8) {
+            const int cap = ksrc == 64 ? team_capacity<uint8_t, 64>(team) : team_capacity<uint8_t, 32>(team);
+            if (getenv("NEC_TEAM_VERBOSE")) fprintf(stderr, "[nec] cluster teams of %u: capacity %d, slots %u\n", team, cap, slots);
+            // clusters are placed per GPC, so slightly fewer teams than slots may fit (93 of 96 on a B200); a team
+            // finishes a batch ~1.2x sooner (measured on config 5), so trade slots for teams when the waves say so
+            if (cap >= (int)slots) team_size = team;
+            else if (cap > 0) {
+                const double waves_team = (double)((n_batches + cap - 1) / cap) / 1.2, waves_plain = (double)((n_batches + slots - 1) / slots);
+                if (waves_team < waves_plain) { team_size = team; slots = (uint32_t)cap; }
+            }
+        }
+    }
+    out = BatchedPlan{ksrc, want, slots, team_size, wide};
     return NEC_OK;
 }
 
@@ -251,24 +343,15 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     for (uint32_t k = 0; k < n_sources; ++k)
         if (h_sources[k] >= n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, n);
 
-    // batch width: 64 sources per batch once there is at least one such batch per SM (the bit-parallel
-    // forward pass costs the same per adjacency entry at either width), else 32 for more parallelism
+    BatchedPlan plan{};
+    int rc = plan_batched(ctx, n, n_sources, debug, mo != nullptr, plan);
+    if (rc != NEC_OK) return rc;
+    const uint32_t ksrc = plan.ksrc;
     const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
-    // -- provided the workspace budget holds one 64-wide slot per SM (a slot's state doubles with the
-    // width; with fewer slots than SMs the narrower batches win: same sources in flight, more CTAs)
-    uint32_t ksrc = 32u;
-    if (!debug && (n_sources + 63) / 64 >= sms) {
-        ArenaPlan plan64{};
-        int prc = plan_arena(ctx, n, 1, sms, 64u, plan64);
-        if (prc != NEC_OK) return prc;
-        if (plan64.slots >= sms) ksrc = 64u;
-    }
-    if (!debug && getenv("NEC_BATCH_WIDTH")) ksrc = atoi(getenv("NEC_BATCH_WIDTH")) == 64 ? 64u : 32u;
     const uint32_t n_batches32 = (n_sources + 31) / 32;
     const uint32_t n_batches = (n_sources + ksrc - 1) / ksrc;
     ctx->stats.n_batches = n_batches;
     ctx->stats.batch_width = ksrc;
-    int rc;
     if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
     if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches32)) != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -276,16 +359,10 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
     // ---- pass 1: 8-bit distances -----------------------------------------------------
-    uint32_t want = std::min<uint32_t>(n_batches, (uint32_t)ctx->occ_u8 * sms);
-    if (debug) want = 1;
-    if ((rc = ensure_arena(ctx, n, 1, want, ksrc)) != NEC_OK) return rc;
-    uint32_t slots = std::min<uint32_t>(want, ctx->arena.n_slots);
-    // large graphs (beyond the mid engine) and memory-limited slot counts: 1024-thread CTAs, one per SM.
-    // Same 32 warps per SM as 2 x 512, but half the resident slots (less HBM state in flight, smaller
-    // level-boundary imbalance): 1.3x faster on the N = 2^20 graph in a same-box A/B.
-    ctx->wide_ctas = !debug && (n > nec::kMidMaxN || (n_batches > slots && slots < sms + sms / 2));
-    if (getenv("NEC_BATCHED_WIDE")) ctx->wide_ctas = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
-    if (ctx->wide_ctas) slots = std::min<uint32_t>(slots, sms);
+    if ((rc = ensure_arena(ctx, n, 1, plan.want, ksrc)) != NEC_OK) return rc;
+    const uint32_t slots = std::min<uint32_t>(plan.slots, ctx->arena.n_slots);
+    ctx->wide_ctas = plan.wide;
+    ctx->team_size = slots == plan.slots ? plan.team : 1;
     const Arena &a = ctx->arena;
     NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * slots, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
@@ -345,6 +422,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
         if (debug) want2 = 1;
         ctx->wide_ctas = false;
+        ctx->team_size = 1;
         cudaStreamSynchronize(ctx->stream);  // arena may be reallocated below
         if ((rc = ensure_arena(ctx, n, 4, want2)) != NEC_OK) { cudaFree(d_keep); return rc; }
         const Arena &w = ctx->arena;
@@ -847,6 +925,26 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
     cudaSetDevice(ctx->device);
     return nec::small_batch_run(ctx->small, ctx->stream, ctx->ev0, ctx->ev1, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
                                 row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
+} NEC_CATCH_ALL(ctx)
+
+int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, uint32_t *sources_per_wave) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || !sources_per_wave) return fail(ctx, NEC_EINVAL, "nec_wave_size: NULL argument");
+    *sources_per_wave = 0;
+    if (g->n == 0 || n_sources_total == 0) return NEC_OK;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t ns = (uint32_t)std::min<uint64_t>(n_sources_total, 0xFFFFFFFFull);
+    const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
+                        ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
+    if (mid_ok) {       // one source per CTA, two CTAs per SM
+        *sources_per_wave = std::min<uint32_t>(ns, 2u * (uint32_t)ctx->prop.multiProcessorCount);
+        return NEC_OK;
+    }
+    BatchedPlan plan{};
+    const int rc = plan_batched(ctx, g->n, ns, false, false, plan);
+    if (rc != NEC_OK) return rc;
+    *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, (uint64_t)plan.slots * plan.ksrc);
+    return NEC_OK;
 } NEC_CATCH_ALL(ctx)
 
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out) {

@@ -41,6 +41,7 @@
 //     distances and reached count (nec_distance_measures).
 //   * slots' private b[] are summed in slot order by reduce_slots_kernel.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -167,9 +168,16 @@ constexpr size_t engine_smem_bytes() {
     return (size_t)(kThreads / 32) * (2 * 32 * sizeof(typename SrcTraits<kSrc>::Stage) + (sizeof(DistT) == 1 ? 2 * 32 * kSrc : 0));
 }
 
-template <typename DistT, int kMode, int kEngineThreads, int kSrc>
+// kTeam: the CTAs of a thread-block CLUSTER work on one slot together (cluster size from the launch).  Used when
+// memory holds fewer slots than there are SMs (config 5: 96 slots on 148 SMs): three 512-thread CTAs per slot
+// put 1536 threads on each batch.  The team shares the queue tail and the failure flag through distributed
+// shared memory (rank 0's copies) and meets at cluster barriers instead of __syncthreads; everything else is
+// per warp and unchanged, and since every (vertex, source) value still has exactly one writer and the same
+// summation order, results are bit-identical to the single-CTA kernel.
+template <typename DistT, int kMode, int kEngineThreads, int kSrc, bool kTeam = false>
 __global__ void __launch_bounds__(kEngineThreads, kEngineThreads == 512 ? 2 : 1)
 vertex_load_engine(const EngineParams p) {
+    static_assert(!kTeam || kMode == 0, "cluster teams run the vertex_load mode only");
     using ST = SrcTraits<kSrc>;
     using Mask = typename ST::Mask;
     using Stage = typename ST::Stage;
@@ -182,23 +190,59 @@ vertex_load_engine(const EngineParams p) {
     static_assert(!kDebug || kSrc == 32, "debug planes are 32 sources wide");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    uint32_t team_size = 1, team_rank = 0;               // CTAs per slot, this CTA's rank among them
+    if constexpr (kTeam) {
+        team_size = cooperative_groups::this_cluster().num_blocks();
+        team_rank = cooperative_groups::this_cluster().block_rank();
+    }
+    const uint32_t slot = blockIdx.x / team_size, n_slots = gridDim.x / team_size;
+    const uint32_t tid_t = team_rank * kEngineThreads + threadIdx.x;      // thread and warp index within the team
+    const uint32_t threads_t = team_size * kEngineThreads;
+    const uint32_t warp_t = team_rank * kWarps + warp, warps_t = team_size * kWarps;
+    auto team_sync = [&]() {
+        if constexpr (kTeam) cooperative_groups::this_cluster().sync();
+        else __syncthreads();
+    };
     const uint32_t lane_lt = (1u << lane) - 1u;
     const uint32_t n = p.n;
 
-    DistT *__restrict__ dist = reinterpret_cast<DistT *>(p.dist_base + (size_t)blockIdx.x * p.dist_stride);
-    double *__restrict__ q = p.q_base + (size_t)blockIdx.x * p.q_stride;
+    DistT *__restrict__ dist = reinterpret_cast<DistT *>(p.dist_base + (size_t)slot * p.dist_stride);
+    double *__restrict__ q = p.q_base + (size_t)slot * p.q_stride;
     // per-vertex mask record {seen, next[even level], next[odd level], -}: one 16 B / 32 B sector, so the
     // atomics that follow the `seen` test of a neighbour hit the sector that test just fetched
-    Mask *rec = reinterpret_cast<Mask *>(p.mask_base + (size_t)blockIdx.x * p.mask_stride);
-    double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
-    uint32_t *__restrict__ queue_v = p.queue_v_base + (size_t)blockIdx.x * p.queue_stride;
-    Mask *__restrict__ queue_m = reinterpret_cast<Mask *>(p.queue_m_base + (size_t)blockIdx.x * p.queue_stride * sizeof(Mask));
-    uint32_t *__restrict__ lvl = p.lvl_base + (size_t)blockIdx.x * p.lvl_stride;
+    Mask *rec = reinterpret_cast<Mask *>(p.mask_base + (size_t)slot * p.mask_stride);
+    double *__restrict__ bslot = p.bslot_base + (size_t)slot * p.bslot_stride;
+    uint32_t *__restrict__ queue_v = p.queue_v_base + (size_t)slot * p.queue_stride;
+    Mask *__restrict__ queue_m = reinterpret_cast<Mask *>(p.queue_m_base + (size_t)slot * p.queue_stride * sizeof(Mask));
+    uint32_t *__restrict__ lvl = p.lvl_base + (size_t)slot * p.lvl_stride;
     const uint32_t qcap = (uint32_t)p.queue_cap;
     const uint32_t level_limit = p.max_levels < DistTraits<DistT>::kMaxLevel ? p.max_levels : DistTraits<DistT>::kMaxLevel;
 
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
+    // a team's queue tail and failure flag are rank 0's copies, reached through distributed shared memory;
+    // a single CTA uses its own shared variables directly (shared-space atomics, no generic addressing)
+    uint32_t *tail_p = nullptr, *fail_p = nullptr;
+    if constexpr (kTeam) {
+        tail_p = cooperative_groups::this_cluster().map_shared_rank(&s_tail, 0);
+        fail_p = cooperative_groups::this_cluster().map_shared_rank(&s_fail, 0);
+    }
+    auto tail_add = [&](uint32_t cnt) -> uint32_t {
+        if constexpr (kTeam) return atomicAdd(tail_p, cnt);
+        else return atomicAdd(&s_tail, cnt);
+    };
+    auto tail_read = [&]() -> uint32_t {
+        if constexpr (kTeam) return *(volatile uint32_t *)tail_p;
+        else return s_tail;
+    };
+    auto fail_set = [&]() {
+        if constexpr (kTeam) *(volatile uint32_t *)fail_p = 1;
+        else s_fail = 1;
+    };
+    auto fail_read = [&]() -> bool {
+        if constexpr (kTeam) return *(volatile uint32_t *)fail_p != 0;
+        else return s_fail != 0;
+    };
     __shared__ unsigned long long s_msum[kSrc];          // kMode 2: per source of the batch
     __shared__ uint32_t s_mreach[kSrc], s_mecc[kSrc];
     __shared__ unsigned long long s_cnt[3];
@@ -212,7 +256,7 @@ vertex_load_engine(const EngineParams p) {
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 
-    for (uint32_t work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+    for (uint32_t work = slot; work < p.n_work; work += n_slots) {
         const uint32_t batch = p.work_list ? p.work_list[work] : work;
         uint32_t b_reached = 0, b_edges = 0, b_visits = 0;   // per lane, per batch; counted only if the batch completes
 
@@ -223,20 +267,20 @@ vertex_load_engine(const EngineParams p) {
         {
             uint4 *r16 = reinterpret_cast<uint4 *>(rec);
             const size_t n16 = (size_t)n * 4 * sizeof(Mask) / 16;
-            for (size_t i = threadIdx.x; i < n16; i += kEngineThreads) __stcg(&r16[i], make_uint4(0u, 0u, 0u, 0u));
+            for (size_t i = tid_t; i < n16; i += threads_t) __stcg(&r16[i], make_uint4(0u, 0u, 0u, 0u));
         }
         if (kDebug) {
             const size_t n16 = ((size_t)n * kSrc * sizeof(DistT)) / 16;
             uint4 *d16 = reinterpret_cast<uint4 *>(dist);
             const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (size_t i = threadIdx.x; i < n16; i += kEngineThreads) d16[i] = inf4;
+            for (size_t i = tid_t; i < n16; i += threads_t) d16[i] = inf4;
         }
         if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; }
         if (kMeasure && threadIdx.x < kSrc) { s_msum[threadIdx.x] = 0; s_mreach[threadIdx.x] = 0; s_mecc[threadIdx.x] = 0; }
-        __syncthreads();
+        team_sync();
 
         // ---- seed level 0: bit k <-> source k of the batch ------------------------------
-        if (warp == 0) {
+        if (warp_t == 0) {
 #pragma unroll
             for (int h = 0; h < kH; ++h) {
                 const uint32_t k = h * 32 + lane;
@@ -245,23 +289,24 @@ vertex_load_engine(const EngineParams p) {
                     const uint32_t s = p.sources[sidx];
                     dist[(size_t)s * kSrc + k] = (DistT)0;
                     const Mask old = atomicOr(&rec[(size_t)s * 4 + 1], (Mask)1 << k);
-                    if (old == 0) queue_v[atomicAdd(&s_tail, 1u)] = s;
+                    if (old == 0) queue_v[tail_add(1u)] = s;
                 }
             }
         }
 
-        __syncthreads();
+        team_sync();
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
         // ---- forward: level-synchronous, bit-parallel, one lane per adjacency entry -----
         uint32_t level = 0, qbeg = 0, qend = 0;
         bool too_deep = false;
         for (;;) {
-            __syncthreads();                         // previous level fully expanded
-            const uint32_t tail_now = s_tail < qcap ? s_tail : qcap;
-            __syncthreads();                         // every warp sampled the tail before it moves again
+            team_sync();                             // previous level fully expanded
+            const uint32_t tail_raw = tail_read();
+            const uint32_t tail_now = tail_raw < qcap ? tail_raw : qcap;
+            team_sync();                             // every warp sampled the tail before it moves again
             qbeg = qend;
             qend = tail_now;
-            if (threadIdx.x == 0) lvl[level] = qbeg;
+            if (tid_t == 0) lvl[level] = qbeg;
             if (qend == qbeg) break;                 // level `level` is empty: done
             if (level >= level_limit) { too_deep = true; break; }
             Mask *next_cur = rec + 1 + (level & 1);          // word of the record, indexed [4 * vertex]
@@ -272,7 +317,7 @@ vertex_load_engine(const EngineParams p) {
             // expansion needs no atomic on `seen` (a plain test suffices: bits of this and earlier levels are
             // final, and a source discovered twice on the level being built is caught by the atomic on next[]).
             // The entry's mask moves to the queue (the backward pass wants it there) and next[] cleans itself.
-            for (uint32_t idx = qbeg + threadIdx.x; idx < qend; idx += kEngineThreads) {
+            for (uint32_t idx = qbeg + tid_t; idx < qend; idx += threads_t) {
                 const uint32_t u = queue_v[idx];
                 const Mask m = __ldcg(&next_cur[(size_t)u * 4]);
                 const Mask sn = __ldcg(&rec[(size_t)u * 4]);
@@ -280,9 +325,9 @@ vertex_load_engine(const EngineParams p) {
                 __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // this parity is reused at level+2
                 queue_m[idx] = m;
             }
-            __syncthreads();
+            team_sync();
 
-            for (uint32_t tile = qbeg + warp * 32; tile < qend; tile += kWarps * 32) {
+            for (uint32_t tile = qbeg + warp_t * 32; tile < qend; tile += warps_t * 32) {
                 const uint32_t idx = tile + lane;
                 Mask m = 0;
                 uint32_t rs = 0, deg = 0, u = 0;
@@ -376,12 +421,12 @@ vertex_load_engine(const EngineParams p) {
                         if (bal) {
                             uint32_t base = 0;
                             const int leader = __ffs(bal) - 1;
-                            if (lane == leader) base = atomicAdd(&s_tail, (uint32_t)__popc(bal));
+                            if (lane == leader) base = tail_add((uint32_t)__popc(bal));
                             base = __shfl_sync(0xFFFFFFFFu, base, leader);
                             if (enqueue) {
                                 const uint32_t pos = base + __popc(bal & lane_lt);
                                 if (pos < qcap) queue_v[pos] = x[j];
-                                else s_fail = 1;
+                                else fail_set();
                             }
                         }
                     }
@@ -391,14 +436,14 @@ vertex_load_engine(const EngineParams p) {
         }
         // here: levels 0..level-1 are non-empty (if !too_deep), lvl[l] = start of level l,
         // lvl[level] = end of the last level.
-        __syncthreads();
-        const bool failed = s_fail != 0;
+        team_sync();
+        const bool failed = fail_read();
 
         if (too_deep || failed) {
             // leave the slot clean for the next batch: drop pending mask bits (rare path)
-            for (uint32_t v = threadIdx.x; v < n; v += kEngineThreads) { __stcg(&rec[(size_t)v * 4 + 1], (Mask)0); __stcg(&rec[(size_t)v * 4 + 2], (Mask)0); }
-            if (threadIdx.x == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
-            __syncthreads();
+            for (uint32_t v = tid_t; v < n; v += threads_t) { __stcg(&rec[(size_t)v * 4 + 1], (Mask)0); __stcg(&rec[(size_t)v * 4 + 2], (Mask)0); }
+            if (tid_t == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
+            team_sync();
             continue;
         }
         atomicAdd(&s_cnt[0], (unsigned long long)b_reached);
@@ -426,7 +471,7 @@ vertex_load_engine(const EngineParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t lb = lvl[l], le = lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
-            for (uint32_t tile = lb + warp * 32; tile < le; tile += kWarps * 32) {
+            for (uint32_t tile = lb + warp_t * 32; tile < le; tile += warps_t * 32) {
                 const uint32_t idx = tile + lane;
                 uint32_t w = 0, rs = 0, deg = 0;
                 Mask m = 0;
@@ -563,7 +608,7 @@ vertex_load_engine(const EngineParams p) {
                 if (cur >= 0) finish_entry();
                 if (idx < le && deg != 0) bslot[w] += my_total;     // one writer per vertex per level
             }
-            __syncthreads();
+            team_sync();
         }
         if (kDebug) {
             // the sources themselves (level 0) get bk but no load contribution
@@ -583,12 +628,12 @@ vertex_load_engine(const EngineParams p) {
                 }
             }
         }
-        if (threadIdx.x == 0) { p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
-        __syncthreads();
+        if (threadIdx.x == 0) { if (team_rank == 0) p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
+        team_sync();
     }
 
     // ---- flush counters -------------------------------------------------------------------
-    __syncthreads();
+    team_sync();                                         // (rank 0's shared memory stays alive until every CTA of the team is done)
     if (threadIdx.x < 3) atomicAdd(&p.counters[threadIdx.x], s_cnt[threadIdx.x]);
     if (threadIdx.x == 0) {
         atomicMax(&p.counters[3], (unsigned long long)my_depth);

@@ -12,7 +12,7 @@ if len(sys.argv) > 2:
     n = len(rp) - 1
     ctx = ne.Context(0)
     dg = ctx.upload(rp, col)
-    ns = 9472 if which == "erm" else 3072
+    ns = int(os.environ.get("AB_NS", 9472 if which == "erm" else 3072))
     src = (np.arange(ns, dtype=np.uint64) * 2654435761 % n).astype(np.uint32)
     ts = []
     for _ in range(3):

@@ -483,3 +483,46 @@ def test_full_size_properties_config5_barabasi_albert(ctx, oracle):
     src = (np.arange(1536, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
     st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)
     assert st["reached_pairs"] == 1536 * (1 << 22)           # a BA graph is connected
+
+
+@pytest.mark.parametrize("width", ["32", "64"])
+def test_cluster_teams_are_bitwise_identical_to_single_ctas(ctx, oracle, monkeypatch, width):
+    """Memory-limited slot counts run each slot on a thread-block cluster of 512-thread CTAs (shared queue tail
+    in distributed shared memory, cluster barriers).  Same writers, same summation order: bit-identical."""
+    g = ne.ErEnsembleC(1800, 3.0, 77)                        # several components, isolated vertices
+    rp, col = g.export_csr()
+    ba = ne.ba_scalable(5000, 3, 4, 9)                       # hubs
+    rp2, col2 = ba.export_csr()
+    ctx.set_engine(1)
+    monkeypatch.setenv("NEC_BATCH_WIDTH", width)
+    monkeypatch.setenv("NEC_BATCHED_WIDE", "1")
+    for rp_, col_, src in ((rp, col, None), (rp2, col2, np.arange(0, 5000, 3, dtype=np.uint32))):
+        dg = ctx.upload(rp_, col_)
+        monkeypatch.setenv("NEC_TEAM_SIZE", "1")
+        one = dg.vertex_load(False) if src is None else dg.vertex_load_sources(src, False)
+        monkeypatch.setenv("NEC_TEAM_SIZE", "3")
+        team = dg.vertex_load(False) if src is None else dg.vertex_load_sources(src, False)
+        st = ctx.stats()
+        monkeypatch.setenv("NEC_TEAM_SIZE", "4")
+        team4 = dg.vertex_load(False) if src is None else dg.vertex_load_sources(src, False)
+        assert one.tobytes() == team.tobytes() == team4.tobytes()
+        assert close(team, oracle.vertex_load(rp_, col_, False, sources=src, threads=0), REL)
+        assert st["batch_width"] == int(width)
+        dg.free()
+    ctx.set_engine(0)
+
+
+def test_wave_size_matches_what_a_call_uses(ctx):
+    sw = ne.SwEnsemble(4096, 0.1, 3)
+    dg = sw.to_device(ctx)
+    assert dg.wave_size() == 296 and dg.wave_size(10) == 10           # mid engine: one source per CTA, two CTAs per SM
+    dg.free()
+    g = ne.gnm_scalable(200_000, 800_000, 5)                           # beyond the mid engine: batched
+    rp, col = g.export_csr()
+    dg = ctx.upload(rp, col)
+    wave = dg.wave_size()
+    src = np.arange(wave, dtype=np.uint32)
+    dg.vertex_load_sources(src, True)
+    st = ctx.stats()
+    assert st["engine"] == 1 and st["n_slots"] * st["batch_width"] == wave and st["n_batches"] == st["n_slots"]
+    dg.free()
