@@ -39,6 +39,10 @@
 //     level => no atomics).  Predecessor lists are never materialised; sigma never enters the
 //     value.  kMode 2 runs the forward pass only and reports per-source eccentricity, sum of
 //     distances and reached count (nec_distance_measures).
+//   * CTA shape follows residency: 2 x 512 threads per SM when slots are plentiful, 1 x 1024 when memory
+//     allows about one slot per SM, and - when it allows fewer slots than SMs - a thread-block CLUSTER of
+//     512-thread CTAs per slot (kTeam): the team splits each level's tiles, shares the queue tail and the
+//     failure flag through distributed shared memory and meets at cluster barriers.
 //   * slots' private b[] are summed in slot order by reduce_slots_kernel.
 #pragma once
 #include <cooperative_groups.h>

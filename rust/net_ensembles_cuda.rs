@@ -31,6 +31,7 @@ extern "C" {
                              ecc: *mut u32, sum_dist: *mut u64, reached: *mut u32) -> c_int;
     #[allow(dead_code)]
     fn nec_set_stream(ctx: *mut NecCtx, cuda_stream: *mut c_void) -> c_int;
+    fn nec_wave_size(ctx: *mut NecCtx, g: *const NecGraph, n_sources_total: u64, sources_per_wave: *mut u32) -> c_int;
 }
 
 /// One GPU context (device, stream, workspace).  Not `Sync`: one per thread, like the C ABI says.
