@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -280,16 +281,18 @@ int engine_occupancy(nec_ctx *ctx) {
 struct BatchedPlan { uint32_t ksrc, want, slots, team; bool wide; };
 int plan_batched(nec_ctx *ctx, uint32_t n, uint32_t n_sources, bool debug, bool measure, BatchedPlan &out) {
     const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
-    // batch width: 64 sources per batch once there is at least one such batch per SM (the bit-parallel
-    // forward pass costs the same per adjacency entry at either width), else 32 for more parallelism
-    // -- provided the workspace budget holds one 64-wide slot per SM (a slot's state doubles with the
-    // width; with fewer slots than SMs the narrower batches win: same sources in flight, more CTAs)
+    // batch width: 64 sources per batch (the bit-parallel forward pass costs the same per adjacency entry at
+    // either width, and a 64 B distance row is a whole DRAM burst) when the call has enough batches to fill the
+    // slots a 64-wide layout gets AND those slots can keep the GPU busy: one per SM, or - a slot's state doubles
+    // with the width, so huge graphs get fewer - at least the 2*SMs/8 that cluster teams of up to eight 512-thread
+    // CTAs fill the GPU from.  Else 32: more, narrower batches.
     uint32_t ksrc = 32u;
-    if (!debug && (n_sources + 63) / 64 >= sms) {
+    if (!debug && n_sources >= 64) {
         ArenaPlan plan64{};
         int prc = plan_arena(ctx, n, 1, sms, 64u, plan64);
         if (prc != NEC_OK) return prc;
-        if (plan64.slots >= sms) ksrc = 64u;
+        const uint32_t nb64 = (n_sources + 63) / 64, min_team_slots = (2 * sms + 7) / 8;
+        if (plan64.slots >= sms ? nb64 >= sms : (plan64.slots >= min_team_slots && nb64 >= plan64.slots)) ksrc = 64u;
     }
     if (!debug && getenv("NEC_BATCH_WIDTH")) ksrc = atoi(getenv("NEC_BATCH_WIDTH")) == 64 ? 64u : 32u;
     const uint32_t n_batches = (n_sources + ksrc - 1) / ksrc;
@@ -305,23 +308,28 @@ int plan_batched(nec_ctx *ctx, uint32_t n, uint32_t n_sources, bool debug, bool 
     bool wide = !debug && (n > nec::kMidMaxN || (n_batches > slots && slots < sms + sms / 2));
     if (getenv("NEC_BATCHED_WIDE")) wide = atoi(getenv("NEC_BATCHED_WIDE")) != 0;
     if (wide) slots = std::min<uint32_t>(slots, sms);
-    // fewer slots than SMs can keep busy (memory-limited: config 5 gets 96 slots on 148 SMs): several 512-thread
-    // CTAs per slot as a thread-block cluster, as many as fit two per SM
+    // fewer slots than SMs can keep busy (memory-limited: config 5): several 512-thread CTAs per slot as a
+    // thread-block cluster.  Clusters are placed per GPC, so cudaOccupancyMaxActiveClusters decides how many
+    // teams of each size fit (93 of 3, 71 of 4, 56 of 5, 45 of 6 on a B200); a batch finishes sooner the more
+    // threads work on it (~ threads^0.75 measured), and the static batch -> slot mapping costs whole waves.
     uint32_t team_size = 1;
     if (wide && !measure && slots > 0 && n_batches >= slots) {
-        uint32_t team = std::min<uint32_t>(8u, 2u * sms / slots);
-        if (getenv("NEC_TEAM_SIZE")) team = (uint32_t)atoi(getenv("NEC_TEAM_SIZE"));
-        if (team >= 3 && team <= 8) {
+        const uint32_t tmax = std::min<uint32_t>(8u, 2u * sms / slots);
+        const bool verbose = getenv("NEC_TEAM_VERBOSE") != nullptr;
+        auto cost = [&](uint32_t s, double units) { return (double)((n_batches + s - 1) / s) / pow(units, 0.75); };
+        double best = cost(slots, 2.0);                 // one 1024-thread CTA per slot = two 512-thread units
+        uint32_t best_slots = slots;
+        uint32_t t_lo = 3, t_hi = tmax;
+        if (getenv("NEC_TEAM_SIZE")) { t_lo = t_hi = (uint32_t)atoi(getenv("NEC_TEAM_SIZE")); best = 1e300; }
+        for (uint32_t team = t_hi; team >= t_lo && team >= 2 && team <= 8; --team) {
             const int cap = ksrc == 64 ? team_capacity<uint8_t, 64>(team) : team_capacity<uint8_t, 32>(team);
-            if (getenv("NEC_TEAM_VERBOSE")) fprintf(stderr, "[nec] cluster teams of %u: capacity %d, slots %u\n", team, cap, slots);
-            // clusters are placed per GPC, so slightly fewer teams than slots may fit (93 of 96 on a B200); a team
-            // finishes a batch ~1.2x sooner (measured on config 5), so trade slots for teams when the waves say so
-            if (cap >= (int)slots) team_size = team;
-            else if (cap > 0) {
-                const double waves_team = (double)((n_batches + cap - 1) / cap) / 1.2, waves_plain = (double)((n_batches + slots - 1) / slots);
-                if (waves_team < waves_plain) { team_size = team; slots = (uint32_t)cap; }
-            }
+            if (verbose) fprintf(stderr, "[nec] cluster teams of %u: capacity %d, slots %u\n", team, cap, slots);
+            if (cap <= 0) continue;
+            const uint32_t s_t = std::min<uint32_t>(slots, (uint32_t)cap);
+            const double c = cost(s_t, (double)team);
+            if (c < best) { best = c; team_size = team; best_slots = s_t; }
         }
+        slots = best_slots;
     }
     out = BatchedPlan{ksrc, want, slots, team_size, wide};
     return NEC_OK;
