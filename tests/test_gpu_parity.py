@@ -508,6 +508,20 @@ def test_cluster_teams_are_bitwise_identical_to_single_ctas(ctx, oracle, monkeyp
         assert one.tobytes() == team.tobytes() == team4.tobytes()
         assert close(team, oracle.vertex_load(rp_, col_, False, sources=src, threads=0), REL)
         assert st["batch_width"] == int(width)
+        # few slots, many batches per slot: the team re-uses queues, masks and rows batch after batch
+        # (partial loads are summed per slot, so the comparison is at the same slot count)
+        # (only on the shallow BA graph: a tight budget also shrinks the queues to 8 entries per vertex)
+        if rp_ is rp:
+            dg.free()
+            continue
+        ctx.set_workspace_limit(16_000_000 * int(width) // 32)
+        monkeypatch.setenv("NEC_TEAM_SIZE", "1")
+        few = dg.vertex_load(False) if src is None else dg.vertex_load_sources(src, False)
+        monkeypatch.setenv("NEC_TEAM_SIZE", "3")
+        again = dg.vertex_load(False) if src is None else dg.vertex_load_sources(src, False)
+        st = ctx.stats()
+        assert st["n_batches"] >= 3 * st["n_slots"] and again.tobytes() == few.tobytes() and close(again, one, 1e-12)
+        ctx.set_workspace_limit(0)
         dg.free()
     ctx.set_engine(0)
 
