@@ -72,6 +72,7 @@ struct nec_ctx {
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
     bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
     uint32_t team_size = 1;                           // batched engine: CTAs per slot (thread-block cluster), set per call
+    int team_cap[2][9];                               // resident clusters per (batch width 32/64, team size); -1 = not asked yet
     nec::SmallWorkspace small;
     nec_stats stats{};
 };
@@ -273,6 +274,7 @@ int engine_occupancy(nec_ctx *ctx) {
     NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, nec::vertex_load_engine<uint32_t, 0, 512, 32>, 512, nec::engine_smem_bytes<uint32_t, 512, 32>()));
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
+    for (auto &row : ctx->team_cap) for (int &c : row) c = -1;
     return NEC_OK;
 }
 
@@ -322,7 +324,9 @@ int plan_batched(nec_ctx *ctx, uint32_t n, uint32_t n_sources, bool debug, bool 
         uint32_t t_lo = 3, t_hi = tmax;
         if (getenv("NEC_TEAM_SIZE")) { t_lo = t_hi = (uint32_t)atoi(getenv("NEC_TEAM_SIZE")); best = 1e300; }
         for (uint32_t team = t_hi; team >= t_lo && team >= 2 && team <= 8; --team) {
-            const int cap = ksrc == 64 ? team_capacity<uint8_t, 64>(team) : team_capacity<uint8_t, 32>(team);
+            int &cached = ctx->team_cap[ksrc == 64][team];
+            if (cached < 0) cached = ksrc == 64 ? team_capacity<uint8_t, 64>(team) : team_capacity<uint8_t, 32>(team);
+            const int cap = cached;
             if (verbose) fprintf(stderr, "[nec] cluster teams of %u: capacity %d, slots %u\n", team, cap, slots);
             if (cap <= 0) continue;
             const uint32_t s_t = std::min<uint32_t>(slots, (uint32_t)cap);
