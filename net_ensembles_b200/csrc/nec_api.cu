@@ -733,14 +733,21 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr[0] must be 0 and row_ptr[n] == nnz");
     std::vector<uint32_t> rp32((size_t)n + 1);
     uint32_t max_deg = 0;
-    for (uint32_t v = 0; v < n; ++v) {
-        if (row_ptr[v + 1] < row_ptr[v]) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr not monotone at %u", v);
+    // validation and the 64 -> 32 bit row pointers on all host cores for large graphs (tens of ms at N = 2^22)
+    long long bad_row = (long long)n, bad_entry = (long long)nnz;
+#pragma omp parallel for schedule(static) reduction(max : max_deg) reduction(min : bad_row) if (n > 100000)
+    for (long long v = 0; v < (long long)n; ++v) {
+        if (row_ptr[v + 1] < row_ptr[v]) bad_row = std::min(bad_row, v);
+        else max_deg = std::max<uint32_t>(max_deg, (uint32_t)std::min<uint64_t>(row_ptr[v + 1] - row_ptr[v], 0xFFFFFFFFull));
         rp32[v] = (uint32_t)row_ptr[v];
-        max_deg = std::max<uint32_t>(max_deg, (uint32_t)(row_ptr[v + 1] - row_ptr[v]));
     }
+    if (bad_row < (long long)n) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr not monotone at %u", (uint32_t)bad_row);
     rp32[n] = (uint32_t)nnz;
-    for (uint64_t e = 0; e < nnz; ++e)
-        if (col_idx[e] >= n) return fail(ctx, NEC_EINVAL, "nec_graph_upload: col_idx[%llu]=%u out of range (n=%u)", (unsigned long long)e, col_idx[e], n);
+#pragma omp parallel for schedule(static) reduction(min : bad_entry) if (nnz > 400000)
+    for (long long e = 0; e < (long long)nnz; ++e)
+        if (col_idx[e] >= n) bad_entry = std::min(bad_entry, e);
+    if (bad_entry < (long long)nnz)
+        return fail(ctx, NEC_EINVAL, "nec_graph_upload: col_idx[%llu]=%u out of range (n=%u)", (unsigned long long)bad_entry, col_idx[bad_entry], n);
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     nec_graph *g = new (std::nothrow) nec_graph();
     if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
