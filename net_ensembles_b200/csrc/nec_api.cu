@@ -942,7 +942,7 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
         return fail(ctx, NEC_EINVAL, "nec_vertex_load_batch: NULL argument");
     ctx->stats = nec_stats{};
     cudaSetDevice(ctx->device);
-    return nec::small_batch_run(ctx->small, ctx->stream, ctx->ev0, ctx->ev1, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
+    return nec::small_batch_run(ctx->small, ctx->stream, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
                                 row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
 } NEC_CATCH_ALL(ctx)
 

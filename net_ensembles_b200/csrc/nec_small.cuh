@@ -248,7 +248,7 @@ inline int small_fail(std::string *err, int code, const std::string &msg) { if (
 // The call is synchronous (host pointers in, host pointers out) but pipelined inside: the graphs are cut
 // into up to 8 chunks; while the kernel works on chunk c, chunk c+1 is validated and packed into pinned
 // memory by all host cores and copied in, and chunk c-1's loads are copied out and handed to the caller.
-inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, cudaEvent_t, cudaEvent_t, std::string *err,
+inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, std::string *err,
                            nec_stats *stats, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *rp_off,
                            const uint32_t *rp, const uint64_t *col_off, const uint32_t *col, int include_endpoints, double *out) {
     if (n_graphs == 0) return NEC_OK;
