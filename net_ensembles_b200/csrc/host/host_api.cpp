@@ -206,7 +206,11 @@ void prepare_group(ChainGroup &grp, void *const *handles, uint32_t g0, uint32_t 
     const uint32_t cnt = g1 - g0;
     grp.n_per.resize(cnt); grp.rp_off.resize(cnt); grp.col_off.resize(cnt);
     int bad = 0;
-    // chains are independent: step them on all host cores (each chain owns its generator)
+    std::vector<uint64_t> &nnz_per = grp.col_off;        // first the per-graph entry counts, then their prefix sums
+    // chains are independent: step them on all host cores (each chain owns its generator).  A CSR's size is
+    // 2 x edge_count (every edge sits in both endpoints' lists; the containers keep the count), so sizing needs
+    // no walk over the 256 separately allocated adjacency vectors of each chain - the export below is the only
+    // pass over them, and it checks the size it was promised
 #pragma omp parallel for schedule(static) reduction(+ : bad)
     for (int64_t g = g0; g < (int64_t)g1; ++g) {
         Handle *h = static_cast<Handle *>(handles[g]);
@@ -216,34 +220,43 @@ void prepare_group(ChainGroup &grp, void *const *handles, uint32_t g0, uint32_t 
             case Kind::Sw: h->sw->m_step(); break;
             default: bad += 1; k = m_steps; break;
         }
+        with_graph(h, [&](auto &gr) {
+            grp.n_per[g - g0] = (uint32_t)gr.vertex_count();
+            nnz_per[g - g0] = 2 * (uint64_t)gr.edge_count;
+            return 0;
+        });
     }
     grp.bad = bad;
     uint64_t rp_total = 0, col_total = 0, out_count = 0;
-    for (uint32_t g = g0; g < g1; ++g)
-        with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
-            grp.n_per[g - g0] = (uint32_t)gr.vertex_count();
-            grp.rp_off[g - g0] = rp_total; grp.col_off[g - g0] = col_total;
-            rp_total += gr.vertex_count() + 1; col_total += gr.nnz(); out_count += gr.vertex_count();
-            return 0;
-        });
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint64_t nnz_k = nnz_per[k];
+        grp.rp_off[k] = rp_total; grp.col_off[k] = col_total;
+        rp_total += grp.n_per[k] + 1; col_total += nnz_k; out_count += grp.n_per[k];
+    }
     grp.out_count = out_count;
     if (grp.rp.size() < rp_total) grp.rp.resize(rp_total + rp_total / 8);
     if (grp.col.size() < col_total + 1) grp.col.resize(col_total + col_total / 8 + 1);
     uint32_t *const rp_buf = grp.rp.data(), *const col_buf = grp.col.data();
     const uint64_t *const rp_off = grp.rp_off.data(), *const col_off = grp.col_off.data();
-#pragma omp parallel for schedule(static)
+    int mismatch = 0;
+#pragma omp parallel for schedule(static) reduction(+ : mismatch)
     for (int64_t g = g0; g < (int64_t)g1; ++g)
         with_graph(static_cast<Handle *>(handles[g]), [&](auto &gr) {
             uint32_t *r = rp_buf + rp_off[g - g0];
             uint32_t *c = col_buf + col_off[g - g0];
-            uint32_t at = 0;
+            const uint64_t room = 2 * (uint64_t)gr.edge_count;
+            uint64_t at = 0;
             for (size_t v = 0; v < gr.vertices.size(); ++v) {
-                r[v] = at;
-                for (auto &e : gr.vertices[v].adj) c[at++] = e.to;
+                r[v] = (uint32_t)at;
+                const auto &adj = gr.vertices[v].adj;
+                if (at + adj.size() > room) { mismatch += 1; break; }    // never: edge_count is maintained by add/remove
+                for (auto &e : adj) c[at++] = e.to;
             }
-            r[gr.vertices.size()] = at;
+            r[gr.vertices.size()] = (uint32_t)at;
+            if (at != room) mismatch += 1;
             return 0;
         });
+    if (mismatch) grp.bad = -2;
 }
 }  // namespace
 
@@ -256,7 +269,7 @@ int nech_chains_step_and_load_cuda(void *const *handles, uint32_t n_chains, uint
         g_chain_stats = nec_stats{};
         ChainGroup &grp = g_group;
         prepare_group(grp, handles, 0, n_chains, m_steps);
-        if (grp.bad) { g_err = "chain has no Markov step"; return NEC_EINVAL; }
+        if (grp.bad) { g_err = grp.bad == -2 ? "adjacency lists disagree with edge_count" : "chain has no Markov step"; return NEC_EINVAL; }
         const double t1 = now();
         const int rc = nec_vertex_load_batch(ctx, n_chains, grp.n_per.data(), grp.rp_off.data(), grp.rp.data(),
                                              grp.col_off.data(), grp.col.data(), include_endpoints, out);
