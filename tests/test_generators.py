@@ -91,3 +91,20 @@ def test_pcg64_known_answer(built):
     assert a.tolist() == b.tolist()
     lib.nech_pcg64_draws(2, 4, b.ctypes.data)
     assert a.tolist() != b.tolist()
+
+
+def test_adjacency_entries_are_twice_the_edge_count_after_any_move():
+    """The chain exporter sizes a CSR as 2 * edge_count without walking the adjacency lists (and checks it
+    while exporting): the containers must keep the count through every kind of move."""
+    import net_ensembles_b200 as ne
+    ens = [ne.ErEnsembleC(200, 3.0, 1), ne.ErEnsembleM(150, 400, 2), ne.SwEnsemble(300, 0.3, 3), ne.BAensemble(120, 3, 4, 5)]
+    for e in ens:
+        for _ in range(3):
+            rp, col = e.export_csr()
+            assert len(col) == 2 * e.edge_count() and int(rp[-1]) == len(col)      # export_csr sizes by walking the lists
+            e.randomize()
+            if not isinstance(e, ne.BAensemble):
+                e.m_steps(500)
+    g = ne.Graph(10)
+    assert g.add_edge(0, 1) and g.add_edge(1, 2) and not g.add_edge(0, 1) and g.remove_edge(0, 1) and not g.remove_edge(0, 1)
+    assert len(g.export_csr()[1]) == 2 * g.edge_count() == 2
