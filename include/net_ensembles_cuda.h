@@ -168,6 +168,10 @@ typedef struct nec_stats {
     uint32_t engine;          /* traversal kernel that ran: 1 batched (vertex_load_engine), 2 mid (mid_engine),
                                  3 small-graph batch (small_graph_kernel); batched|mid<<4 if mid handed sources back */
     uint32_t batch_width;     /* sources per batch of the batched engine in this call: 32 or 64 (0: engine not used) */
+    uint32_t team_size;       /* batched engine: CTAs per batch slot (thread-block cluster size; 1 = one CTA per slot) */
+    uint32_t cta_threads;     /* threads per CTA of the traversal kernel that ran */
+    uint32_t pull_levels;     /* batched engine: (batch, level) expansions done in pull direction ... */
+    uint32_t push_levels;     /* ... and in push direction */
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);
 

@@ -70,6 +70,7 @@ struct nec_ctx {
     uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
     bool mid_attr_set = false;
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
+    uint32_t pull_mode = 1;                           // batched forward pass: 0 push only, 1 per-level cost model, 2 pull only (NEC_PULL, tests)
     bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
     uint32_t team_size = 1;                           // batched engine: CTAs per slot (thread-block cluster), set per call
     int team_cap[2][9];                               // resident clusters per (batch width 32/64, team size); -1 = not asked yet
@@ -247,6 +248,9 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.n = g->n; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
     p.sources = ctx->d_sources; p.n_sources = n_sources;
     p.work_list = d_worklist; p.n_work = n_work; p.include_endpoints = include_endpoints;
+    p.pull_mode = ctx->pull_mode;
+    if (const char *env = getenv("NEC_PULL")) p.pull_mode = (uint32_t)std::min(2, std::max(0, atoi(env)));   // tests / A-B runs
+    p.avg_deg = (uint32_t)std::max<uint64_t>(1, (g->nnz + g->n - 1) / std::max<uint32_t>(g->n, 1u));
     p.dist_base = a.dist; p.dist_stride = a.dist_stride;
     p.q_base = a.q; p.q_stride = a.q_stride;
     p.mask_base = a.mask; p.mask_stride = a.mask_stride;
@@ -375,6 +379,7 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     const uint32_t slots = std::min<uint32_t>(plan.slots, ctx->arena.n_slots);
     ctx->wide_ctas = plan.wide;
     ctx->team_size = slots == plan.slots ? plan.team : 1;
+    const uint32_t team_used = ctx->team_size, cta_threads_used = ctx->team_size > 1 ? 512u : (ctx->wide_ctas ? 1024u : 512u);
     const Arena &a = ctx->arena;
     NEC_CUDA(ctx, cudaMemsetAsync(a.mask, 0, a.mask_stride * slots, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
@@ -473,6 +478,10 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
         }
     }
     ctx->stats.engine = 1;
+    ctx->stats.team_size = team_used;
+    ctx->stats.cta_threads = cta_threads_used;
+    ctx->stats.pull_levels = (uint32_t)(counters[7] >> 32);
+    ctx->stats.push_levels = (uint32_t)counters[7];
     ctx->stats.reached_pairs = counters[0];
     ctx->stats.edge_pairs = counters[1];
     ctx->stats.vertex_visits = counters[2];
@@ -570,6 +579,8 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.engine_ms = ms;
     ctx->stats.kernel_launches = 2;
     ctx->stats.engine = 2;
+    ctx->stats.team_size = 1;
+    ctx->stats.cta_threads = nec::kMidThreads;
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->mid_bytes;
     for (uint32_t k = 0; k < n_sources; ++k) {

@@ -55,7 +55,9 @@ constexpr int kLanes = 32;            // lanes per warp = sources per narrow bat
 // CTA shape: 512 threads x 2 CTAs per SM when the workspace budget allows two slots per SM, else
 // 1024 threads x 1 CTA per SM (large graphs are slot-limited by memory; wider CTAs keep the SMs busy)
 constexpr int kUnroll = 8;            // neighbour rows in flight per warp step (backward)
-constexpr int kFwdUnroll = 4;         // flattened adjacency entries per lane and step (forward)
+constexpr int kFwdUnroll = 4;         // flattened adjacency entries per lane and step (forward, push)
+constexpr int kPullUnroll = 4;        // neighbours' frontier masks in flight per thread (forward, pull)
+constexpr uint32_t kPullHubDeg = 64;  // longer adjacency lists are gathered by a whole warp in the pull scan
 
 enum BatchStatus : uint8_t { kPending = 0, kDone = 1, kTooDeep = 2, kQueueOverflow = 3 };
 
@@ -70,6 +72,10 @@ struct EngineParams {
     const uint32_t *__restrict__ work_list;   // batch ids to run (nullptr: 0..n_work-1)
     uint32_t n_work;
     int include_endpoints;
+    // forward pass direction per level: 0 always push (frontier -> neighbours, atomics on next[]), 1 cost model,
+    // 2 always pull (every not-yet-complete vertex gathers its neighbours' frontier masks; no atomics)
+    uint32_t pull_mode;
+    uint32_t avg_deg;                         // ceil(nnz / n), >= 1 (cost model of the direction choice)
     // per-slot arenas (slot = blockIdx.x)
     uint8_t *dist_base;   size_t dist_stride;   // bytes per slot
     double *q_base;       size_t q_stride;      // doubles per slot
@@ -83,7 +89,7 @@ struct EngineParams {
     uint32_t max_levels;                        // deepest level index the slot can record
     // outputs
     uint8_t *batch_status;                      // per batch id
-    unsigned long long *counters;               // [0] reached pairs [1] edge pairs [2] visits [3] max depth [4..6] CTA cycles in reset/forward/backward
+    unsigned long long *counters;               // [0] reached pairs [1] edge pairs [2] visits [3] max depth [4..6] CTA cycles in reset/forward/backward [7] pulled << 32 | pushed level expansions
     // optional per-(vertex,lane) debug planes of slot 0 (nec_bfs_debug)
     uint32_t *dbg_npred;
     double *dbg_bk;
@@ -224,13 +230,23 @@ vertex_load_engine(const EngineParams p) {
 
     __shared__ uint32_t s_tail;
     __shared__ uint32_t s_fail;
+    __shared__ uint32_t s_open;                          // pull scans count the vertices that still miss a source
     // a team's queue tail and failure flag are rank 0's copies, reached through distributed shared memory;
     // a single CTA uses its own shared variables directly (shared-space atomics, no generic addressing)
-    uint32_t *tail_p = nullptr, *fail_p = nullptr;
+    uint32_t *tail_p = nullptr, *fail_p = nullptr, *open_p = nullptr;
     if constexpr (kTeam) {
         tail_p = cooperative_groups::this_cluster().map_shared_rank(&s_tail, 0);
         fail_p = cooperative_groups::this_cluster().map_shared_rank(&s_fail, 0);
+        open_p = cooperative_groups::this_cluster().map_shared_rank(&s_open, 0);
     }
+    auto open_add = [&](uint32_t cnt) {
+        if constexpr (kTeam) atomicAdd(open_p, cnt);
+        else atomicAdd(&s_open, cnt);
+    };
+    auto open_read = [&]() -> uint32_t {
+        if constexpr (kTeam) return *(volatile uint32_t *)open_p;
+        else return s_open;
+    };
     auto tail_add = [&](uint32_t cnt) -> uint32_t {
         if constexpr (kTeam) return atomicAdd(tail_p, cnt);
         else return atomicAdd(&s_tail, cnt);
@@ -258,6 +274,7 @@ vertex_load_engine(const EngineParams p) {
 
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
+    unsigned long long dir_levels = 0;                      // thread 0 only: pulled levels << 32 | pushed levels
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 
     for (uint32_t work = slot; work < p.n_work; work += n_slots) {
@@ -279,7 +296,7 @@ vertex_load_engine(const EngineParams p) {
             const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             for (size_t i = tid_t; i < n16; i += threads_t) d16[i] = inf4;
         }
-        if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; }
+        if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; s_open = 0; }
         if (kMeasure && threadIdx.x < kSrc) { s_msum[threadIdx.x] = 0; s_mreach[threadIdx.x] = 0; s_mecc[threadIdx.x] = 0; }
         team_sync();
 
@@ -300,35 +317,62 @@ vertex_load_engine(const EngineParams p) {
 
         team_sync();
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
-        // ---- forward: level-synchronous, bit-parallel, one lane per adjacency entry -----
+        // ---- forward: level-synchronous, bit-parallel; direction chosen per level -------
+        // PUSH (narrow levels): one lane per adjacency entry of the frontier, atomicOr into next[] of the neighbour.
+        // PULL (wide levels): one thread per vertex that still misses a source ORs the frontier masks of its
+        // neighbours - no atomics, one writer per vertex, the vertex records / row pointers / adjacency lists are
+        // read as streams and only the neighbours' 8-byte frontier masks are random reads.  Both produce the same
+        // level sets, masks and (up to order within a level, which no sum depends on) queues.
         uint32_t level = 0, qbeg = 0, qend = 0;
         bool too_deep = false;
+        uint32_t n_open = n;                         // vertices that miss a source of the batch (upper bound until a pull scan counts them)
+        uint32_t defer_beg = 0, defer_end = 0;       // queue range of a pulled level: its next[] words are cleared one level later
+        bool prev_pull = false;
+        Mask valid_src = ~(Mask)0;                   // sources this batch really has
+        {
+            const uint32_t first = batch * kSrc;
+            const uint32_t have = p.n_sources - first < (uint32_t)kSrc ? p.n_sources - first : (uint32_t)kSrc;
+            if (have < (uint32_t)kSrc) valid_src = ((Mask)1 << have) - 1;
+        }
         for (;;) {
             team_sync();                             // previous level fully expanded
             const uint32_t tail_raw = tail_read();
+            const uint32_t open_raw = open_read();
             const uint32_t tail_now = tail_raw < qcap ? tail_raw : qcap;
             team_sync();                             // every warp sampled the tail before it moves again
             qbeg = qend;
             qend = tail_now;
+            if (prev_pull) n_open = open_raw;
             if (tid_t == 0) lvl[level] = qbeg;
             if (qend == qbeg) break;                 // level `level` is empty: done
             if (level >= level_limit) { too_deep = true; break; }
             Mask *next_cur = rec + 1 + (level & 1);          // word of the record, indexed [4 * vertex]
             Mask *next_nxt = rec + 2 - (level & 1);
             const DistT cur_d = (DistT)level;
+            // direction: a pushed row costs a random record read plus (mostly) an atomic, a pulled row a random
+            // 8-byte read; the pull scan also streams all records once
+            const uint32_t entries = qend - qbeg;
+            const bool pull = p.pull_mode == 2 ||
+                              (p.pull_mode == 1 && 2ull * entries * p.avg_deg > (9ull * n) / 16 + (unsigned long long)n_open * p.avg_deg);
 
             // mark: the level's vertices become `seen` for their sources BEFORE anything is expanded, so the
             // expansion needs no atomic on `seen` (a plain test suffices: bits of this and earlier levels are
             // final, and a source discovered twice on the level being built is caught by the atomic on next[]).
-            // The entry's mask moves to the queue (the backward pass wants it there) and next[] cleans itself.
+            // The entry's mask moves to the queue (the backward pass wants it there) and next[] cleans itself -
+            // one level later if this level is pulled (the scan reads the masks from the records).
             for (uint32_t idx = qbeg + tid_t; idx < qend; idx += threads_t) {
                 const uint32_t u = queue_v[idx];
                 const Mask m = __ldcg(&next_cur[(size_t)u * 4]);
                 const Mask sn = __ldcg(&rec[(size_t)u * 4]);
                 __stcg(&rec[(size_t)u * 4], sn | m);
-                __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // this parity is reused at level+2
+                if (!pull) __stcg(&next_cur[(size_t)u * 4], (Mask)0);   // this parity is reused at level+2
                 queue_m[idx] = m;
             }
+            for (uint32_t idx = defer_beg + tid_t; idx < defer_end; idx += threads_t)
+                __stcg(&next_nxt[(size_t)queue_v[idx] * 4], (Mask)0);   // the pulled level-1's masks: same parity as level+1
+            defer_beg = pull ? qbeg : 0u;
+            defer_end = pull ? qend : 0u;
+            if (pull && threadIdx.x == 0) s_open = 0;
             team_sync();
 
             for (uint32_t tile = qbeg + warp_t * 32; tile < qend; tile += warps_t * 32) {
@@ -378,6 +422,7 @@ vertex_load_engine(const EngineParams p) {
                             if ((uint32_t)(m_e >> (h * 32 + lane)) & 1u) dist[(size_t)u_e * kSrc + h * 32 + lane] = cur_d;
                     }
                 }
+                if (pull) continue;                  // (uniform for the whole slot) the scan below does the expansion
                 const uint32_t incl = warp_inclusive_scan(deg, lane);
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 const uint32_t off = incl - deg;
@@ -436,6 +481,67 @@ vertex_load_engine(const EngineParams p) {
                     }
                 }
             }
+            if (pull) {
+                // ---- pull scan: thread per vertex, vertices in id order (streams), neighbours' masks gathered ----
+                uint32_t my_open = 0;
+                for (uint32_t base = warp_t * 32; base < n; base += warps_t * 32) {
+                    const uint32_t x = base + lane;
+                    Mask unseen = 0;
+                    uint32_t rs = 0, deg = 0;
+                    if (x < n) {
+                        unseen = ~__ldcg(&rec[(size_t)x * 4]) & valid_src;
+                        if (unseen) {
+                            rs = __ldg(p.row_ptr + x);
+                            deg = __ldg(p.row_ptr + x + 1) - rs;
+                        }
+                    }
+                    Mask acc = 0;
+                    const bool hub = deg > kPullHubDeg;
+                    if (!hub) {
+                        for (uint32_t e = 0; e < deg; e += kPullUnroll) {
+                            uint32_t un[kPullUnroll];
+                            Mask mm[kPullUnroll];
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : 0xFFFFFFFFu;
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) mm[j] = un[j] != 0xFFFFFFFFu ? __ldcg(&next_cur[(size_t)un[j] * 4]) : (Mask)0;
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) acc |= mm[j];
+                            if ((acc & unseen) == unseen) break;      // nothing left to find for this vertex
+                        }
+                    }
+                    // hubs: the whole warp gathers one adjacency list (BA: degrees up to ~ m * sqrt(N))
+                    for (uint32_t hub_bal = __ballot_sync(0xFFFFFFFFu, hub); hub_bal; hub_bal &= hub_bal - 1) {
+                        const int o = __ffs(hub_bal) - 1;
+                        const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o), deg_o = __shfl_sync(0xFFFFFFFFu, deg, o);
+                        Mask a = 0;
+                        for (uint32_t e = lane; e < deg_o; e += 32) a |= __ldcg(&next_cur[(size_t)__ldg(p.col_idx + rs_o + e) * 4]);
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) a |= __shfl_xor_sync(0xFFFFFFFFu, a, sh);
+                        if (lane == o) acc = a;
+                    }
+                    const Mask fresh = acc & unseen;
+                    if (fresh) __stcg(&next_nxt[(size_t)x * 4], fresh);       // one writer per vertex
+                    my_open += (unseen & ~fresh) != 0 ? 1u : 0u;
+                    const bool enqueue = fresh != 0;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, enqueue);
+                    if (bal) {
+                        uint32_t qb = 0;
+                        const int leader = __ffs(bal) - 1;
+                        if (lane == leader) qb = tail_add((uint32_t)__popc(bal));
+                        qb = __shfl_sync(0xFFFFFFFFu, qb, leader);
+                        if (enqueue) {
+                            const uint32_t pos = qb + __popc(bal & lane_lt);
+                            if (pos < qcap) queue_v[pos] = x;
+                            else fail_set();
+                        }
+                    }
+                }
+                my_open = __reduce_add_sync(0xFFFFFFFFu, my_open);
+                if (lane == 0 && my_open) open_add(my_open);
+            }
+            prev_pull = pull;
+            if (tid_t == 0) dir_levels += pull ? (1ull << 32) : 1ull;
             ++level;
         }
         // here: levels 0..level-1 are non-empty (if !too_deep), lvl[l] = start of level l,
@@ -644,6 +750,7 @@ vertex_load_engine(const EngineParams p) {
         atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
         atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
         atomicAdd(&p.counters[6], (unsigned long long)cyc_bwd);
+        if (dir_levels) atomicAdd(&p.counters[7], dir_levels);
     }
 }
 

@@ -16,13 +16,17 @@ REL = 1e-9
 ENGINES = {"auto": 0, "batched": 1, "mid": 2}
 
 
-@pytest.fixture(params=["batched", "batched64", "mid"])
+@pytest.fixture(params=["batched", "batched64", "batched_pull", "batched64_pull", "batched64_push", "mid"])
 def engine_ctx(ctx, request, monkeypatch):
-    """Runs a test once per traversal engine and batch width (the C ABI picks by graph size and source
-    count by default; NEC_BATCH_WIDTH pins the batched engine's 32 / 64 sources per batch)."""
-    ctx.set_engine(ENGINES[request.param.rstrip("64")])
-    if request.param.startswith("batched"):
-        monkeypatch.setenv("NEC_BATCH_WIDTH", "64" if request.param.endswith("64") else "32")
+    """Runs a test once per traversal engine, batch width and forward direction (the C ABI picks by graph size,
+    source count and a per-level cost model by default; NEC_BATCH_WIDTH pins the batched engine's 32 / 64 sources
+    per batch, NEC_PULL its forward pass to push only (0) or pull only (2))."""
+    name, _, direction = request.param.partition("_")
+    ctx.set_engine(ENGINES[name.rstrip("64")])
+    if name.startswith("batched"):
+        monkeypatch.setenv("NEC_BATCH_WIDTH", "64" if name.endswith("64") else "32")
+        if direction:
+            monkeypatch.setenv("NEC_PULL", "2" if direction == "pull" else "0")
     yield ctx
     ctx.set_engine(0)
 
@@ -540,3 +544,35 @@ def test_wave_size_matches_what_a_call_uses(ctx):
     st = ctx.stats()
     assert st["engine"] == 1 and st["n_slots"] * st["batch_width"] == wave and st["n_batches"] == st["n_slots"]
     dg.free()
+
+
+@pytest.mark.parametrize("width", ["32", "64"])
+def test_forward_directions_are_bitwise_identical(ctx, oracle, monkeypatch, width):
+    """The batched forward pass expands a level by push (frontier -> neighbours, atomics) or by pull (every
+    incomplete vertex gathers its neighbours' frontier masks), chosen per level by a cost model.  Level sets and
+    masks are the same either way and no sum depends on the order of a level's queue: bit-identical loads."""
+    ctx.set_engine(1)
+    monkeypatch.setenv("NEC_BATCH_WIDTH", width)
+    graphs = [ne.gnm_scalable(30000, 120000, 3).export_csr(), ne.ba_scalable(20000, 4, 5, 5).export_csr(),
+              ne.ErEnsembleC(2500, 1.2, 8).export_csr()]                     # expander, hubs, many small components
+    for rp, col in graphs:
+        n = len(rp) - 1
+        dg = ctx.upload(rp, col)
+        src = np.arange(0, n, max(1, n // 200), dtype=np.uint32)
+        outs, stats = [], []
+        for mode in ("0", "1", "2"):
+            monkeypatch.setenv("NEC_PULL", mode)
+            outs.append(dg.vertex_load_sources(src, False))
+            stats.append(ctx.stats())
+        assert outs[0].tobytes() == outs[1].tobytes() == outs[2].tobytes()
+        assert stats[0]["pull_levels"] == 0 and stats[0]["push_levels"] > 0
+        assert stats[2]["push_levels"] == 0 and stats[2]["pull_levels"] == stats[0]["push_levels"]
+        assert stats[1]["pull_levels"] + stats[1]["push_levels"] == stats[0]["push_levels"]
+        assert [s["reached_pairs"] for s in stats] == [stats[0]["reached_pairs"]] * 3
+        assert [s["vertex_visits"] for s in stats] == [stats[0]["vertex_visits"]] * 3
+        assert close(outs[1], oracle.vertex_load(rp, col, False, sources=src, threads=0), REL)
+        ecc, sumd, reached = dg.distance_measures(src)                      # the forward pass alone, pulled
+        recc, rsum, rreach = oracle.distance_measures(rp, col, src)
+        assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
+        dg.free()
+    ctx.set_engine(0)
