@@ -172,6 +172,8 @@ typedef struct nec_stats {
     uint32_t cta_threads;     /* threads per CTA of the traversal kernel that ran */
     uint32_t pull_levels;     /* batched engine: (batch, level) expansions done in pull direction ... */
     uint32_t push_levels;     /* ... and in push direction */
+    uint32_t requeued_batches;/* batches re-run with the full level queue after an overflow of the memory-trimmed one */
+    uint32_t reserved0;
 } nec_stats;
 int nec_get_stats(const nec_ctx *ctx, nec_stats *out);
 

@@ -18,7 +18,8 @@ class NecStats(ctypes.Structure):
                 ("vertex_visits", c_u64), ("max_depth", c_u32), ("kernel_launches", c_u32),
                 ("wide_batches", c_u32), ("n_slots", c_u32), ("kernel_ms", ctypes.c_float), ("engine_ms", ctypes.c_float), ("frac_reset", ctypes.c_float), ("frac_forward", ctypes.c_float), ("frac_backward", ctypes.c_float),
                 ("workspace_bytes", c_u64), ("engine", c_u32), ("batch_width", c_u32),
-                ("team_size", c_u32), ("cta_threads", c_u32), ("pull_levels", c_u32), ("push_levels", c_u32)]
+                ("team_size", c_u32), ("cta_threads", c_u32), ("pull_levels", c_u32), ("push_levels", c_u32),
+                ("requeued_batches", c_u32), ("reserved0", c_u32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

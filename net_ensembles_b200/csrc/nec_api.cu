@@ -65,6 +65,12 @@ struct nec_ctx {
     uint32_t *d_worklist = nullptr; size_t d_worklist_cap = 0;
     unsigned long long *d_counters = nullptr;       // 8
     double *d_out = nullptr; size_t d_out_cap = 0;  // result staging for host-pointer calls
+    double *d_keep = nullptr; size_t d_keep_cap = 0;  // pass-1 sums while the 32-bit distance pass runs
+    double *d_tmp = nullptr; size_t d_tmp_cap = 0;    // partial load of the sources the mid engine handed back
+    // nec_distance_measures outputs (per source) and the hand-back subset's, kept across calls
+    uint32_t *d_mecc = nullptr, *d_mreach = nullptr, *d_pecc = nullptr, *d_preach = nullptr, *d_scatter = nullptr;
+    unsigned long long *d_msum = nullptr, *d_psum = nullptr;
+    size_t d_mecc_cap = 0, d_mreach_cap = 0, d_msum_cap = 0, d_pecc_cap = 0, d_preach_cap = 0, d_psum_cap = 0, d_scatter_cap = 0;
     int occ_u8 = 0, occ_u32 = 0;
     void *mid_base = nullptr; size_t mid_bytes = 0;   // arena of the one-source-per-CTA engine
     uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
@@ -131,7 +137,7 @@ size_t per_slot_bytes(uint32_t n, uint32_t dist_bytes, size_t qcap, uint32_t max
 
 // Slots and queue capacity the workspace budget allows for (n, distance width, batch width, wanted slots).
 struct ArenaPlan { uint32_t slots; size_t qcap, per_slot, budget; };
-int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc, ArenaPlan &out) {
+int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc, ArenaPlan &out, bool full_queue = false) {
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     size_t free_b = 0, total_b = 0;
     NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -143,7 +149,7 @@ int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slot
     if (ps * slots > budget) {
         // prefer keeping one slot per SM; shrink the queue bound (overflow is detected) first
         const uint32_t floor_slots = std::min<uint32_t>(slots, (uint32_t)ctx->prop.multiProcessorCount);
-        while (ps * floor_slots > budget && qcap > (size_t)n * 8 + ksrc) {
+        while (!full_queue && ps * floor_slots > budget && qcap > (size_t)n * 8 + ksrc) {
             qcap = std::max((size_t)n * 8 + ksrc, qcap / 2);
             ps = per_slot_bytes(n, dist_bytes, qcap, max_levels, ksrc);
         }
@@ -154,11 +160,11 @@ int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slot
 }
 
 // Build (or reuse) the arena for (n, distance width, wanted slots).
-int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc = nec::kLanes) {
+int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc = nec::kLanes, bool full_queue = false) {
     Arena &a = ctx->arena;
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     ArenaPlan plan{};
-    int prc = plan_arena(ctx, n, dist_bytes, want_slots, ksrc, plan);
+    int prc = plan_arena(ctx, n, dist_bytes, want_slots, ksrc, plan, full_queue);
     if (prc != NEC_OK) return prc;
     const uint32_t slots = plan.slots;
     const size_t qcap = plan.qcap, ps = plan.per_slot;
@@ -195,11 +201,10 @@ struct MeasureOut {                  // device outputs of the distance-measure m
 template <typename DistT, int kMode, int kThreads, int kSrc>
 int launch_engine_t(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots) {
     constexpr size_t smem = nec::engine_smem_bytes<DistT, kThreads, kSrc>();
-    static bool attr_done = false;                      // per instantiation
-    if (!attr_done && smem > 48 * 1024) {
+    // the attribute is per device (primary context), and contexts on several devices share this process: set it
+    // on every launch (a host-side call of about a microsecond) instead of remembering it per instantiation
+    if (smem > 48 * 1024)
         NEC_CUDA(ctx, cudaFuncSetAttribute(nec::vertex_load_engine<DistT, kMode, kThreads, kSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     nec::vertex_load_engine<DistT, kMode, kThreads, kSrc><<<slots, kThreads, smem, ctx->stream>>>(p);
     NEC_CUDA(ctx, cudaGetLastError());
     return NEC_OK;
@@ -235,6 +240,8 @@ template <typename DistT, int kSrc>
 int launch_engine_team(nec_ctx *ctx, const nec::EngineParams &p, uint32_t slots, uint32_t team) {
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = team_config<DistT, kSrc>(attr, slots, team, ctx->stream);
+    if (cfg.dynamicSmemBytes > 48 * 1024)      // per device, see launch_engine_t
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::vertex_load_engine<DistT, 0, 512, kSrc, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
     NEC_CUDA(ctx, cudaLaunchKernelEx(&cfg, nec::vertex_load_engine<DistT, 0, 512, kSrc, true>, p));
     return NEC_OK;
 }
@@ -414,67 +421,109 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
     ctx->stats.engine_ms = ms;
 
-    std::vector<uint32_t> deep;                     // 32-source batch ids for the 32-bit distance pass
-    for (uint32_t b = 0; b < n_batches; ++b) {
-        if (status[b] == nec::kTooDeep) {
-            if (ksrc == 32) deep.push_back(b);
-            else { deep.push_back(2 * b); if (2 * b + 1 < n_batches32) deep.push_back(2 * b + 1); }
-        } else if (status[b] == nec::kQueueOverflow)
-            return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
-        else if (status[b] != nec::kDone)
-            return fail(ctx, NEC_EINTERNAL, "batch %u was not processed (status %u)", b, (unsigned)status[b]);
-    }
-
-    // ---- pass 2: batches deeper than 253 levels, 32-bit distances ----------------------
-    if (!deep.empty()) {
-        ctx->stats.wide_batches = (uint32_t)deep.size();
-        // keep pass-1 result: d_out already holds the sum of the shallow batches
-        double *d_keep = nullptr;
-        NEC_CUDA(ctx, cudaMalloc((void **)&d_keep, (size_t)n * sizeof(double)));
-        if (!mo) cudaMemcpyAsync(d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
-        if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, deep.size())) != NEC_OK) { cudaFree(d_keep); return rc; }
-        cudaMemcpyAsync(ctx->d_worklist, deep.data(), deep.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemsetAsync(ctx->d_status, 0, n_batches32, ctx->stream);
-        status.assign(n_batches32, 0);
-        uint32_t want2 = std::min<uint32_t>((uint32_t)deep.size(), (uint32_t)(ctx->occ_u32 * ctx->prop.multiProcessorCount));
+    // Batches that did not complete are re-run, never approximated: a queue overflow (the planner halves the
+    // queue bound under memory pressure to keep one slot per SM) with the full n * width queue on fewer slots, a
+    // BFS deeper than 253 levels with 32-bit distance rows.  `rerun` keeps the sums so far, runs the listed batch
+    // ids (of the given width) in a freshly planned arena and reads their verdicts back.
+    auto rerun = [&](const std::vector<uint32_t> &list, uint32_t dist_bytes, uint32_t width, bool full_queue,
+                     std::vector<uint8_t> &verdict) -> int {
+        int r;
+        if ((r = grow(ctx, ctx->d_keep, ctx->d_keep_cap, n)) != NEC_OK) return r;
+        if (!mo) NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_keep, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((r = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, list.size())) != NEC_OK) return r;
+        NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_worklist, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t n_ids = (n_sources + width - 1) / width;
+        NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, n_ids, ctx->stream));
+        uint32_t want2 = std::min<uint32_t>((uint32_t)list.size(), (uint32_t)((dist_bytes == 1 ? ctx->occ_u8 : ctx->occ_u32) * ctx->prop.multiProcessorCount));
         if (debug) want2 = 1;
         ctx->wide_ctas = false;
         ctx->team_size = 1;
-        cudaStreamSynchronize(ctx->stream);  // arena may be reallocated below
-        if ((rc = ensure_arena(ctx, n, 4, want2)) != NEC_OK) { cudaFree(d_keep); return rc; }
+        NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the arena may be reallocated below
+        if ((r = ensure_arena(ctx, n, dist_bytes, want2, width, full_queue)) != NEC_OK) return r;
         const Arena &w = ctx->arena;
-        uint32_t slots2 = std::min<uint32_t>(want2, w.n_slots);
-        cudaMemsetAsync(w.mask, 0, w.mask_stride * slots2, ctx->stream);
-        cudaMemsetAsync(w.bslot, 0, w.bslot_stride * sizeof(double) * slots2, ctx->stream);
-        cudaEventRecord(ctx->ev0, ctx->stream);
-        rc = mo    ? launch_engine<uint32_t, 2>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr, mo)
-           : debug ? launch_engine<uint32_t, 1>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, dbg_npred, dbg_bk)
-                   : launch_engine<uint32_t, 0>(ctx, g, n_sources, ctx->d_worklist, (uint32_t)deep.size(), include_endpoints, slots2, nullptr, nullptr);
-        if (rc != NEC_OK) { cudaFree(d_keep); return rc; }
-        cudaEventRecord(ctx->ev_mid, ctx->stream);
+        const uint32_t slots2 = std::min<uint32_t>(want2, w.n_slots);
+        NEC_CUDA(ctx, cudaMemsetAsync(w.mask, 0, w.mask_stride * slots2, ctx->stream));
+        NEC_CUDA(ctx, cudaMemsetAsync(w.bslot, 0, w.bslot_stride * sizeof(double) * slots2, ctx->stream));
+        NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        const uint32_t cnt = (uint32_t)list.size();
+        if (dist_bytes == 4)
+            r = mo    ? launch_engine<uint32_t, 2>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr, mo)
+              : debug ? launch_engine<uint32_t, 1>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, dbg_npred, dbg_bk)
+                      : launch_engine<uint32_t, 0>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr);
+        else if (width == 64)
+            r = mo ? launch_engine<uint8_t, 2, 64>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr, mo)
+                   : launch_engine<uint8_t, 0, 64>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr);
+        else
+            r = mo    ? launch_engine<uint8_t, 2>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr, mo)
+              : debug ? launch_engine<uint8_t, 1>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, dbg_npred, dbg_bk)
+                      : launch_engine<uint8_t, 0>(ctx, g, n_sources, ctx->d_worklist, cnt, include_endpoints, slots2, nullptr, nullptr);
+        if (r != NEC_OK) return r;
+        NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
         if (!mo) {
-            // slot 0's partial absorbs the pass-1 sums so that one reduction produces the result
-            nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, d_keep, n);
+            // slot 0's partial absorbs the sums so far so that one reduction produces the result
+            nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, ctx->d_keep, n);
             nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(w.bslot, w.bslot_stride, slots2, n, d_out);
+            NEC_CUDA(ctx, cudaGetLastError());
             ctx->stats.kernel_launches += 2;
         }
-        cudaEventRecord(ctx->ev1, ctx->stream);
-        cudaMemcpyAsync(status.data(), ctx->d_status, n_batches32, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_keep);
-        if (e != cudaSuccess) return fail(ctx, NEC_ECUDA, "wide-distance pass failed: %s", cudaGetErrorString(e));
+        NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        verdict.assign(n_ids, 0);
+        NEC_CUDA(ctx, cudaMemcpyAsync(verdict.data(), ctx->d_status, n_ids, cudaMemcpyDeviceToHost, ctx->stream));
+        NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+        NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms2 = 0.f;
-        cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1);
+        NEC_CUDA(ctx, cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1));
         ctx->stats.kernel_ms += ms2;
-        cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev_mid);
+        NEC_CUDA(ctx, cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev_mid));
         ctx->stats.engine_ms += ms2;
         ctx->stats.workspace_bytes = std::max<uint64_t>(ctx->stats.workspace_bytes, ctx->arena.bytes);
+        return NEC_OK;
+    };
+
+    std::vector<uint32_t> deep;                     // 32-source batch ids for the 32-bit distance pass
+    std::vector<uint32_t> overflowed;               // batch ids (of width ksrc) whose level queue overflowed
+    auto sort_verdicts = [&](const std::vector<uint8_t> &verdict, const uint32_t *ids, uint32_t count, bool allow_overflow) -> int {
+        for (uint32_t i = 0; i < count; ++i) {
+            const uint32_t b = ids ? ids[i] : i;
+            if (verdict[b] == nec::kTooDeep) {
+                if (ksrc == 32) deep.push_back(b);
+                else { deep.push_back(2 * b); if (2 * b + 1 < n_batches32) deep.push_back(2 * b + 1); }
+            } else if (verdict[b] == nec::kQueueOverflow) {
+                if (!allow_overflow)
+                    return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
+                overflowed.push_back(b);
+            } else if (verdict[b] != nec::kDone)
+                return fail(ctx, NEC_EINTERNAL, "batch %u was not processed (status %u)", b, (unsigned)verdict[b]);
+        }
+        return NEC_OK;
+    };
+    const bool queue_was_cut = ctx->arena.qcap < (size_t)n * ksrc + ksrc;
+    if ((rc = sort_verdicts(status, nullptr, n_batches, queue_was_cut)) != NEC_OK) return rc;
+
+    if (!overflowed.empty()) {
+        ArenaPlan full{};
+        if ((rc = plan_arena(ctx, n, 1, 1, ksrc, full, true)) != NEC_OK) return rc;
+        if (full.slots == 0)
+            return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (capacity %zu entries) and the workspace limit cannot hold one slot with "
+                        "the full queue (%zu B); raise the workspace limit", overflowed[0], ctx->arena.qcap, full.per_slot);
+        ctx->stats.requeued_batches = (uint32_t)overflowed.size();
+        const std::vector<uint32_t> list = overflowed;
+        overflowed.clear();
+        std::vector<uint8_t> verdict;
+        if ((rc = rerun(list, 1, ksrc, true, verdict)) != NEC_OK) return rc;
+        if ((rc = sort_verdicts(verdict, list.data(), (uint32_t)list.size(), false)) != NEC_OK) return rc;
+    }
+
+    // ---- batches deeper than 253 levels: 32-bit distances, 32 sources per batch ----------------
+    if (!deep.empty()) {
+        ctx->stats.wide_batches = (uint32_t)deep.size();
+        std::vector<uint8_t> verdict;
+        if ((rc = rerun(deep, 4, 32, false, verdict)) != NEC_OK) return rc;
         for (uint32_t b : deep) {
-            if (status[b] == nec::kQueueOverflow)
+            if (verdict[b] == nec::kQueueOverflow)
                 return fail(ctx, NEC_EINTERNAL, "frontier queue overflow in batch %u (32-bit distance pass, capacity %zu entries); raise the workspace limit", b, ctx->arena.qcap);
-            if (status[b] != nec::kDone)
-                return fail(ctx, NEC_EINTERNAL, "batch %u failed in the 32-bit distance pass (status %u)", b, (unsigned)status[b]);
+            if (verdict[b] != nec::kDone)
+                return fail(ctx, NEC_EINTERNAL, "batch %u failed in the 32-bit distance pass (status %u)", b, (unsigned)verdict[b]);
         }
     }
     ctx->stats.engine = 1;
@@ -616,16 +665,12 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     if (rc != NEC_OK || fallback.empty()) return rc;
     // the few sources the mid engine could not encode (depth > 126, > 62 predecessors, queue overflow)
     const nec_stats first = ctx->stats;
-    double *d_tmp = nullptr;
-    NEC_CUDA(ctx, cudaMalloc((void **)&d_tmp, (size_t)g->n * sizeof(double)));
+    if ((rc = grow(ctx, ctx->d_tmp, ctx->d_tmp_cap, g->n)) != NEC_OK) return rc;
+    double *d_tmp = ctx->d_tmp;
     rc = run_sources_batched(ctx, g, fallback.data(), (uint32_t)fallback.size(), include_endpoints, d_tmp, false, nullptr, nullptr);
-    if (rc == NEC_OK) {
-        nec::add_into_kernel<<<std::min<uint32_t>((g->n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_out, d_tmp, g->n);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, NEC_ECUDA, "fallback merge failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d_tmp);
     if (rc != NEC_OK) return rc;
+    nec::add_into_kernel<<<std::min<uint32_t>((g->n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_out, d_tmp, g->n);
+    NEC_CUDA(ctx, cudaGetLastError());
     nec_stats &st = ctx->stats;                      // merge the two passes
     st.n_sources += first.n_sources - fallback.size();
     st.n_batches += first.n_batches;
@@ -706,6 +751,9 @@ void nec_destroy(nec_ctx *ctx) {
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_out) cudaFree(ctx->d_out);
+    for (void *ptr : {(void *)ctx->d_keep, (void *)ctx->d_tmp, (void *)ctx->d_mecc, (void *)ctx->d_mreach, (void *)ctx->d_msum,
+                      (void *)ctx->d_pecc, (void *)ctx->d_preach, (void *)ctx->d_psum, (void *)ctx->d_scatter})
+        if (ptr) cudaFree(ptr);
     if (ctx->mid_base) cudaFree(ctx->mid_base);
     if (ctx->d_src_status) cudaFree(ctx->d_src_status);
     ctx->small.release();
@@ -891,58 +939,47 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     ctx->stats = nec_stats{};
     if (n_sources == 0 || g->n == 0) return NEC_OK;
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
-    MeasureOut mo{};
-    cudaError_t e = cudaMalloc((void **)&mo.ecc, (size_t)n_sources * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mo.sumdist, (size_t)n_sources * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mo.reached, (size_t)n_sources * 4);
-    auto cleanup = [&]() { cudaFree(mo.ecc); cudaFree(mo.sumdist); cudaFree(mo.reached); };
-    if (e != cudaSuccess) { cleanup(); return fail(ctx, NEC_ENOMEM, "nec_distance_measures: %s", cudaGetErrorString(e)); }
+    int rc;
+    if ((rc = grow(ctx, ctx->d_mecc, ctx->d_mecc_cap, n_sources)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_msum, ctx->d_msum_cap, n_sources)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_mreach, ctx->d_mreach_cap, n_sources)) != NEC_OK) return rc;
+    MeasureOut mo{ctx->d_mecc, ctx->d_msum, ctx->d_mreach};
     for (uint32_t k = 0; k < n_sources; ++k)
-        if (sources[k] >= g->n) { cleanup(); return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", sources[k], k, g->n); }
+        if (sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", sources[k], k, g->n);
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2) &&
                         nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u;
-    int rc;
     if (mid_ok) {
         std::vector<uint32_t> fb, fb_index;
         rc = run_sources_mid(ctx, g, sources, n_sources, 1, nullptr, fb, &mo, &fb_index);
-        if (rc == NEC_OK && !fb.empty()) {       // sources deeper than 126 levels: batched engine, scattered back
+        if (rc == NEC_OK && !fb.empty()) {       // sources deeper than 126 levels: batched engine, scattered back on the stream
             const nec_stats first = ctx->stats;
-            MeasureOut part{};
             const size_t k = fb.size();
-            cudaError_t e2 = cudaMalloc((void **)&part.ecc, k * 4);
-            if (e2 == cudaSuccess) e2 = cudaMalloc((void **)&part.sumdist, k * 8);
-            if (e2 == cudaSuccess) e2 = cudaMalloc((void **)&part.reached, k * 4);
-            if (e2 != cudaSuccess) rc = fail(ctx, NEC_ENOMEM, "nec_distance_measures: %s", cudaGetErrorString(e2));
-            if (rc == NEC_OK) rc = run_sources_batched(ctx, g, fb.data(), (uint32_t)k, 1, nullptr, false, nullptr, nullptr, &part);
-            if (rc == NEC_OK) {
-                std::vector<uint32_t> pe(k), pr(k);
-                std::vector<unsigned long long> ps(k);
-                cudaMemcpy(pe.data(), part.ecc, k * 4, cudaMemcpyDeviceToHost);
-                cudaMemcpy(ps.data(), part.sumdist, k * 8, cudaMemcpyDeviceToHost);
-                cudaMemcpy(pr.data(), part.reached, k * 4, cudaMemcpyDeviceToHost);
-                for (size_t j = 0; j < k; ++j) {
-                    cudaMemcpy(mo.ecc + fb_index[j], &pe[j], 4, cudaMemcpyHostToDevice);
-                    cudaMemcpy(mo.sumdist + fb_index[j], &ps[j], 8, cudaMemcpyHostToDevice);
-                    cudaMemcpy(mo.reached + fb_index[j], &pr[j], 4, cudaMemcpyHostToDevice);
-                }
-                ctx->stats.kernel_ms += first.kernel_ms; ctx->stats.engine_ms += first.engine_ms;
-                ctx->stats.edge_pairs += first.edge_pairs; ctx->stats.reached_pairs += first.reached_pairs;
-                ctx->stats.n_sources = n_sources; ctx->stats.engine = 1u | (2u << 4);
-            }
-            cudaFree(part.ecc); cudaFree(part.sumdist); cudaFree(part.reached);
+            if ((rc = grow(ctx, ctx->d_pecc, ctx->d_pecc_cap, k)) != NEC_OK) return rc;
+            if ((rc = grow(ctx, ctx->d_psum, ctx->d_psum_cap, k)) != NEC_OK) return rc;
+            if ((rc = grow(ctx, ctx->d_preach, ctx->d_preach_cap, k)) != NEC_OK) return rc;
+            if ((rc = grow(ctx, ctx->d_scatter, ctx->d_scatter_cap, k)) != NEC_OK) return rc;
+            MeasureOut part{ctx->d_pecc, ctx->d_psum, ctx->d_preach};
+            rc = run_sources_batched(ctx, g, fb.data(), (uint32_t)k, 1, nullptr, false, nullptr, nullptr, &part);
+            if (rc != NEC_OK) return rc;
+            NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_scatter, fb_index.data(), k * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            nec::scatter_measures_kernel<<<(unsigned)std::min<size_t>((k + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(
+                (uint32_t)k, ctx->d_scatter, part.ecc, part.sumdist, part.reached, mo.ecc, mo.sumdist, mo.reached);
+            NEC_CUDA(ctx, cudaGetLastError());
+            NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // fb_index is a pageable host vector
+            ctx->stats.kernel_ms += first.kernel_ms; ctx->stats.engine_ms += first.engine_ms;
+            ctx->stats.edge_pairs += first.edge_pairs; ctx->stats.reached_pairs += first.reached_pairs;
+            ctx->stats.kernel_launches += first.kernel_launches + 1;
+            ctx->stats.n_sources = n_sources; ctx->stats.engine = 1u | (2u << 4);
         }
     } else {
         rc = run_sources_batched(ctx, g, sources, n_sources, 1, nullptr, false, nullptr, nullptr, &mo);
     }
-    if (rc == NEC_OK) {
-        if (ecc) cudaMemcpyAsync(ecc, mo.ecc, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (sum_dist) cudaMemcpyAsync(sum_dist, mo.sumdist, (size_t)n_sources * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (reached) cudaMemcpyAsync(reached, mo.reached, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, NEC_ECUDA, "nec_distance_measures: %s", cudaGetErrorString(e));
-    }
-    cleanup();
-    return rc;
+    if (rc != NEC_OK) return rc;
+    if (ecc) NEC_CUDA(ctx, cudaMemcpyAsync(ecc, mo.ecc, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sum_dist) NEC_CUDA(ctx, cudaMemcpyAsync(sum_dist, mo.sumdist, (size_t)n_sources * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reached) NEC_CUDA(ctx, cudaMemcpyAsync(reached, mo.reached, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NEC_OK;
 } NEC_CATCH_ALL(ctx)
 
 int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,

@@ -769,6 +769,16 @@ __global__ void add_into_kernel(double *__restrict__ a, const double *__restrict
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) a[v] += b[v];
 }
 
+// Distance measures of the sources one engine handed to the other, scattered back to their places.
+__global__ void scatter_measures_kernel(uint32_t k, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ pe,
+                                        const unsigned long long *__restrict__ ps, const uint32_t *__restrict__ pr,
+                                        uint32_t *__restrict__ ecc, unsigned long long *__restrict__ sum, uint32_t *__restrict__ reached) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+        const uint32_t at = idx[j];
+        ecc[at] = pe[j]; sum[at] = ps[j]; reached[at] = pr[j];
+    }
+}
+
 __global__ void fill_f64_kernel(double *__restrict__ a, size_t count, double value) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) a[i] = value;
 }

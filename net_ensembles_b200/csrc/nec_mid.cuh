@@ -516,8 +516,11 @@ mid_engine(const MidParams p) {
                 if (d != 0xFFu) {
                     t_reached += 1;                                   // exact (the queue may hold duplicates)
                     t_edges += dg != 0xFFu ? dg : __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
-                    // finished mark carries npred; no FMA contraction: a BFS leaf must give exactly bk - 1 = 0
-                    if (d != 0u) b += __dsub_rn(__dmul_rn(qv, (double)(d & 0x3Fu)), sub);
+                    // the finished mark carries npred, and q * npred is bk to within one unit in the last place
+                    // (q = bk / npred was rounded once).  bk >= 1 always, and only bk == 1 (a BFS leaf) can come
+                    // back below 1 (e.g. (1/49)*49): the clamp makes a leaf contribute exactly bk - 1 = 0, as
+                    // `b += bk; b -= 1.0` does in the crate (generic_graph.rs:1371-1374).  No FMA contraction.
+                    if (d != 0u) b += __dsub_rn(fmax(__dmul_rn(qv, (double)(d & 0x3Fu)), 1.0), sub);
                 }
             };
             const uint32_t n2 = n & ~1u;

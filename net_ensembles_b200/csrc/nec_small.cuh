@@ -9,8 +9,9 @@
 // q = bk / npred) — with __syncwarp only; no block barrier inside a source.  Warp w takes
 // sources w, w+W, ... in order and the warps' partial loads are summed in warp order at the
 // end, so the result is reproducible run to run.  Per-source values bk_s(v) are bit-identical
-// to the other engines (same formula, same CSR order); only the order in which sources are
-// added differs, so the batch agrees with nec_vertex_load to rounding (<= 1e-12), not bitwise.
+// to the batched engine's (same formula, same CSR order; the mid engine adds q * npred, which is
+// bk to within one unit in the last place); the order in which sources are added differs as
+// well, so the batch agrees with nec_vertex_load to rounding (<= 1e-12), not bitwise.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
