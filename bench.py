@@ -4,18 +4,26 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
   (N > 1: launched by torch.distributed.run, one rank per GPU.)
 
-A step = one all-source vertex_load(true) pass over the workload graph, sources sharded
-block-cyclically over the ranks, partial loads combined by one all-reduce.  Definitions follow
-SURVEY.md section 8(d):
+Default workload: BASELINE.json configs[3], the north-star target — G(n,m) N=2^20 with average degree 8
+(ErM at a size its O(N^2) constructor cannot reach; distribution-equivalent scalable generator), a fixed strided
+sample of sources equal to four resident waves of the engine per GPU (GTEPS is a rate; the all-source job is
+scripts/full_config4.py).  At N=1 the other four BASELINE configs are measured for one short run each and reported in
+`secondary` (same keys: value, e2e, roofline, parity).
+
+A step = one vertex_load(true) pass over the step's sources, sharded block-cyclically over the ranks, the
+partial loads combined by one all-reduce.  Definitions follow SURVEY.md section 8(d):
   TE(s)    = undirected edges in the component of source s = E_s / 2
   GTEPS    = sum_s TE(s) / seconds / 1e9
   B_alg(s) = 24*E_s + 40*|R_s| bytes;  roofline.achieved = sum_s B_alg(s) / traversal-kernel time
 
 `value`: device-timed (CUDA events on the launching stream), CSR resident in HBM.
-`e2e`:   same pass through the host API with host buffers: pinned-host CSR -> H2D upload ->
-         kernels (-> all-reduce) -> D2H of the load vector, every step.
-`--impl reference`: the reference's CPU algorithm (oracle port; the Rust crate cannot be built
-here), all host threads, on a bounded sample of sources of the same workload.
+`e2e`:   the same pass through the host API starting from the ADJACENCY LISTS in pageable host memory
+         (nec_graph_upload_adjacency: flatten + narrow + validate into pinned staging, H2D) -> kernels
+         (-> all-reduce) -> D2H of the load vector, every step.
+`--impl reference`: the reference's CPU algorithm (oracle port; the Rust crate cannot be built here) on all
+         host cores the process may run on (os.sched_getaffinity, passed explicitly: torchrun's
+         OMP_NUM_THREADS=1 is ignored), on a bounded sample of sources of the same workload; a 1-thread figure
+         (the crate itself is single-threaded) is printed beside it.
 """
 import argparse
 import json
@@ -33,15 +41,24 @@ sys.path.insert(0, ROOT)
 
 METRIC = "vertex_load GTEPS (all-source)"
 SEED = 123_239_010  # the crate's bench seed (benches/bench_vertex_load.rs:8)
+DEFAULT_WORKLOAD = "erm2p20"
+WAVES = 4           # sampled workloads: resident waves of the engine per step and GPU
 
 WORKLOADS = {
-    # name: (description, builder, sampled sources per rank-step or None for all sources)
-    "erc1000": "ErC N=1000 c=4 vertex_load(include_endpoint=true), seeded Pcg64 (BASELINE configs[0])",
+    "erc1000": "ErC N=1000 c=4 vertex_load(include_endpoint=true), seeded Pcg64, all sources (BASELINE configs[0])",
     "sw65536": "SwEnsemble N=2^16 neighbor_distance=2 p=0.1 vertex_load(true), all 65536 sources (BASELINE configs[1])",
-    "erm2p20": "G(n,m) N=2^20 M=2^22 (ErM avg degree 8, scalable generator) vertex_load(true), sampled sources (BASELINE configs[3])",
-    "ba2p22": "Barabasi-Albert N=2^22 m=4 (scalable generator) vertex_load(true), sampled sources (BASELINE configs[4])",
     "markov4096": "batched Markov chain: 4096 ErC graphs N=256 c=4, one m_step then vertex_load(true) of all graphs, one CTA per graph (BASELINE configs[2])",
+    "erm2p20": "ErM N=2^20 avg degree 8 (G(n,m) M=2^22, scalable generator) vertex_load(true), sampled sources: %d resident waves per GPU (BASELINE configs[3], north-star target)" % WAVES,
+    "ba2p22": "Barabasi-Albert N=2^22 m=4 (scalable generator) vertex_load(true), sampled sources: %d resident waves per GPU (BASELINE configs[4])" % WAVES,
 }
+SAMPLED = ("erm2p20", "ba2p22")
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def build_workload(name):
@@ -59,7 +76,12 @@ def build_workload(name):
     raise SystemExit("unknown workload %r (have: %s)" % (name, ", ".join(WORKLOADS)))
 
 
-def step_sources(name, n, sample):
+def static_config(name, n, nnz):
+    """The part of `config` both arms print identically."""
+    return {"workload": WORKLOADS[name], "n": int(n), "undirected_edges": int(nnz // 2), "include_endpoints": True}
+
+
+def step_sources(n, sample):
     """All sources, or (large graphs) a fixed strided sample made of whole 32-blocks."""
     if sample is None or sample >= n:
         return np.arange(n, dtype=np.uint32)
@@ -128,39 +150,63 @@ def cpu_oracle():
     return Oracle(_build.build_oracle())
 
 
+def rel_err(got, want):
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))) if len(want) else 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU port on the host cores
+# ------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
-    """The reference's CPU path (oracle port, OpenMP over sources) on a bounded sample."""
     if rank != 0:
         return
     g = build_workload(args.workload)
     rp, col = g.export_csr()
     n = len(rp) - 1
     orc = cpu_oracle()
-    cores = 1 if args.workload == "markov4096" else orc.max_threads()   # 256-vertex graphs: threads only add overhead
-    # size the sample from one probe source so that a step is ~2 s of wall time
-    t0 = time.perf_counter()
-    orc.vertex_load(rp, col, True, sources=np.array([n // 2], np.uint32))
-    per_source = max(time.perf_counter() - t0, 1e-5)
-    per_step = int(min(n, max(cores, min(4096, 2.0 * cores / per_source))))
-    src_all = step_sources(args.workload, n, per_step)
+    cores = host_cores()
+    if args.workload == "markov4096":
+        # the workload is 4096 independent 256-vertex graphs: one graph per thread is how host cores are used;
+        # the port parallelises over the sources of one graph, so a step = `cores` all-source passes of the
+        # representative chain graph run back to back with all threads
+        reps = max(1, cores)
+        src_all = np.arange(n, dtype=np.uint32)
+        per_step = n
+    else:
+        # size the sample from one probe source so that a step is ~2 s of wall time
+        t0 = time.perf_counter()
+        orc.vertex_load(rp, col, True, sources=np.array([n // 2], np.uint32))
+        per_source = max(time.perf_counter() - t0, 1e-5)
+        per_step = int(min(n, max(cores, min(4096, 2.0 * cores / per_source))))
+        src_all = step_sources(n, per_step)
+        reps = 1
     times, te = [], 0
     for it in range(args.warmup + args.steps):
         src = np.roll(src_all, 7 * it)[:per_step]
         t0 = time.perf_counter()
-        orc.vertex_load(rp, col, True, sources=src, threads=cores)
+        for _ in range(reps):
+            orc.vertex_load(rp, col, True, sources=src, threads=cores)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
-            te += orc.last_stats["edge_pairs"] / 2
+            te += reps * orc.last_stats["edge_pairs"] / 2
     total = sum(times)
     value = te / total / 1e9
-    sample = "%d strided sources per step of %d (%s)" % (per_step, n, args.workload)
+    # the crate itself is single-threaded: one-thread figure on a bounded sample, beside the all-cores one
+    k1 = max(1, min(per_step, int(per_step / cores) or 1))
+    t0 = time.perf_counter()
+    orc.vertex_load(rp, col, True, sources=src_all[:k1])
+    one_thread = (orc.last_stats["edge_pairs"] / 2) / max(time.perf_counter() - t0, 1e-9) / 1e9
+    sample = "%d strided sources per step of %d, %d thread(s) (os.sched_getaffinity; OMP_NUM_THREADS ignored)" % (per_step * reps, n, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "sample": sample,
-                   "note": "CPU port of generic_graph.rs:1310-1385 (Rust crate not buildable here), OpenMP over sources"},
+        "higher_is_better": True, "scaling": "weak" if args.workload in SAMPLED else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": static_config(args.workload, n, len(col)),
+        "details": {"note": "CPU port of generic_graph.rs:1310-1385 (Rust crate not buildable here), OpenMP over sources; a rate "
+                            "on a bounded source sample of the same graph, comparable with the GPU arm's rate",
+                    "one_thread_gteps": one_thread, "one_thread_sample": "%d sources" % k1},
         "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,101 +214,103 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def run_markov(args, rank, world, local_rank):
-    """BASELINE configs[2]: chains are independent, so ranks take disjoint chains and nothing is exchanged
-    ("scaling": "weak" would need 4096 chains per rank; here the 4096 chains are split = strong)."""
+# ------------------------------------------------------------------------------------------------
+# Markov-chain workload (configs[2]): 4096 chains, one step + vertex_load of all graphs
+# ------------------------------------------------------------------------------------------------
+def measure_markov(ctx, steps, warmup, rank, world, with_cpu, comm=None):
     import torch
-    import torch.distributed as dist
     import net_ensembles_b200 as ne
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     mine = [g for g in range(4096) if g % world == rank]
     chains = [ne.ErEnsembleC(256, 4.0, SEED + g) for g in mine]
-    ctx = ne.Context(local_rank)
     batch = ne.ChainBatch(chains)
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         batch.step_and_load(ctx, 1, True)
-    sync()
+    torch.cuda.synchronize()
+    if comm:
+        comm.barrier()
     t0 = time.perf_counter()
-    kernel_ms, te, launches = 0.0, 0.0, 0
-    for _ in range(args.steps):
+    kernel_ms, te, launches, b_alg, outs = 0.0, 0.0, 0, 0.0, None
+    for _ in range(steps):
         outs = batch.step_and_load(ctx, 1, True)      # (chains, 256) loads in host memory
         st = batch.stats
         kernel_ms += st["kernel_ms"]; te += st["edge_pairs"] / 2; launches += st["kernel_launches"]
-    sync()
-    vals = torch.tensor([time.perf_counter() - t0, kernel_ms], dtype=torch.float64, device="cuda")
-    work = torch.tensor([te, launches], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work)
-    if rank == 0:
-        wall, kms = float(vals[0]), float(vals[1])
-        te_all = float(work[0])
-        n_tot = 256 * len(mine)
-        line = {"metric": METRIC, "value": te_all / (kms * 1e-3) / 1e9, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": kms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOADS["markov4096"], "graphs": 4096, "n_per_graph": 256,
-                           "note": "value: kernel only (CUDA events inside the C ABI call); e2e: m_step on host cores + CSR export + H2D + kernel + D2H",
-                           "l2": "4096 graphs x (CSR ~5 KB + 2 KB result); state lives in shared memory"},
-                "clocks": None,
-                "e2e": {"value": te_all / wall / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": int(4096 * (257 * 4 + 1030 * 4) / world),
-                        "d2h_bytes_per_step": int(n_tot * 8)},
-                "gpu_launches": int(work[1]),
-                "roofline": {"bound": "hbm", "achieved": None, "peak": hbm_peak()[0], "unit": "GB/s", "frac": None, "traffic": None,
-                             "kernel": "small_graph_kernel (one CTA per graph, one warp per source; shared-memory resident)"}}
-        print(json.dumps(line), flush=True)
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+        b_alg += 24.0 * st["edge_pairs"] + 40.0 * st["reached_pairs"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    res = {"wall_s": wall, "kernel_ms": kernel_ms, "te": te, "launches": launches, "b_alg": b_alg,
+           "n_chains": len(mine), "h2d": int(getattr(batch, "h2d_bytes_last_step", len(mine) * (257 * 4 + 1030 * 4))),
+           "d2h": int(256 * len(mine) * 8), "mode": getattr(batch, "mode", "CSR re-exported and re-uploaded every step")}
+    if with_cpu:
+        # parity gate + CPU baseline on a bounded sample of the chains (1 thread per graph: the crate's shape)
+        orc = cpu_oracle()
+        pick = list(range(0, len(chains), max(1, len(chains) // 128)))[:128]
+        csr = [chains[g].export_csr() for g in pick]
+        want, te_cpu = [], 0.0
+        t1 = time.perf_counter()
+        for rp, col in csr:
+            want.append(orc.vertex_load(rp, col, True))
+            te_cpu += orc.last_stats["edge_pairs"] / 2
+        dt = time.perf_counter() - t1
+        res["cpu_baseline"] = {"value": te_cpu / dt / 1e9, "unit": "GTEPS", "cores": 1, "kind": "port",
+                               "sample": "%d of the %d chains' graphs after the last step, all 256 sources each, 1 thread" % (len(pick), len(chains))}
+        res["parity"] = max(rel_err(np.asarray(outs[g]), w) for g, w in zip(pick, want))
+        assert res["parity"] <= 1e-9, "Markov batch differs from the oracle: %g" % res["parity"]
+    return res
 
 
-def run_ours(args, rank, world, local_rank):
+def markov_line(res, steps, warmup, world, clocks=None):
+    peak, peak_src = hbm_peak()
+    kms = res["kernel_ms"]
+    achieved = res["b_alg"] / (kms * 1e-3) / 1e9 if kms > 0 else None
+    return {
+        "metric": METRIC, "value": res["te"] / (kms * 1e-3) / 1e9, "unit": "GTEPS", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": kms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS["markov4096"], "n": 256, "graphs": 4096, "include_endpoints": True},
+        "details": {"note": "value: kernel only (CUDA events inside the C ABI call); e2e: m_step of every chain + delivery of the "
+                            "graphs to the device + kernel + D2H of all load vectors, wall clock",
+                    "chain_transport": res["mode"], "e2e_ms_per_step": 1e3 * res["wall_s"] / steps,
+                    "l2": "per-graph state lives in shared memory; inputs are 4096 x ~5 KB"},
+        "clocks": clocks,
+        "e2e": {"value": res["te"] / res["wall_s"] / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"]},
+        "gpu_launches": int(res["launches"]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "small_graph_kernel (one CTA per graph, one warp per source)",
+                     "note": "algorithmic bytes (24 E_s + 40 |R_s|) over kernel time; the kernel keeps a graph's state in shared "
+                             "memory, so its real bound is instruction issue (profiles/), not DRAM",
+                     "algorithmic_bytes_per_step": res["b_alg"] / steps},
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# single-graph workloads
+# ------------------------------------------------------------------------------------------------
+def measure_graph(name, steps, warmup, rank, world, local_rank, with_cpu_baseline, sources_override=None, sample_clocks=False, e2e_steps=None):
     import torch
     import torch.distributed as dist
     import net_ensembles_b200 as ne
     from net_ensembles_b200.parallel import shard_sources
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    g = build_workload(args.workload)                   # same seed on every rank: identical replicas
-    rp, col = g.export_csr()
-    n, nnz = len(rp) - 1, len(col)
-    sample = args.sources
-    if sample is None and args.workload in ("erm2p20", "ba2p22"):
-        sample = 9472 * world if args.workload == "erm2p20" else 3072 * world   # one 64-source batch per SM / one 32-source batch per memory-limited slot
-    sources = step_sources(args.workload, n, sample)
-    mine = sources[shard_sources(len(sources), rank, world)]
-
+    g = build_workload(name)                            # same seed on every rank: identical replicas
+    n, nnz = g.vertex_count(), 2 * g.edge_count()
     ctx = ne.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    dg = ctx.upload(rp, col)
+    dg = g.to_device(ctx)                               # adjacency lists -> pinned staging -> device CSR
+    sample = sources_override
+    wave = dg.wave_size(n)
+    if sample is None and name in SAMPLED:
+        # whole resident waves of the engine as it plans the full job (all n sources) for this graph on this
+        # GPU (wave = slots x sources per batch, nec_wave_size), so that no CTA idles in the last wave
+        sample = WAVES * wave * world
+    sources = step_sources(n, sample)
+    mine = sources[shard_sources(len(sources), rank, world)]
     out = torch.empty(n, dtype=torch.float64, device="cuda")
-
-    if args.sources is None and args.workload in ("erm2p20", "ba2p22"):
-        # the sample is FOUR resident waves of the engine as it plans the whole job (all n sources) for this graph
-        # on this GPU (wave = slots x sources per batch, nec_wave_size): whole waves so that no CTA idles.  Still a
-        # conservative figure: in the full job the slots drift out of phase over many waves and the measured
-        # all-source run is 12 % faster per source (54.1 vs 48.1 GTEPS on config 4, scripts/full_config4.py)
-        wave = dg.wave_size(n)
-        if 4 * wave * world != len(sources):
-            sample = 4 * wave * world
-            sources = step_sources(args.workload, n, sample)
-            mine = sources[shard_sources(len(sources), rank, world)]
 
     def step():
         dg.vertex_load_sources_device(mine, True, out.data_ptr())
@@ -271,10 +319,10 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(out)
         return st
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
@@ -282,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ev0.record()
     engine_ms, launches, st = 0.0, 0, None
-    for _ in range(args.steps):
+    for _ in range(steps):
         st = step()
         engine_ms += st["engine_ms"]
         launches += st["kernel_launches"]
@@ -296,18 +344,16 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(work)
     ms_total = float(ms.item())
     edge_pairs, reached_pairs, launches_all = (float(x) for x in work.tolist())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / steps
     value = (edge_pairs / 2) / (ms_per_step * 1e-3) / 1e9
     result_dev = out.clone()
 
-    # ---- e2e: host buffers in, host vector out, every step ---------------------------------
-    rp_pin = torch.from_numpy(rp.astype(np.uint64).view(np.int64)).pin_memory()
-    col_pin = torch.from_numpy(col.astype(np.uint32).view(np.int32)).pin_memory()
-    rp_h, col_h = rp_pin.numpy().view(np.uint64), col_pin.numpy().view(np.uint32)
+    # ---- e2e: adjacency lists in pageable host memory in, host vector out, every step ---------------
     host_out = torch.empty(n, dtype=torch.float64).pin_memory()
+    n_e2e = max(1, min(steps, e2e_steps if e2e_steps else steps))
 
     def e2e_step():
-        g2 = ctx.upload(rp_h, col_h)                                   # H2D of the CSR
+        g2 = g.to_device(ctx)                                          # flatten + narrow + validate + H2D
         if world == 1:
             res = g2.vertex_load_sources(mine, True)                   # kernels + D2H
         else:
@@ -321,50 +367,60 @@ def run_ours(args, rank, world, local_rank):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         res = e2e_step()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = (edge_pairs / 2) / (float(e2e_s.item()) / args.steps) / 1e9
-    h2d = (n + 1) * 4 + nnz * 4 + len(mine) * 4        # what crosses PCIe per step on this rank (row_ptr is narrowed to u32)
+    e2e_value = (edge_pairs / 2) / (float(e2e_s.item()) / n_e2e) / 1e9
+    h2d = (n + 1) * 4 + nnz * 4 + len(mine) * 4        # what crosses PCIe per step on this rank (32-bit CSR + source list)
     d2h = n * 8
 
+    line = None
     if rank == 0:
         # device and host-API results must be the same vector
         assert np.array_equal(np.asarray(res), result_dev.cpu().numpy()), "e2e result differs from device-timed result"
         peak, peak_src = hbm_peak()
         st0 = st                                            # rank 0's last step
         b_alg = 24.0 * st0["edge_pairs"] + 40.0 * st0["reached_pairs"]
-        eng_s = engine_ms / args.steps * 1e-3
+        eng_s = engine_ms / steps * 1e-3
         achieved = b_alg / eng_s / 1e9 if eng_s > 0 else None
+        eng = st0["engine"] & 15
+        kernel = {1: "vertex_load_engine<u8> (batched, %d sources per batch, %d-thread CTAs, %d per slot)" % (
+                        st0.get("batch_width") or 32, st0.get("cta_threads") or 0, st0.get("team_size") or 1),
+                  2: "mid_engine (one source per CTA)"}.get(eng, "?")
         line = {
-            "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if sample is None else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "n": n, "undirected_edges": nnz // 2,
-                       "sources_per_step": int(len(sources)), "include_endpoints": True,
-                       "sharding": "block-cyclic 32-source blocks over %d rank(s), one f64 all-reduce" % world,
-                       "l2": "no explicit flush: one step streams %.1f GB of per-source state (%.2f GB of arenas on rank 0, "
-                             "> 126 MB L2) and ends with different data in L2 than it starts with; the 2 MB adjacency slab is "
-                             "L2-resident by design" % (16e-6 * len(mine), st0["workspace_bytes"] / 1e9),
-                       "slots": st0["n_slots"], "batch_width": st0.get("batch_width"), "max_depth": st0["max_depth"],
-                       "queue_entries_per_vertex_per_batch": st0["vertex_visits"] / max(1, st0["n_batches"] * n),
-                       "phase_share": {"reset": st0["frac_reset"], "forward": st0["frac_forward"], "backward": st0["frac_backward"]}},
+            "config": static_config(name, n, nnz),
+            "details": {"sources_per_step": int(len(sources)), "resident_wave": int(wave),
+                        "sharding": "block-cyclic 32-source blocks over %d rank(s), one f64 all-reduce" % world,
+                        "l2": "no explicit flush: one step moves %.1f GB of per-batch state through %.2f GB of arenas on rank 0 "
+                              "(> 126 MB L2) and ends with different data in L2 than it starts with" % (
+                                  (profiled_traffic(name, len(mine)) or 0) / 1e9, st0["workspace_bytes"] / 1e9),
+                        "slots": st0["n_slots"], "batch_width": st0.get("batch_width"), "team_size": st0.get("team_size"),
+                        "cta_threads": st0.get("cta_threads"), "max_depth": st0["max_depth"],
+                        "levels_pulled": st0.get("pull_levels"), "levels_pushed": st0.get("push_levels"),
+                        "queue_entries_per_vertex_per_batch": st0["vertex_visits"] / max(1, st0["n_batches"] * n),
+                        "phase_share": {"reset": st0["frac_reset"], "forward": st0["frac_forward"], "backward": st0["frac_backward"]}},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+                    "from": "adjacency lists in pageable host memory (nec_graph_upload_adjacency), result to host"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(args.workload, len(mine)),
-                         "kernel": {1: "vertex_load_engine<u8> (batched, %d sources per CTA)" % (st0.get("batch_width") or 32), 2: "mid_engine (one source per CTA)"}.get(st0["engine"] & 15, "?"),
-                         "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(name, len(mine)),
+                         "kernel": kernel, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg, "kernel_ms_per_launch": eng_s * 1e3},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            orc = cpu_oracle()
+        # ---- parity gate beside the timing (every run, every N): sampled sources vs the oracle ----------
+        orc = cpu_oracle()
+        cores = host_cores()
+        if with_cpu_baseline:
             # bounded sample: ~10-20 s of single-thread CPU work (the crate is single-threaded)
             t0 = time.perf_counter()
+            rp, col = g.export_csr()
             orc.vertex_load(rp, col, True, sources=np.array([n // 2], np.uint32))
             per_source = max(time.perf_counter() - t0, 1e-5)
             k = int(min(len(sources), max(32, min(8192, 12.0 / per_source))))
@@ -374,16 +430,83 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": (orc.last_stats["edge_pairs"] / 2) / dt / 1e9, "unit": "GTEPS", "cores": 1,
                                     "kind": "port", "sample": "%d strided sources of %d, 1 thread (the crate is single-threaded)" % (len(src), n)}
-            # correctness gate beside the timing: same sample on the GPU, <= 1e-9 relative
-            got = dg.vertex_load_sources(src, True)
-            err = np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))
-            line["config"]["parity_vs_oracle_max_rel_err"] = float(err)
-            assert err <= 1e-9, "GPU result differs from the oracle: %g" % err
-        print(json.dumps(line), flush=True)
+        else:
+            rp, col = g.export_csr()
+            k = min(len(sources), 64)
+            src = sources[:: max(1, len(sources) // k)][:k]
+            want = orc.vertex_load(rp, col, True, sources=src, threads=cores)
+        got = dg.vertex_load_sources(src, True)
+        err = rel_err(got, want)
+        line["parity_vs_oracle_max_rel_err"] = err
+        line["details"]["parity_sample"] = "%d strided sources of the step's %d" % (len(src), len(sources))
+        assert err <= 1e-9, "GPU result differs from the oracle: %g" % err
+    barrier()
     dg.free()
     ctx.close()
+    return line
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "markov4096":
+        import net_ensembles_b200 as ne
+        ctx = ne.Context(local_rank)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        res = measure_markov(ctx, args.steps, args.warmup, rank, world, with_cpu=(rank == 0), comm=dist if world > 1 else None)
+        clocks = sampler.stop() if sampler else None
+        vals = torch.tensor([res["wall_s"], res["kernel_ms"]], dtype=torch.float64, device="cuda")
+        work = torch.tensor([res["te"], res["launches"], res["b_alg"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+            dist.all_reduce(work)
+        if rank == 0:
+            res.update(wall_s=float(vals[0]), kernel_ms=float(vals[1]), te=float(work[0]), launches=float(work[1]), b_alg=float(work[2]))
+            line = markov_line(res, args.steps, args.warmup, world, clocks)
+            line["cpu_baseline"] = res.get("cpu_baseline")
+            line["parity_vs_oracle_max_rel_err"] = res.get("parity")
+            print(json.dumps(line), flush=True)
+        ctx.close()
+    else:
+        line = measure_graph(args.workload, args.steps, args.warmup, rank, world, local_rank,
+                             with_cpu_baseline=(world == 1 and not args.no_cpu_baseline), sources_override=args.sources,
+                             sample_clocks=True, e2e_steps=5)
+        if rank == 0:
+            if world == 1 and not args.no_secondary and args.workload == DEFAULT_WORKLOAD and args.sources is None:
+                line["secondary"] = secondary_lines(local_rank)
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_lines(local_rank):
+    """The other four BASELINE configs, one short run each (N = 1 only), so that the driver's record holds a
+    measured value, e2e, roofline and parity figure for every config, not only the headline one."""
+    import net_ensembles_b200 as ne
+    out = {}
+    for name, (k, w) in (("erc1000", (20, 5)), ("sw65536", (3, 2)), ("ba2p22", (1, 1))):
+        try:
+            ln = measure_graph(name, k, w, 0, 1, local_rank, with_cpu_baseline=(name != "ba2p22"), e2e_steps=3)
+            out[name] = {key: ln.get(key) for key in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "details",
+                                                      "e2e", "roofline", "cpu_baseline", "parity_vs_oracle_max_rel_err", "gpu_launches")}
+        except Exception as ex:                       # a secondary failure must not lose the headline line
+            out[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    try:
+        ctx = ne.Context(local_rank)
+        res = measure_markov(ctx, 10, 3, 0, 1, with_cpu=True)
+        ln = markov_line(res, 10, 3, 1)
+        ln["cpu_baseline"], ln["parity_vs_oracle_max_rel_err"] = res.get("cpu_baseline"), res.get("parity")
+        out["markov4096"] = {key: ln.get(key) for key in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "details",
+                                                         "e2e", "roofline", "cpu_baseline", "parity_vs_oracle_max_rel_err", "gpu_launches")}
+        ctx.close()
+    except Exception as ex:
+        out["markov4096"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return out
 
 
 def main():
@@ -392,9 +515,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sw65536", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sources", type=int, default=None, help="sample this many sources per step (whole 32-blocks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the one-step runs of the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -404,10 +528,7 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus %d needs torch.distributed.run with --nproc-per-node %d" % (args.gpus, args.gpus))
-    if args.workload == "markov4096":
-        run_markov(args, rank, world, local_rank)
-    else:
-        run_ours(args, rank, world, local_rank)
+    run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

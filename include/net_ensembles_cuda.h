@@ -87,6 +87,13 @@ int nec_set_engine(nec_ctx *ctx, int engine);
  * col_idx < n).  Replaces the per-call traversal of the crate's adjacency lists. */
 int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr,
                      const uint32_t *col_idx, nec_graph **out);
+/* Same graph, handed over as the crate stores it: vertex v's neighbours are the `degrees[v]` elements of the
+ * contiguous slice rows[v] (`AdjList::edges()`: &[usize] src/graph.rs:145-150, &[SwEdge] src/sw_graph.rs:164-170),
+ * each element `elem_stride` bytes with the neighbour id (`to_width` = 4 or 8 bytes, little endian) at byte
+ * `to_offset`.  The library flattens, narrows to u32, validates and stages the rows itself (all host cores, pinned
+ * memory), preserving adjacency order: the export fast path that spares the caller a CSR in pageable memory. */
+int nec_graph_upload_adjacency(nec_ctx *ctx, uint32_t n, const void *const *rows, const uint64_t *degrees,
+                               uint32_t elem_stride, uint32_t to_offset, uint32_t to_width, nec_graph **out);
 void nec_graph_free(nec_ctx *ctx, nec_graph *g);
 
 /* vertex_load(include_endpoints) over all sources: out[n] (host) is overwritten.

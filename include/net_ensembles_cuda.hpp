@@ -12,6 +12,7 @@
 // vector owned by the caller.  The reference call is infallible; here a failing device call
 // throws (the Rust shim panics) — there is no CPU fallback.
 #pragma once
+#include <cstddef>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -43,11 +44,13 @@ class DeviceGraph {
 public:
     template <class E>
     DeviceGraph(Context &ctx, const nec_host::GenericGraph<E> &g) : ctx_(ctx), n_((uint32_t)g.vertex_count()) {
-        std::vector<uint64_t> row_ptr(g.vertex_count() + 1);
-        std::vector<uint32_t> col(g.nnz());
-        g.export_csr(row_ptr.data(), col.data());
-        if (nec_graph_upload(ctx.raw(), n_, col.size(), row_ptr.data(), col.data(), &g_) != NEC_OK)
-            throw std::runtime_error(std::string("nec_graph_upload: ") + nec_last_error(ctx.raw()));
+        // the containers keep a vertex's neighbours in one contiguous slice (AdjList::edges()): hand the slices
+        // over and let the library flatten them into its pinned staging area (export fast path)
+        std::vector<const void *> rows(n_);
+        std::vector<uint64_t> deg(n_);
+        for (uint32_t v = 0; v < n_; ++v) { rows[v] = g.vertices[v].adj.data(); deg[v] = g.vertices[v].adj.size(); }
+        if (nec_graph_upload_adjacency(ctx.raw(), n_, rows.data(), deg.data(), (uint32_t)sizeof(E), (uint32_t)offsetof(E, to), 4u, &g_) != NEC_OK)
+            throw std::runtime_error(std::string("nec_graph_upload_adjacency: ") + nec_last_error(ctx.raw()));
     }
     ~DeviceGraph() { nec_graph_free(ctx_.raw(), g_); }
     DeviceGraph(const DeviceGraph &) = delete;

@@ -9,13 +9,15 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnet_ensembles_cuda.so")
+HOST_LIB_PATH = os.path.join(LIB_DIR, "libnec_host.so")     # graph / ensemble mirror: no CUDA, not linked to the CUDA library
 ORACLE_PATH = os.path.join(ROOT, "oracle", "build", "liboracle.so")
 
-CUDA_SOURCES = [os.path.join(PKG, "csrc", "nec_api.cu"), os.path.join(PKG, "csrc", "host", "host_api.cpp")]
-CUDA_DEPS = CUDA_SOURCES + [
+HOST_HEADERS = [os.path.join(PKG, "csrc", "host", h) for h in ("nec_graphs.hpp", "nec_rand.hpp", "nec_handle.hpp")]
+HOST_SOURCES = [os.path.join(PKG, "csrc", "host", "host_api.cpp")]
+CUDA_SOURCES = [os.path.join(PKG, "csrc", "nec_api.cu"), os.path.join(PKG, "csrc", "host", "host_bridge.cpp")]
+CUDA_DEPS = CUDA_SOURCES + HOST_HEADERS + [
     os.path.join(PKG, "csrc", "nec_kernels.cuh"), os.path.join(PKG, "csrc", "nec_small.cuh"),
-    os.path.join(PKG, "csrc", "nec_mid.cuh"),
-    os.path.join(PKG, "csrc", "host", "nec_graphs.hpp"), os.path.join(PKG, "csrc", "host", "nec_rand.hpp"),
+    os.path.join(PKG, "csrc", "nec_mid.cuh"), os.path.join(PKG, "csrc", "nec_chain.cuh"), os.path.join(PKG, "csrc", "nec_multi.hpp"),
     os.path.join(ROOT, "include", "net_ensembles_cuda.h"),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,6 +53,18 @@ def build_cuda(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_host(force=False):
+    if not force and not _stale(HOST_LIB_PATH, HOST_SOURCES + HOST_HEADERS):
+        return HOST_LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-fopenmp", "-shared"] + HOST_SOURCES + ["-o", HOST_LIB_PATH]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host library build failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    return HOST_LIB_PATH
+
+
 def build_oracle(force=False):
     src = os.path.join(ROOT, "oracle", "ref_vertex_load.c")
     if not force and not _stale(ORACLE_PATH, [src, os.path.join(ROOT, "oracle", "ref_measures.c"), os.path.join(ROOT, "oracle", "Makefile")]):
@@ -63,6 +77,7 @@ def build_oracle(force=False):
 
 
 def build_all(force=False, verbose=False):
+    build_host(force)
     return build_cuda(force, verbose), build_oracle(force)
 
 

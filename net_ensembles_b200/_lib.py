@@ -35,6 +35,7 @@ NEC_SYMBOLS = {
     "nec_set_workspace_limit": (c_int, [c_vp, c_u64]),
     "nec_set_engine": (c_int, [c_vp, c_int]),
     "nec_graph_upload": (c_int, [c_vp, c_u32, c_u64, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "nec_graph_upload_adjacency": (c_int, [c_vp, c_u32, c_vp, c_vp, c_u32, c_u32, c_u32, ctypes.POINTER(c_vp)]),
     "nec_graph_free": (None, [c_vp, c_vp]),
     "nec_vertex_load": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nec_vertex_load_sources": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, c_vp]),
@@ -65,13 +66,34 @@ NECH_SYMBOLS = {
     "nech_export_csr": (c_int, [c_vp, c_vp, c_vp]),
     "nech_sw_root_targets": (c_int, [c_vp, c_vp]),
     "nech_rng_state": (c_int, [c_vp, c_vp]),
+    "nech_pcg64_draws": (None, [c_u64, c_u64, c_vp]),
+}
+# the drop-in calls over host-mirror handles: compiled into the CUDA library (csrc/host/host_bridge.cpp)
+BRIDGE_SYMBOLS = {
+    "nech_upload_cuda": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nech_vertex_load_cuda": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nech_chains_step_and_load_cuda": (c_int, [c_vp, c_u32, c_u64, c_vp, c_int, c_vp]),
     "nech_last_chain_stats": (None, [ctypes.POINTER(NecStats)]),
-    "nech_pcg64_draws": (None, [c_u64, c_u64, c_vp]),
 }
 
 _lib = None
+_host = None
+
+
+def load_host():
+    """The graph / ensemble mirror (libnec_host.so): input producers only, no CUDA behind it."""
+    global _host
+    if _host is not None:
+        return _host
+    path = os.environ.get("NEC_HOST_LIB_PATH") or _build.HOST_LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in NECH_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _host = lib
+    return lib
 
 
 def lib_path():
@@ -90,7 +112,7 @@ def load():
             "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(net_ensembles_b200 has no CPU fallback)" % path)
     lib = ctypes.CDLL(path)
-    for table in (NEC_SYMBOLS, NECH_SYMBOLS):
+    for table in (NEC_SYMBOLS, BRIDGE_SYMBOLS):
         for name, (res, args) in table.items():
             fn = getattr(lib, name)          # AttributeError if the export is missing
             fn.restype, fn.argtypes = res, args

@@ -77,8 +77,15 @@ def default_context():
 class DeviceGraph:
     """Device-resident CSR of one sampled graph (nec_graph): export once, measure many times."""
 
-    def __init__(self, ctx, row_ptr, col_idx):
+    def __init__(self, ctx, row_ptr=None, col_idx=None, _host=None):
         self.ctx = ctx
+        if _host is not None:
+            # straight from a host mirror's adjacency lists (export fast path: no CSR is built on the Python side)
+            self.n, self.nnz = _host.vertex_count(), 2 * _host.edge_count()
+            h = c_vp()
+            ctx._check(ctx._lib.nech_upload_cuda(_host._h, ctx._h, ctypes.byref(h)))
+            self._h = h
+            return
         row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
         col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
         self.n = int(row_ptr.shape[0]) - 1
@@ -193,13 +200,11 @@ class ChainBatch:
     def step_and_load(self, ctx, m_steps, include_endpoints):
         """Returns the load vectors: a (chains, n) array when all graphs have the same size, else a list of
         views.  The buffer is reused by the next call."""
-        lib = _lib.load()
+        lib = ctx._lib
         if not self.chains:
             return []
-        rc = lib.nech_chains_step_and_load_cuda(self._handles, len(self.chains), int(m_steps), ctx._h,
-                                                int(bool(include_endpoints)), _ptr(self._out))
-        if rc != 0:
-            raise NecError(rc, lib.nech_last_error().decode())
+        ctx._check(lib.nech_chains_step_and_load_cuda(self._handles, len(self.chains), int(m_steps), ctx._h,
+                                                      int(bool(include_endpoints)), _ptr(self._out)))
         st = _lib.NecStats()
         lib.nech_last_chain_stats(ctypes.byref(st))
         self.stats = st.as_dict()          # counters of this step
@@ -220,7 +225,7 @@ class _HostGraph:
     """Base of the host-side mirrors: owns a nech handle (adjacency lists live in C++)."""
 
     def __init__(self, handle):
-        self._lib = _lib.load()
+        self._lib = _lib.load_host()       # input side only: no CUDA library is needed to build or step graphs
         if not handle:
             raise ValueError(self._lib.nech_last_error().decode())
         self._h = c_vp(handle)
@@ -265,14 +270,13 @@ class _HostGraph:
         a fresh f64 vector.  Raises NecError on any device failure (no CPU fallback)."""
         ctx = ctx or default_context()
         out = np.empty(self.vertex_count(), dtype=np.float64)
-        rc = self._lib.nech_vertex_load_cuda(self._h, ctx._h, int(bool(include_endpoints)), _ptr(out))
-        if rc != 0:
-            raise NecError(rc, self._lib.nech_last_error().decode())
+        ctx._check(ctx._lib.nech_vertex_load_cuda(self._h, ctx._h, int(bool(include_endpoints)), _ptr(out)))
         return out
 
     def to_device(self, ctx=None):
+        """Device-resident CSR of the current adjacency lists ("export once per sampled graph")."""
         ctx = ctx or default_context()
-        return DeviceGraph(ctx, *self.export_csr())
+        return DeviceGraph(ctx, _host=self)
 
     # the all-source BFS measures that sit beside vertex_load in the crate's benches
     def diameter(self, ctx=None):
@@ -301,7 +305,7 @@ class Graph(_HostGraph):
     """`Graph<T>` = GenericGraph with plain adjacency lists (src/graph.rs:309)."""
 
     def __init__(self, n, _handle=None):
-        lib = _lib.load()
+        lib = _lib.load_host()
         super().__init__(_handle if _handle is not None else lib.nech_graph_new(n))
 
 
@@ -331,21 +335,21 @@ class ErEnsembleC(_Ensemble):
     """ErEnsembleC::new(n, c_target, Pcg64::seed_from_u64(seed)) (src/er_c.rs:239)."""
 
     def __init__(self, n, c_target, seed):
-        super().__init__(_lib.load().nech_erc_new(n, c_target, seed))
+        super().__init__(_lib.load_host().nech_erc_new(n, c_target, seed))
 
 
 class ErEnsembleM(_Ensemble):
     """ErEnsembleM::new(n, m, rng) (src/er_m.rs:245); O(n^2) memory like the crate."""
 
     def __init__(self, n, m, seed):
-        super().__init__(_lib.load().nech_erm_new(n, m, seed))
+        super().__init__(_lib.load_host().nech_erm_new(n, m, seed))
 
 
 class SwEnsemble(_Ensemble):
     """SwEnsemble::new(n, r_prob, rng) / new_with_distance (src/sw.rs:214,234)."""
 
     def __init__(self, n, r_prob, seed, ring_distance=2):
-        super().__init__(_lib.load().nech_sw_new(n, r_prob, seed, ring_distance))
+        super().__init__(_lib.load_host().nech_sw_new(n, r_prob, seed, ring_distance))
 
     def root_targets(self):
         out = np.empty(int(self._lib.nech_nnz(self._h)), np.uint32)
@@ -357,14 +361,14 @@ class BAensemble(_Ensemble):
     """BAensemble::new(n, rng, m, source_n) (src/barabasi_albert.rs:89); O(n^2) like the crate."""
 
     def __init__(self, n, seed, m, source_n):
-        super().__init__(_lib.load().nech_ba_new(n, m, source_n, seed))
+        super().__init__(_lib.load_host().nech_ba_new(n, m, source_n, seed))
 
 
 def gnm_scalable(n, m, seed):
     """G(n,m) for sizes the crate's ErEnsembleM cannot reach; not seed-identical to the crate."""
-    return Graph(n, _handle=_lib.load().nech_gnm_scalable(n, m, seed))
+    return Graph(n, _handle=_lib.load_host().nech_gnm_scalable(n, m, seed))
 
 
 def ba_scalable(n, m, source_n, seed):
     """Barabasi-Albert for sizes the crate's BAensemble cannot reach; not seed-identical."""
-    return Graph(n, _handle=_lib.load().nech_ba_scalable(n, m, source_n, seed))
+    return Graph(n, _handle=_lib.load_host().nech_ba_scalable(n, m, source_n, seed))

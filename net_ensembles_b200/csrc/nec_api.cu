@@ -81,6 +81,7 @@ struct nec_ctx {
     uint32_t team_size = 1;                           // batched engine: CTAs per slot (thread-block cluster), set per call
     int team_cap[2][9];                               // resident clusters per (batch width 32/64, team size); -1 = not asked yet
     nec::SmallWorkspace small;
+    void *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of an upload's 32-bit CSR
     nec_stats stats{};
 };
 
@@ -692,6 +693,9 @@ const char *nec_version(void) { return "net_ensembles_cuda 0.1.0 sm_100a"; }
 
 const char *nec_last_error(const nec_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 
+// for host_bridge.cpp (same library): failures detected above the C ABI are reported through the context too
+void nec_internal_set_error(nec_ctx *ctx, const char *msg) { if (ctx) ctx->err = msg ? msg : ""; }
+
 int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     if (!out) return fail(nullptr, NEC_EINVAL, "nec_init: out is NULL");
     *out = nullptr;
@@ -757,6 +761,7 @@ void nec_destroy(nec_ctx *ctx) {
     if (ctx->mid_base) cudaFree(ctx->mid_base);
     if (ctx->d_src_status) cudaFree(ctx->d_src_status);
     ctx->small.release();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
@@ -782,31 +787,11 @@ int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes) {
     return NEC_OK;
 }
 
-int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr, const uint32_t *col_idx, nec_graph **out) try {
-    if (!ctx) return NEC_EINVAL;
-    if (!out) return fail(ctx, NEC_EINVAL, "nec_graph_upload: out is NULL");
-    *out = nullptr;
-    if (!row_ptr || (nnz && !col_idx)) return fail(ctx, NEC_EINVAL, "nec_graph_upload: NULL CSR pointer");
-    if (nnz >= 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload: nnz=%llu does not fit 32-bit row pointers", (unsigned long long)nnz);
-    if (n > 0x7FFFFFFFu / nec::kLanes * 16) return fail(ctx, NEC_EINVAL, "nec_graph_upload: n=%u too large", n);
-    if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr[0] must be 0 and row_ptr[n] == nnz");
-    std::vector<uint32_t> rp32((size_t)n + 1);
-    uint32_t max_deg = 0;
-    // validation and the 64 -> 32 bit row pointers on all host cores for large graphs (tens of ms at N = 2^22)
-    long long bad_row = (long long)n, bad_entry = (long long)nnz;
-#pragma omp parallel for schedule(static) reduction(max : max_deg) reduction(min : bad_row) if (n > 100000)
-    for (long long v = 0; v < (long long)n; ++v) {
-        if (row_ptr[v + 1] < row_ptr[v]) bad_row = std::min(bad_row, v);
-        else max_deg = std::max<uint32_t>(max_deg, (uint32_t)std::min<uint64_t>(row_ptr[v + 1] - row_ptr[v], 0xFFFFFFFFull));
-        rp32[v] = (uint32_t)row_ptr[v];
-    }
-    if (bad_row < (long long)n) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr not monotone at %u", (uint32_t)bad_row);
-    rp32[n] = (uint32_t)nnz;
-#pragma omp parallel for schedule(static) reduction(min : bad_entry) if (nnz > 400000)
-    for (long long e = 0; e < (long long)nnz; ++e)
-        if (col_idx[e] >= n) bad_entry = std::min(bad_entry, e);
-    if (bad_entry < (long long)nnz)
-        return fail(ctx, NEC_EINVAL, "nec_graph_upload: col_idx[%llu]=%u out of range (n=%u)", (unsigned long long)bad_entry, col_idx[bad_entry], n);
+// Shared tail of the two upload entry points: the 32-bit CSR sits validated in the context's pinned staging
+// area (row pointers, then neighbour ids); allocate the device graph, copy, and build the mid engine's slab
+// rows and degree bytes ON THE DEVICE from the CSR that has just arrived.
+static int finish_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint32_t *h_rp32, const uint32_t *h_col,
+                         uint32_t max_deg, size_t over8, nec_graph **out) {
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     nec_graph *g = new (std::nothrow) nec_graph();
     if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
@@ -815,36 +800,135 @@ int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row
     // cudaMalloc/cudaFree pairs (device-wide synchronisation, up to 0.5 s observed) would dominate
     cudaError_t e = cudaMallocAsync((void **)&g->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_col_idx, std::max<size_t>(nnz, 1) * sizeof(uint32_t), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, rp32.data(), ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    std::vector<uint32_t> slab;
-    std::vector<uint8_t> deg8;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_row_ptr, h_rp32, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(g->d_col_idx, h_col, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n > 0 && n <= nec::kMidMaxN) {
         // slab rows: [degree, first W-1 neighbours]; W = 8 unless more than 10 % of the rows would overflow
-        size_t over8 = 0;
-        for (uint32_t v = 0; v < n; ++v) over8 += (row_ptr[v + 1] - row_ptr[v]) > 7;
         g->slab_w = over8 * 10 > n ? 16 : 8;
-        const int W = g->slab_w;
-        slab.assign((size_t)n * W, 0u);
-        for (uint32_t v = 0; v < n; ++v) {
-            const uint64_t rs = row_ptr[v], deg = row_ptr[v + 1] - rs;
-            slab[(size_t)v * W] = (uint32_t)deg;
-            for (uint64_t k = 0; k < deg && k < (uint64_t)(W - 1); ++k) slab[(size_t)v * W + 1 + k] = col_idx[rs + k];
+        const size_t slab_words = (size_t)n * g->slab_w;
+        e = cudaMallocAsync((void **)&g->d_slab, slab_words * sizeof(uint32_t), ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_deg8, (size_t)n + 2, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->d_deg8 + n, 0, 2, ctx->stream);
+        if (e == cudaSuccess) {
+            const unsigned blocks = (unsigned)std::min<size_t>((slab_words + 255) / 256, 148u * 16u);
+            nec::build_slab_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g->slab_w, g->d_row_ptr, g->d_col_idx, reinterpret_cast<uint32_t *>(g->d_slab), g->d_deg8);
+            e = cudaGetLastError();
         }
-        deg8.resize((size_t)n + 2);
-        for (uint32_t v = 0; v < n; ++v) deg8[v] = (uint8_t)std::min<uint64_t>(row_ptr[v + 1] - row_ptr[v], 255);
-        e = cudaMallocAsync((void **)&g->d_slab, slab.size() * sizeof(uint32_t), ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_slab, slab.data(), slab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_deg8, deg8.size(), ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(g->d_deg8, deg8.data(), deg8.size(), cudaMemcpyHostToDevice, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // the staging area is reused by the next upload
     if (e != cudaSuccess) {
         nec_graph_free(ctx, g);
-        return fail(ctx, e == cudaErrorMemoryAllocation ? NEC_ENOMEM : NEC_ECUDA, "nec_graph_upload: %s", cudaGetErrorString(e));
+        return fail(ctx, e == cudaErrorMemoryAllocation ? NEC_ENOMEM : NEC_ECUDA, "graph upload: %s", cudaGetErrorString(e));
     }
     *out = g;
     return NEC_OK;
+}
+
+// Pinned staging of the 32-bit CSR: [row_ptr (n+1) | pad to 256 B | col_idx (nnz)].
+static int stage_reserve(nec_ctx *ctx, uint32_t n, uint64_t nnz, uint32_t *&h_rp32, uint32_t *&h_col) {
+    const size_t rp_bytes = align_up(((size_t)n + 1) * 4, 256), need = rp_bytes + std::max<uint64_t>(nnz, 1) * 4;
+    if (need > ctx->h_stage_cap) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+        const size_t cap = need + need / 8;
+        cudaError_t e = cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(ctx, NEC_ENOMEM, "cudaHostAlloc(%zu B CSR staging) failed: %s", cap, cudaGetErrorString(e));
+        ctx->h_stage_cap = cap;
+    }
+    h_rp32 = reinterpret_cast<uint32_t *>(ctx->h_stage);
+    h_col = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ctx->h_stage) + rp_bytes);
+    return NEC_OK;
+}
+
+int nec_graph_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint64_t *row_ptr, const uint32_t *col_idx, nec_graph **out) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!out) return fail(ctx, NEC_EINVAL, "nec_graph_upload: out is NULL");
+    *out = nullptr;
+    if (!row_ptr || (nnz && !col_idx)) return fail(ctx, NEC_EINVAL, "nec_graph_upload: NULL CSR pointer");
+    if (nnz >= 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload: nnz=%llu does not fit 32-bit row pointers", (unsigned long long)nnz);
+    if (n > 0x7FFFFFFFu / 64u * 16) return fail(ctx, NEC_EINVAL, "nec_graph_upload: n=%u too large", n);
+    if ((uint64_t)n * 64u + 64u > 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload: n=%u: the level queues (64 entries per vertex) need 32-bit positions", n);
+    if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr[0] must be 0 and row_ptr[n] == nnz");
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t *rp32 = nullptr, *col32 = nullptr;
+    int rc = stage_reserve(ctx, n, nnz, rp32, col32);
+    if (rc != NEC_OK) return rc;
+    uint32_t max_deg = 0;
+    size_t over8 = 0;
+    // validation, the 64 -> 32 bit row pointers and the copy into pinned memory in ONE pass per array, on all
+    // host cores for large graphs (tens of ms at N = 2^22)
+    long long bad_row = (long long)n, bad_entry = (long long)nnz;
+#pragma omp parallel for schedule(static) reduction(max : max_deg) reduction(min : bad_row) reduction(+ : over8) if (n > 100000)
+    for (long long v = 0; v < (long long)n; ++v) {
+        if (row_ptr[v + 1] < row_ptr[v]) bad_row = std::min(bad_row, v);
+        else {
+            const uint64_t d = row_ptr[v + 1] - row_ptr[v];
+            max_deg = std::max<uint32_t>(max_deg, (uint32_t)std::min<uint64_t>(d, 0xFFFFFFFFull));
+            over8 += d > 7;
+        }
+        rp32[v] = (uint32_t)row_ptr[v];
+    }
+    if (bad_row < (long long)n) return fail(ctx, NEC_EINVAL, "nec_graph_upload: row_ptr not monotone at %u", (uint32_t)bad_row);
+    rp32[n] = (uint32_t)nnz;
+#pragma omp parallel for schedule(static) reduction(min : bad_entry) if (nnz > 400000)
+    for (long long e = 0; e < (long long)nnz; ++e) {
+        const uint32_t x = col_idx[e];
+        if (x >= n) bad_entry = std::min(bad_entry, e);
+        col32[e] = x;
+    }
+    if (bad_entry < (long long)nnz)
+        return fail(ctx, NEC_EINVAL, "nec_graph_upload: col_idx[%llu]=%u out of range (n=%u)", (unsigned long long)bad_entry, col_idx[bad_entry], n);
+    return finish_upload(ctx, n, nnz, rp32, col32, max_deg, over8, out);
+} NEC_CATCH_ALL(ctx)
+
+// Export fast path: the crate keeps a vertex's neighbours in one contiguous slice (`AdjList::edges()`:
+// &[usize] for NodeContainer, src/graph.rs:145-150; &[SwEdge] for SwContainer, src/sw_graph.rs:164-170), so
+// the caller hands over n (pointer, length) pairs plus the element layout and the library flattens them -
+// narrowing to u32, validating and writing straight into its pinned staging area on all host cores - instead
+// of the caller building a CSR in pageable memory that is then copied again.  Adjacency ORDER is preserved.
+int nec_graph_upload_adjacency(nec_ctx *ctx, uint32_t n, const void *const *rows, const uint64_t *degrees, uint32_t elem_stride,
+                               uint32_t to_offset, uint32_t to_width, nec_graph **out) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!out) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: out is NULL");
+    *out = nullptr;
+    if (n && (!rows || !degrees)) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: NULL argument");
+    if ((to_width != 4 && to_width != 8) || elem_stride < to_offset + to_width)
+        return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: element layout stride=%u offset=%u width=%u is not a 4- or 8-byte id inside the element", elem_stride, to_offset, to_width);
+    if ((uint64_t)n * 64u + 64u > 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: n=%u too large", n);
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t nnz = 0;
+    uint32_t max_deg = 0;
+    size_t over8 = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        if (degrees[v] && !rows[v]) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: row %u is NULL with %llu entries", v, (unsigned long long)degrees[v]);
+        nnz += degrees[v];
+        if (nnz >= 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: more than 2^32 - 2 adjacency entries");
+        max_deg = std::max<uint32_t>(max_deg, (uint32_t)degrees[v]);
+        over8 += degrees[v] > 7;
+    }
+    uint32_t *rp32 = nullptr, *col32 = nullptr;
+    int rc = stage_reserve(ctx, n, nnz, rp32, col32);
+    if (rc != NEC_OK) return rc;
+    {
+        uint64_t at = 0;
+        for (uint32_t v = 0; v < n; ++v) { rp32[v] = (uint32_t)at; at += degrees[v]; }
+        rp32[n] = (uint32_t)at;
+    }
+    long long bad_row = (long long)n;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(min : bad_row) if (nnz > 400000)
+    for (long long v = 0; v < (long long)n; ++v) {
+        const uint8_t *src = static_cast<const uint8_t *>(rows[v]) + to_offset;
+        uint32_t *dst = col32 + rp32[v];
+        const uint64_t d = degrees[v];
+        bool ok = true;
+        if (to_width == 8)
+            for (uint64_t k = 0; k < d; ++k) { uint64_t x; std::memcpy(&x, src + k * elem_stride, 8); ok = ok && x < n; dst[k] = (uint32_t)x; }
+        else
+            for (uint64_t k = 0; k < d; ++k) { uint32_t x; std::memcpy(&x, src + k * elem_stride, 4); ok = ok && x < n; dst[k] = x; }
+        if (!ok) bad_row = std::min(bad_row, v);
+    }
+    if (bad_row < (long long)n) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: a neighbour id of vertex %u is out of range (n=%u)", (uint32_t)bad_row, n);
+    return finish_upload(ctx, n, nnz, rp32, col32, max_deg, over8, out);
 } NEC_CATCH_ALL(ctx)
 
 void nec_graph_free(nec_ctx *ctx, nec_graph *g) {

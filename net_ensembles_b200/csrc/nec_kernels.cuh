@@ -769,6 +769,21 @@ __global__ void add_into_kernel(double *__restrict__ a, const double *__restrict
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) a[v] += b[v];
 }
 
+// Mid engine's adjacency slab and degree bytes from the device CSR (nec_graph upload): row v =
+// [degree, first W-1 neighbours, zero padding]; one thread per slab word, so the stores are coalesced.
+__global__ void build_slab_kernel(uint32_t n, int W, const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col_idx,
+                                  uint32_t *__restrict__ slab, uint8_t *__restrict__ deg8) {
+    const size_t words = (size_t)n * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = (uint32_t)(i / W), k = (uint32_t)(i % W);
+        const uint32_t rs = row_ptr[v], deg = row_ptr[v + 1] - rs;
+        uint32_t w = 0;
+        if (k == 0) { w = deg; deg8[v] = (uint8_t)(deg < 255u ? deg : 255u); }
+        else if (k - 1 < deg) w = col_idx[rs + k - 1];
+        slab[i] = w;
+    }
+}
+
 // Distance measures of the sources one engine handed to the other, scattered back to their places.
 __global__ void scatter_measures_kernel(uint32_t k, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ pe,
                                         const unsigned long long *__restrict__ ps, const uint32_t *__restrict__ pr,

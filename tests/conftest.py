@@ -16,7 +16,7 @@ def pytest_configure(config):
 def built():
     """Native artefacts present (built in-tree by __graft_entry__.build())."""
     from net_ensembles_b200 import _build
-    if not (os.path.exists(_build.LIB_PATH) and os.path.exists(_build.ORACLE_PATH)):
+    if not (os.path.exists(_build.LIB_PATH) and os.path.exists(_build.HOST_LIB_PATH) and os.path.exists(_build.ORACLE_PATH)):
         _build.build_all()
     return _build
 

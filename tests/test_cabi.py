@@ -29,6 +29,28 @@ def test_header_symbols_are_exported_and_bound(built):
     assert b"sm_100a" in lib.nec_version()
 
 
+def test_host_mirror_is_a_separate_library_without_cuda(built):
+    """The graph / ensemble mirror (input producers) lives in libnec_host.so, which links neither the CUDA
+    runtime nor the product library: harness code that only builds graphs (bench.py's CPU baseline arm) never
+    maps libnet_ensembles_cuda.so.  The drop-in calls over handles are exported by the CUDA library."""
+    import subprocess
+    from net_ensembles_b200 import _lib
+    assert os.path.exists(built.HOST_LIB_PATH)
+    needed = subprocess.run(["readelf", "-d", built.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcudart" not in needed and "libnet_ensembles_cuda" not in needed and "libcuda.so" not in needed
+    host = ctypes.CDLL(built.HOST_LIB_PATH)
+    for name in _lib.NECH_SYMBOLS:
+        assert hasattr(host, name), "libnec_host.so lacks " + name
+    cuda = ctypes.CDLL(built.LIB_PATH)
+    for name in _lib.BRIDGE_SYMBOLS:
+        assert hasattr(cuda, name), "libnet_ensembles_cuda.so lacks " + name
+        assert not hasattr(host, name)
+    code = ("import sys; sys.path.insert(0, %r); import net_ensembles_b200 as ne; e = ne.ErEnsembleC(50, 4.0, 1); e.m_steps(3); e.export_csr();"
+            "maps = open('/proc/self/maps').read(); assert 'libnec_host' in maps and 'libnet_ensembles_cuda' not in maps" % ROOT)
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_library_contains_only_sm100a_code(built):
     import shutil
     import subprocess

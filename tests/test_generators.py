@@ -84,7 +84,7 @@ def test_pcg64_known_answer(built):
     """Pcg64::seed_from_u64(123929) run through ErEnsembleC(123, 2.0) ends in the fixture's state;
     additionally the raw stream is reproducible and distinct per seed."""
     from net_ensembles_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_host()
     a, b = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
     lib.nech_pcg64_draws(1, 4, a.ctypes.data)
     lib.nech_pcg64_draws(1, 4, b.ctypes.data)

@@ -449,6 +449,8 @@ def _full_size_properties(ctx, oracle, rp, col, src, want_engine, want_width):
       sum_v load_true(v)               = sum_{s in S} sum_v d_s(v)       (a unit from v crosses d_s(v) vertices),
     the right-hand sides being the exact integers of nec_distance_measures (forward pass alone)."""
     dg = ctx.upload(rp, col)
+    if callable(src):
+        src = src(dg)
     lt = dg.vertex_load_sources(src, True)
     st = ctx.stats()
     assert st["engine"] & 15 == want_engine and (want_width is None or st["batch_width"] == want_width)
@@ -478,15 +480,50 @@ def test_full_size_properties_config4_gnm(ctx, oracle):
     g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)          # BASELINE configs[3] (scalable generator), sampled sources
     rp, col = g.export_csr()
     src = (np.arange(9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
-    _full_size_properties(ctx, oracle, rp, col, src, 1, 64)
+    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 64)
+    assert st["team_size"] == 1 and st["cta_threads"] == 1024 and st["n_slots"] == 148 and st["pull_levels"] > 0
 
 
 def test_full_size_properties_config5_barabasi_albert(ctx, oracle):
-    g = ne.ba_scalable(1 << 22, 4, 5, 20261020)              # BASELINE configs[4] (scalable generator), sampled sources
+    """BASELINE configs[4] on the path the bench takes: one resident wave of sources through the DEFAULT plan, which
+    on this graph is 64-wide batches on memory-limited slots, each run by a thread-block cluster of 512-thread CTAs."""
+    g = ne.ba_scalable(1 << 22, 4, 5, 20261020)              # (scalable generator), sampled sources
+    rp, col = g.export_csr()
+
+    def one_wave(dg):
+        wave = dg.wave_size()
+        assert wave % 64 == 0 and wave >= 64 * 37
+        return (np.arange(wave, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
+
+    st = _full_size_properties(ctx, oracle, rp, col, one_wave, 1, 64)
+    assert st["team_size"] >= 3 and st["cta_threads"] == 512 and st["n_slots"] * 64 == st["n_sources"]
+    assert st["n_slots"] * st["team_size"] <= 148 * 2
+    assert st["pull_levels"] > 0 and st["push_levels"] > 0    # direction chosen per level
+    assert st["reached_pairs"] == st["n_sources"] * (1 << 22)  # a BA graph is connected
+
+
+def test_config5_narrow_batches_for_small_calls(ctx, oracle):
+    g = ne.ba_scalable(1 << 22, 4, 5, 20261020)
     rp, col = g.export_csr()
     src = (np.arange(1536, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
-    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)
-    assert st["reached_pairs"] == 1536 * (1 << 22)           # a BA graph is connected
+    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)   # too few sources for the 64-wide layout's slots
+    assert st["reached_pairs"] == 1536 * (1 << 22)
+
+
+def test_config3_verbatim_4096_chains_of_256(ctx, oracle):
+    """BASELINE configs[2] at its real size: 4096 Markov chains of ErC N=256 c=4 in one ChainBatch, three
+    measurement steps; 96 sampled chains are compared with the oracle on independently stepped twins."""
+    seeds = [123_239_010 + g for g in range(4096)]
+    batch = ne.ChainBatch([ne.ErEnsembleC(256, 4.0, s) for s in seeds])
+    pick = list(range(0, 4096, 43))[:96] + [4095]
+    twins = {g: ne.ErEnsembleC(256, 4.0, seeds[g]) for g in pick}
+    for step in range(3):
+        outs = batch.step_and_load(ctx, 1, True)
+        assert outs.shape == (4096, 256) and batch.stats["n_sources"] == 4096 * 256 and batch.stats["engine"] == 3
+        for g in pick:
+            twins[g].m_steps(1)
+            rp, col = twins[g].export_csr()
+            assert close(outs[g], oracle.vertex_load(rp, col, True), REL), (step, g)
 
 
 @pytest.mark.parametrize("width", ["32", "64"])
