@@ -53,10 +53,15 @@ typedef struct nec_graph nec_graph; /* opaque: device-resident CSR of one sample
 /* Library / build identification ("net_ensembles_cuda <version> sm_100a"). */
 const char *nec_version(void);
 
-/* Create a context on CUDA device `devices[0]` (n_devices must be 1 in this
- * revision; multi-GPU runs use one process + one context per GPU and combine the
- * per-GPU vectors with an NCCL all-reduce).  devices == NULL
- * selects the current device. */
+/* Create a context on the listed CUDA devices.  n_devices == 1: one GPU (devices == NULL selects the current
+ * device).  n_devices > 1 (devices == NULL: 0..n_devices-1): ONE process drives all of them — a worker thread,
+ * stream and workspace per device, the graph replicated at upload, the sources of every nec_vertex_load* call
+ * dealt to the devices in 64-source blocks, and the devices' partial load vectors combined with a single
+ * ncclAllReduce(sum, f64, n) over NVLink (ncclCommInitAll; libnccl.so.2 is resolved at run time, only here).
+ * nec_vertex_load on such a context is the reference's one call (graph_traits.rs:328-330) on all GPUs of the box;
+ * nec_vertex_load_batch shards by graph and nec_distance_measures by source (nothing to combine).  The
+ * one-process-per-GPU form (one single-device context per rank + the caller's own all-reduce on the buffer of
+ * nec_vertex_load_sources_device) stays available, see INTEGRATION.md. */
 int nec_init(nec_ctx **out, const int *devices, int n_devices);
 void nec_destroy(nec_ctx *ctx);
 

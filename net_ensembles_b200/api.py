@@ -22,13 +22,20 @@ def _ptr(a):
 
 
 class Context:
-    """One GPU, one stream, one workspace (nec_ctx).  Not thread-safe."""
+    """One GPU, one stream, one workspace (nec_ctx) — or, with `devices=[...]`, ONE context over several GPUs of
+    the box: every vertex_load call then uses all of them (sources dealt to the devices, one NCCL all-reduce
+    behind the C ABI).  Not thread-safe."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, devices=None):
         self._lib = _lib.load()
         h = c_vp()
-        dev = (c_int * 1)(device) if device is not None else None
-        rc = self._lib.nec_init(ctypes.byref(h), dev, 1)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            dev, count = (c_int * len(devices))(*devices), len(devices)
+        else:
+            dev, count = ((c_int * 1)(device) if device is not None else None), 1
+        self.n_devices = count
+        rc = self._lib.nec_init(ctypes.byref(h), dev, count)
         if rc != 0:
             raise NecError(rc, self._lib.nec_last_error(None).decode())
         self._h = h

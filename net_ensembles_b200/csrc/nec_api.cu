@@ -3,6 +3,8 @@
 // kernels of nec_kernels.cuh / nec_small.cuh; there is no host implementation of the
 // algorithm here and no fallback when CUDA is unavailable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -12,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/net_ensembles_cuda.h"
@@ -49,6 +52,7 @@ struct nec_graph {
     uint4 *d_slab = nullptr;         // n rows of slab_w u32 (mid engine), nullptr if n > kMidMaxN
     uint8_t *d_deg8 = nullptr;       // min(degree, 255) per vertex (mid engine)
     int slab_w = 0;
+    std::vector<nec_graph *> replicas;   // multi-device context: the same CSR on devices 1..
 };
 
 struct nec_ctx {
@@ -82,6 +86,10 @@ struct nec_ctx {
     int team_cap[2][9];                               // resident clusters per (batch width 32/64, team size); -1 = not asked yet
     nec::SmallWorkspace small;
     void *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of an upload's 32-bit CSR
+    // multi-device context (nec_init with n_devices > 1): this context works on devices[0]; `peers` are full
+    // single-device contexts for devices[1..], `comms[i]` the NCCL communicator of device i (0 = this one)
+    std::vector<nec_ctx *> peers;
+    std::vector<ncclComm_t> comms;
     nec_stats stats{};
 };
 
@@ -685,6 +693,111 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
     return NEC_OK;
 }
 
+// ---- NCCL, resolved at run time -------------------------------------------------------------------------------
+// Only a multi-device context needs it, and a host process may already carry its own copy (torch bundles one):
+// dlopen by soname picks up whatever libnccl.so.2 the process has loaded, else the system library.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { error = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        auto sym = [&](const char *n) { void *p = dlsym(handle, n); if (!p) error = std::string("libnccl lacks ") + n; return p; };
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+        if (!CommInitAll || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd || !GetErrorString) { handle = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+#define NEC_NCCL(ctx, call)                                                                            \
+    do {                                                                                               \
+        ncclResult_t r__ = (call);                                                                     \
+        if (r__ != ncclSuccess) return fail(ctx, NEC_ECUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+inline nec_ctx *device_ctx(nec_ctx *ctx, size_t d) { return d == 0 ? ctx : ctx->peers[d - 1]; }
+inline const nec_graph *device_graph(const nec_graph *g, size_t d) { return d == 0 ? g : g->replicas[d - 1]; }
+inline size_t n_devices_of(const nec_ctx *ctx) { return 1 + ctx->peers.size(); }
+
+// Runs f(device index) on one host thread per device of a multi-device context and returns the first failure,
+// its message copied into the primary context.
+template <class F>
+int on_all_devices(nec_ctx *ctx, F &&f) {
+    const size_t nd = n_devices_of(ctx);
+    std::vector<int> rcs(nd, NEC_OK);
+    std::vector<std::thread> workers;
+    workers.reserve(nd - 1);
+    for (size_t d = 1; d < nd; ++d) workers.emplace_back([&, d] { rcs[d] = f(d); });
+    rcs[0] = f(0);
+    for (auto &w : workers) w.join();
+    for (size_t d = 0; d < nd; ++d)
+        if (rcs[d] != NEC_OK) {
+            if (d) ctx->err = "device " + std::to_string(device_ctx(ctx, d)->device) + ": " + device_ctx(ctx, d)->err;
+            cudaSetDevice(ctx->device);
+            return rcs[d];
+        }
+    cudaSetDevice(ctx->device);
+    return NEC_OK;
+}
+
+// Sources of a call, dealt to the devices in blocks of 64 (one wide batch), block b to device b mod D: per-source
+// cost is about uniform inside a component, and neighbouring ids stay together (ring-like graphs).
+std::vector<std::vector<uint32_t>> deal_sources(const uint32_t *sources, uint32_t n_sources, size_t nd) {
+    std::vector<std::vector<uint32_t>> out(nd);
+    for (auto &v : out) v.reserve(n_sources / nd + 64);
+    for (uint32_t k = 0; k < n_sources; ++k) out[(k / 64) % nd].push_back(sources[k]);
+    return out;
+}
+
+// Partial loads of all devices of a multi-device context -> the full vector in every device's d_out:
+// ONE ncclAllReduce(sum, f64, n) over NVLink, issued for all devices from this thread inside a group.  Each
+// device's reduce_slots kernel wrote its partial straight into d_out (the NCCL buffer), in place.
+int all_reduce_loads(nec_ctx *ctx, uint32_t n) {
+    const size_t nd = n_devices_of(ctx);
+    NEC_NCCL(ctx, g_nccl.GroupStart());
+    for (size_t d = 0; d < nd; ++d) {
+        nec_ctx *c = device_ctx(ctx, d);
+        ncclResult_t r = g_nccl.AllReduce(c->d_out, c->d_out, n, ncclDouble, ncclSum, ctx->comms[d], c->stream);
+        if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(ctx, NEC_ECUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); }
+    }
+    NEC_NCCL(ctx, g_nccl.GroupEnd());
+    return NEC_OK;
+}
+
+void merge_device_stats(nec_ctx *ctx) {
+    nec_stats total = ctx->stats;
+    for (nec_ctx *pc : ctx->peers) {
+        const nec_stats &s = pc->stats;
+        total.n_sources += s.n_sources; total.n_batches += s.n_batches; total.reached_pairs += s.reached_pairs;
+        total.edge_pairs += s.edge_pairs; total.vertex_visits += s.vertex_visits;
+        total.max_depth = std::max(total.max_depth, s.max_depth);
+        total.kernel_launches += s.kernel_launches; total.wide_batches += s.wide_batches; total.requeued_batches += s.requeued_batches;
+        total.n_slots += s.n_slots;
+        total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms); total.engine_ms = std::max(total.engine_ms, s.engine_ms);
+        total.workspace_bytes += s.workspace_bytes;
+        total.pull_levels += s.pull_levels; total.push_levels += s.push_levels;
+    }
+    ctx->stats = total;
+}
+
+int init_single(nec_ctx **out, int dev);
+
 }  // namespace
 
 extern "C" {
@@ -699,16 +812,52 @@ void nec_internal_set_error(nec_ctx *ctx, const char *msg) { if (ctx) ctx->err =
 int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     if (!out) return fail(nullptr, NEC_EINVAL, "nec_init: out is NULL");
     *out = nullptr;
-    if (n_devices != 1) return fail(nullptr, NEC_EINVAL, "nec_init: n_devices must be 1 (one context per GPU; got %d)", n_devices);
+    if (n_devices < 1 || n_devices > 64) return fail(nullptr, NEC_EINVAL, "nec_init: n_devices must be 1..64 (got %d)", n_devices);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(nullptr, NEC_ENODEVICE, "no CUDA device available (%s); net_ensembles_cuda has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    int dev = 0;
-    if (devices) dev = devices[0];
-    else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    if (dev < 0 || dev >= count) return fail(nullptr, NEC_EINVAL, "nec_init: device %d out of range (have %d)", dev, count);
+    std::vector<int> devs(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        if (devices) devs[i] = devices[i];
+        else if (n_devices > 1) devs[i] = i;
+        else if (cudaGetDevice(&devs[i]) != cudaSuccess) devs[i] = 0;
+        if (devs[i] < 0 || devs[i] >= count) return fail(nullptr, NEC_EINVAL, "nec_init: device %d out of range (have %d)", devs[i], count);
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(nullptr, NEC_EINVAL, "nec_init: device %d listed twice", devs[i]);
+    }
+    nec_ctx *ctx = nullptr;
+    int rc = init_single(&ctx, devs[0]);
+    if (rc != NEC_OK) return rc;
+    if (n_devices > 1) {
+        // one full single-device context per further GPU, and one NCCL communicator per device (single process:
+        // ncclCommInitAll), for the one all-reduce that combines the devices' partial load vectors
+        if (!g_nccl.load()) { rc = fail(nullptr, NEC_ECUDA, "nec_init: %s", g_nccl.error.c_str()); nec_destroy(ctx); return rc; }
+        for (int i = 1; i < n_devices; ++i) {
+            nec_ctx *pc = nullptr;
+            if ((rc = init_single(&pc, devs[i])) != NEC_OK) { nec_destroy(ctx); return rc; }
+            ctx->peers.push_back(pc);
+        }
+        ctx->comms.assign(n_devices, nullptr);
+        ncclResult_t r = g_nccl.CommInitAll(ctx->comms.data(), n_devices, devs.data());
+        if (r != ncclSuccess) {
+            rc = fail(nullptr, NEC_ECUDA, "nec_init: ncclCommInitAll over %d devices failed: %s", n_devices, g_nccl.GetErrorString(r));
+            ctx->comms.clear();
+            nec_destroy(ctx);
+            return rc;
+        }
+        cudaSetDevice(devs[0]);
+    }
+    *out = ctx;
+    return NEC_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int init_single(nec_ctx **out, int dev) {
+    cudaError_t e;
     nec_ctx *ctx = new (std::nothrow) nec_ctx();
     if (!ctx) return fail(nullptr, NEC_ENOMEM, "nec_init: out of host memory");
     ctx->device = dev;
@@ -745,9 +894,17 @@ int nec_init(nec_ctx **out, const int *devices, int n_devices) {
     *out = ctx;
     return NEC_OK;
 }
+}  // namespace
+
+extern "C" {
 
 void nec_destroy(nec_ctx *ctx) {
     if (!ctx) return;
+    for (ncclComm_t c : ctx->comms)
+        if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    ctx->comms.clear();
+    for (nec_ctx *pc : ctx->peers) nec_destroy(pc);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->d_sources) cudaFree(ctx->d_sources);
@@ -771,6 +928,7 @@ void nec_destroy(nec_ctx *ctx) {
 
 int nec_set_stream(nec_ctx *ctx, void *cuda_stream) {
     if (!ctx) return NEC_EINVAL;
+    if (cuda_stream && !ctx->peers.empty()) return fail(ctx, NEC_EINVAL, "nec_set_stream: a multi-device context works on its own streams (one per device)");
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return NEC_OK;
 }
@@ -778,20 +936,40 @@ int nec_set_stream(nec_ctx *ctx, void *cuda_stream) {
 int nec_set_engine(nec_ctx *ctx, int engine) {
     if (!ctx || engine < 0 || engine > 2) return NEC_EINVAL;
     ctx->force_engine = engine;
+    for (nec_ctx *pc : ctx->peers) pc->force_engine = engine;
     return NEC_OK;
 }
 
 int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes) {
     if (!ctx) return NEC_EINVAL;
     ctx->ws_limit = bytes;
+    for (nec_ctx *pc : ctx->peers) pc->ws_limit = bytes;
     return NEC_OK;
 }
 
 // Shared tail of the two upload entry points: the 32-bit CSR sits validated in the context's pinned staging
 // area (row pointers, then neighbour ids); allocate the device graph, copy, and build the mid engine's slab
 // rows and degree bytes ON THE DEVICE from the CSR that has just arrived.
+static int finish_upload_one(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint32_t *h_rp32, const uint32_t *h_col,
+                             uint32_t max_deg, size_t over8, nec_graph **out);
+
+// ... on every device of the context (each copies from the same pinned staging area over its own link)
 static int finish_upload(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint32_t *h_rp32, const uint32_t *h_col,
                          uint32_t max_deg, size_t over8, nec_graph **out) {
+    if (ctx->peers.empty()) return finish_upload_one(ctx, n, nnz, h_rp32, h_col, max_deg, over8, out);
+    std::vector<nec_graph *> made(n_devices_of(ctx), nullptr);
+    int rc = on_all_devices(ctx, [&](size_t d) { return finish_upload_one(device_ctx(ctx, d), n, nnz, h_rp32, h_col, max_deg, over8, &made[d]); });
+    if (rc != NEC_OK) {
+        for (size_t d = 0; d < made.size(); ++d) nec_graph_free(device_ctx(ctx, d), made[d]);
+        return rc;
+    }
+    made[0]->replicas.assign(made.begin() + 1, made.end());
+    *out = made[0];
+    return NEC_OK;
+}
+
+static int finish_upload_one(nec_ctx *ctx, uint32_t n, uint64_t nnz, const uint32_t *h_rp32, const uint32_t *h_col,
+                             uint32_t max_deg, size_t over8, nec_graph **out) {
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     nec_graph *g = new (std::nothrow) nec_graph();
     if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
@@ -831,7 +1009,7 @@ static int stage_reserve(nec_ctx *ctx, uint32_t n, uint64_t nnz, uint32_t *&h_rp
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
         const size_t cap = need + need / 8;
-        cudaError_t e = cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocPortable);   // every device of a multi-device context copies from it
         if (e != cudaSuccess) return fail(ctx, NEC_ENOMEM, "cudaHostAlloc(%zu B CSR staging) failed: %s", cap, cudaGetErrorString(e));
         ctx->h_stage_cap = cap;
     }
@@ -933,6 +1111,9 @@ int nec_graph_upload_adjacency(nec_ctx *ctx, uint32_t n, const void *const *rows
 
 void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
     if (!g) return;
+    for (size_t i = 0; i < g->replicas.size(); ++i)
+        nec_graph_free(ctx && i < ctx->peers.size() ? ctx->peers[i] : nullptr, g->replicas[i]);
+    g->replicas.clear();
     if (ctx) {
         cudaSetDevice(ctx->device);
         if (g->d_row_ptr) cudaFreeAsync(g->d_row_ptr, ctx->stream);
@@ -943,11 +1124,48 @@ void nec_graph_free(nec_ctx *ctx, nec_graph *g) {
     delete g;
 }
 
+// Multi-device call: the sources are dealt to the devices, every device runs its share on its own host thread,
+// stream and arena into its d_out, one all-reduce combines them; afterwards every device's d_out holds the result.
+static int run_sources_all_devices(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources, int include_endpoints) {
+    const size_t nd = n_devices_of(ctx);
+    if (g->replicas.size() + 1 != nd) return fail(ctx, NEC_EINVAL, "graph was not uploaded through this multi-device context");
+    for (uint32_t k = 0; k < n_sources; ++k)
+        if (sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", sources[k], k, g->n);
+    const auto share = deal_sources(sources, n_sources, nd);
+    int rc = on_all_devices(ctx, [&](size_t d) {
+        nec_ctx *c = device_ctx(ctx, d);
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, NEC_ECUDA, "cudaSetDevice(%d) failed", c->device);
+        int r = grow(c, c->d_out, c->d_out_cap, g->n);
+        if (r != NEC_OK) return r;
+        return run_sources(c, device_graph(g, d), share[d].data(), (uint32_t)share[d].size(), include_endpoints, c->d_out, false, nullptr, nullptr);
+    });
+    if (rc != NEC_OK) return rc;
+    merge_device_stats(ctx);
+    if ((rc = all_reduce_loads(ctx, g->n)) != NEC_OK) return rc;
+    ctx->stats.kernel_launches += (uint32_t)nd;      // the collective's kernels, one per device
+    return NEC_OK;
+}
+
+static int sync_all_devices(nec_ctx *ctx) {
+    for (size_t d = n_devices_of(ctx); d-- > 0;) {
+        nec_ctx *c = device_ctx(ctx, d);
+        NEC_CUDA(ctx, cudaSetDevice(c->device));
+        NEC_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    }
+    return NEC_OK;
+}
+
 int nec_vertex_load_sources_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
                                    int include_endpoints, double *d_out) try {
     if (!ctx) return NEC_EINVAL;
     if (!g || (g->n && !d_out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources_device: NULL argument");
-    return run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, d_out, false, nullptr, nullptr);
+    if (ctx->peers.empty()) return run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, d_out, false, nullptr, nullptr);
+    if (g->n == 0) { ctx->stats = nec_stats{}; return NEC_OK; }
+    int rc = run_sources_all_devices(ctx, g, sources, n_sources, include_endpoints ? 1 : 0);
+    if (rc != NEC_OK) return rc;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));        // d_out lives on the context's first device
+    NEC_CUDA(ctx, cudaMemcpyAsync(d_out, ctx->d_out, (size_t)g->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return sync_all_devices(ctx);
 } NEC_CATCH_ALL(ctx)
 
 int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
@@ -955,6 +1173,13 @@ int nec_vertex_load_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *so
     if (!ctx) return NEC_EINVAL;
     if (!g || (g->n && !out) || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_vertex_load_sources: NULL argument");
     if (g->n == 0) { ctx->stats = nec_stats{}; return NEC_OK; }
+    if (!ctx->peers.empty()) {
+        int rc = run_sources_all_devices(ctx, g, sources, n_sources, include_endpoints ? 1 : 0);
+        if (rc != NEC_OK) return rc;
+        NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+        NEC_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, (size_t)g->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));   // D2H once
+        return sync_all_devices(ctx);
+    }
     int rc = grow(ctx, ctx->d_out, ctx->d_out_cap, g->n);
     if (rc != NEC_OK) return rc;
     rc = run_sources(ctx, g, sources, n_sources, include_endpoints ? 1 : 0, ctx->d_out, false, nullptr, nullptr);
@@ -1022,6 +1247,21 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     if (!g || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_distance_measures: NULL argument");
     ctx->stats = nec_stats{};
     if (n_sources == 0 || g->n == 0) return NEC_OK;
+    if (!ctx->peers.empty()) {
+        // per-source outputs: contiguous shares of the source list, one per device, nothing to combine
+        const size_t nd = n_devices_of(ctx);
+        if (g->replicas.size() + 1 != nd) return fail(ctx, NEC_EINVAL, "graph was not uploaded through this multi-device context");
+        int rcm = on_all_devices(ctx, [&](size_t d) {
+            const uint32_t k0 = (uint32_t)((uint64_t)n_sources * d / nd), k1 = (uint32_t)((uint64_t)n_sources * (d + 1) / nd);
+            nec_ctx *c = device_ctx(ctx, d);
+            nec_graph shallow = *device_graph(g, d);          // a single-device view of this device's replica
+            shallow.replicas.clear();
+            return nec_distance_measures(c, &shallow, sources + k0, k1 - k0, ecc ? ecc + k0 : nullptr,
+                                         sum_dist ? sum_dist + k0 : nullptr, reached ? reached + k0 : nullptr);
+        });
+        if (rcm == NEC_OK) merge_device_stats(ctx);
+        return rcm;
+    }
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = grow(ctx, ctx->d_mecc, ctx->d_mecc_cap, n_sources)) != NEC_OK) return rc;
@@ -1073,6 +1313,22 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
     if (n_graphs && (!n_per_graph || !row_ptr_offsets || !row_ptr_concat || !col_offsets || !out_concat))
         return fail(ctx, NEC_EINVAL, "nec_vertex_load_batch: NULL argument");
     ctx->stats = nec_stats{};
+    if (!ctx->peers.empty() && n_graphs >= 2 * n_devices_of(ctx)) {
+        // the batch shards by graph (contiguous ranges, no collective: the load vectors are just concatenated)
+        const size_t nd = n_devices_of(ctx);
+        std::vector<uint64_t> out_off(n_graphs + 1, 0);
+        for (uint32_t i = 0; i < n_graphs; ++i) out_off[i + 1] = out_off[i] + n_per_graph[i];
+        int rcm = on_all_devices(ctx, [&](size_t d) {
+            const uint32_t g0 = (uint32_t)((uint64_t)n_graphs * d / nd), g1 = (uint32_t)((uint64_t)n_graphs * (d + 1) / nd);
+            nec_ctx *c = device_ctx(ctx, d);
+            c->stats = nec_stats{};
+            if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, NEC_ECUDA, "cudaSetDevice(%d) failed", c->device);
+            return nec::small_batch_run(c->small, c->stream, &c->err, &c->stats, g1 - g0, n_per_graph + g0, row_ptr_offsets + g0, row_ptr_concat,
+                                        col_offsets + g0, col_idx_concat, include_endpoints ? 1 : 0, out_concat + out_off[g0]);
+        });
+        if (rcm == NEC_OK) merge_device_stats(ctx);
+        return rcm;
+    }
     cudaSetDevice(ctx->device);
     return nec::small_batch_run(ctx->small, ctx->stream, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
                                 row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
@@ -1084,17 +1340,17 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     *sources_per_wave = 0;
     if (g->n == 0 || n_sources_total == 0) return NEC_OK;
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint32_t ns = (uint32_t)std::min<uint64_t>(n_sources_total, 0xFFFFFFFFull);
+    const uint32_t ns = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, n_sources_total / n_devices_of(ctx)), 0xFFFFFFFFull);   // per device
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
                         ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
     if (mid_ok) {       // one source per CTA, two CTAs per SM
-        *sources_per_wave = std::min<uint32_t>(ns, 2u * (uint32_t)ctx->prop.multiProcessorCount);
+        *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, std::min<uint64_t>(ns, 2ull * (uint32_t)ctx->prop.multiProcessorCount) * n_devices_of(ctx));
         return NEC_OK;
     }
     BatchedPlan plan{};
     const int rc = plan_batched(ctx, g->n, ns, false, false, plan);
     if (rc != NEC_OK) return rc;
-    *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, (uint64_t)plan.slots * plan.ksrc);
+    *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, (uint64_t)plan.slots * plan.ksrc * n_devices_of(ctx));
     return NEC_OK;
 } NEC_CATCH_ALL(ctx)
 
