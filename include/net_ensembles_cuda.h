@@ -137,6 +137,34 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
                           const uint64_t *col_offsets, const uint32_t *col_idx_concat,
                           int include_endpoints, double *out_concat);
 
+/* Device-resident Markov chains (one CTA per graph, as above, but the graphs STAY on the device between
+ * measurements).  A chain's step changes one or two edges (er_c.rs:154-174, er_m.rs:223-236, sw.rs:299-309), so
+ * instead of re-exporting every CSR the host ships the LIST OPERATIONS it performed on its adjacency lists and the
+ * device replays them in order — adjacency order (which defines the rounding of the load) stays identical:
+ *     op = kind << 60 | v << 40 | x << 20 | y      (local vertex ids < 2^20)
+ *     kind 1  push x onto v's list                         NodeContainer::push graph.rs:101-110, SwContainer::push sw_graph.rs:259-279
+ *     kind 2  swap_remove the entry x from v's list        graph.rs:134-142 (Vec::swap_remove), sw_graph.rs:350-442
+ *     kind 3  retarget the entry x of v's list to y        rewire / reset of a small-world root edge, sw_graph.rs:350-442
+ * add_edge(a,b) = push(a,b), push(b,a); remove_edge(a,b) = swap_remove(a,b), swap_remove(b,a).
+ * nec_chains_create uploads the initial graphs (same batch format as nec_vertex_load_batch; `slack` = spare
+ * entries per adjacency row beyond the largest degree).  nec_chains_step_and_load applies graph g's operations
+ * ops[op_offsets[g] .. op_offsets[g+1]) (op_offsets == NULL: measure without stepping), then runs
+ * vertex_load(include_endpoints) on every graph; the load vectors arrive back to back in out_concat, or - with
+ * out_concat == NULL - stay in the set's pinned host buffer, readable through nec_chains_result until the next
+ * call.  A list that outgrows its row is reported (NEC_EINTERNAL): re-create the set with more slack.
+ * nec_chains_download returns the device adjacency as a compact CSR batch (graph g's n_g + 1 local row pointers
+ * start at sum_{h<g} (n_h + 1)) for checking it against the host's lists. */
+typedef struct nec_chains nec_chains;
+int nec_chains_create(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,
+                      const uint32_t *row_ptr_concat, const uint64_t *col_offsets, const uint32_t *col_idx_concat,
+                      uint32_t slack, nec_chains **out);
+int nec_chains_step_and_load(nec_ctx *ctx, nec_chains *chains, const uint32_t *op_offsets, const uint64_t *ops,
+                             int include_endpoints, double *out_concat);
+const double *nec_chains_result(const nec_chains *chains);
+int nec_chains_download(nec_ctx *ctx, nec_chains *chains, uint32_t *row_ptr_concat, uint32_t *col_idx_concat,
+                        uint64_t col_capacity, uint64_t *nnz);
+void nec_chains_free(nec_ctx *ctx, nec_chains *chains);
+
 /* Distance measures over the listed sources — the all-source BFS measures of the crate that sit
  * next to vertex_load in its benches (benches/common/mod.rs:53-64): for source sources[i]
  *   ecc[i]      = depth of the BFS from it   (longest_shortest_path_from_index, generic_graph.rs:1140-1144)

@@ -41,6 +41,11 @@ NEC_SYMBOLS = {
     "nec_vertex_load_sources": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, c_vp]),
     "nec_vertex_load_sources_device": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, c_vp]),
     "nec_vertex_load_batch": (c_int, [c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "nec_chains_create": (c_int, [c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, ctypes.POINTER(c_vp)]),
+    "nec_chains_step_and_load": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "nec_chains_result": (c_vp, [c_vp]),
+    "nec_chains_download": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_vp]),
+    "nec_chains_free": (None, [c_vp, c_vp]),
     "nec_distance_measures": (c_int, [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp]),
     "nec_bfs_debug": (c_int, [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]),
     "nec_wave_size": (c_int, [c_vp, c_vp, c_u64, c_vp]),
@@ -74,6 +79,12 @@ BRIDGE_SYMBOLS = {
     "nech_vertex_load_cuda": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nech_chains_step_and_load_cuda": (c_int, [c_vp, c_u32, c_u64, c_vp, c_int, c_vp]),
     "nech_last_chain_stats": (None, [ctypes.POINTER(NecStats)]),
+    "nech_chain_batch_new": (c_vp, [c_vp, c_u32, c_vp]),
+    "nech_chain_batch_free": (None, [c_vp]),
+    "nech_chain_batch_step": (c_int, [c_vp, c_u64, c_int, c_vp]),
+    "nech_chain_batch_result": (c_vp, [c_vp]),
+    "nech_chain_batch_stats": (None, [c_vp, ctypes.POINTER(NecStats), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
+    "nech_chain_batch_download": (c_int, [c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]),
 }
 
 _lib = None

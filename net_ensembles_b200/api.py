@@ -190,19 +190,40 @@ def vertex_load_batch(ctx, graphs, include_endpoints):
 
 
 class ChainBatch:
-    """A fixed set of Markov chains measured together (benches/common/mod.rs:79-90 run on many chains):
-    holds the handle table, the result buffer and the vertex counts so that a measurement step costs one
-    C call — `m_steps` Markov steps on every chain (all host cores), CSR export, and vertex_load of all the
-    graphs through the one-CTA-per-graph kernel, pipelined with the copies."""
+    """A fixed set of Markov chains measured together (benches/common/mod.rs:79-90 run on many chains).
 
-    def __init__(self, chains):
+    device_resident=True (default): the chains' adjacency lists are uploaded ONCE into slack-padded device rows;
+    a measurement step runs `m_steps` Markov steps on every host chain (all host cores), ships only the list
+    operations they performed (a few bytes per chain) and replays them on the device copy, so adjacency order -
+    hence every rounding - stays identical to the host's; then vertex_load of all graphs, one CTA per graph.
+    device_resident=False: every step re-exports all CSRs and uploads them again (nec_vertex_load_batch)."""
+
+    def __init__(self, chains, device_resident=True):
         self.chains = list(chains)
         self._handles = (c_vp * len(self.chains))(*[c._h for c in self.chains])
         self._ns = np.array([c.vertex_count() for c in self.chains], dtype=np.int64)
         self._out = np.empty(int(self._ns.sum()), dtype=np.float64)
         self._uniform = len(self.chains) > 0 and bool((self._ns == self._ns[0]).all())
         self._cuts = np.cumsum(self._ns)[:-1]
+        self.device_resident = bool(device_resident) and len(self.chains) > 0 and int(self._ns.max(initial=0)) <= _lib.NEC_BATCH_MAX_N
+        self.mode = ("device-resident adjacency rows; a step ships the chains' list operations" if self.device_resident
+                     else "CSR re-exported and re-uploaded every step")
+        self._dev, self._dev_ctx = None, None
+        self.h2d_bytes_last_step = None
+        self.uploads = 0
         self.stats = None
+
+    def _shape(self, flat):
+        if self._uniform:
+            return flat.reshape(len(self.chains), int(self._ns[0]))
+        return np.split(flat, self._cuts)
+
+    def close(self):
+        if self._dev is not None and getattr(self._dev_ctx, "_h", None):
+            self._dev_ctx._lib.nech_chain_batch_free(self._dev)
+        self._dev = None
+
+    __del__ = close
 
     def step_and_load(self, ctx, m_steps, include_endpoints):
         """Returns the load vectors: a (chains, n) array when all graphs have the same size, else a list of
@@ -210,14 +231,42 @@ class ChainBatch:
         lib = ctx._lib
         if not self.chains:
             return []
-        ctx._check(lib.nech_chains_step_and_load_cuda(self._handles, len(self.chains), int(m_steps), ctx._h,
-                                                      int(bool(include_endpoints)), _ptr(self._out)))
-        st = _lib.NecStats()
-        lib.nech_last_chain_stats(ctypes.byref(st))
-        self.stats = st.as_dict()          # counters of this step
-        if self._uniform:
-            return self._out.reshape(len(self.chains), int(self._ns[0]))
-        return np.split(self._out, self._cuts)
+        if not self.device_resident:
+            ctx._check(lib.nech_chains_step_and_load_cuda(self._handles, len(self.chains), int(m_steps), ctx._h,
+                                                          int(bool(include_endpoints)), _ptr(self._out)))
+            st = _lib.NecStats()
+            lib.nech_last_chain_stats(ctypes.byref(st))
+            self.stats = st.as_dict()          # counters of this step
+            return self._shape(self._out)
+        if self._dev is None or self._dev_ctx is not ctx:
+            self.close()
+            h = lib.nech_chain_batch_new(self._handles, len(self.chains), ctx._h)
+            if not h:
+                raise NecError(-1, lib.nec_last_error(ctx._h).decode())
+            self._dev, self._dev_ctx = c_vp(h), ctx
+        ctx._check(lib.nech_chain_batch_step(self._dev, int(m_steps), int(bool(include_endpoints)), None))
+        st, h2d, ups = _lib.NecStats(), c_u64(0), c_u64(0)
+        lib.nech_chain_batch_stats(self._dev, ctypes.byref(st), ctypes.byref(h2d), ctypes.byref(ups))
+        self.stats, self.h2d_bytes_last_step, self.uploads = st.as_dict(), int(h2d.value), int(ups.value)
+        ptr = lib.nech_chain_batch_result(self._dev)         # the library's pinned result buffer: no extra copy
+        flat = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(int(self._ns.sum()),))
+        return self._shape(flat)
+
+    def device_adjacency(self):
+        """The device copy's adjacency lists, graph by graph (order included) - for checking them against the hosts'."""
+        if self._dev is None:
+            raise ValueError("no device copy yet: call step_and_load first")
+        total_rp = int((self._ns + 1).sum())
+        cap = int(sum(2 * c.edge_count() for c in self.chains)) + 16
+        rp, col, nnz = np.zeros(total_rp, np.uint32), np.zeros(cap, np.uint32), c_u64(0)
+        self._dev_ctx._check(self._dev_ctx._lib.nech_chain_batch_download(self._dev, _ptr(rp), _ptr(col), cap, ctypes.byref(nnz)))
+        out, at_rp, at_col = [], 0, 0
+        for n in self._ns:
+            r = rp[at_rp:at_rp + int(n) + 1]
+            out.append([col[at_col + int(r[v]):at_col + int(r[v + 1])].tolist() for v in range(int(n))])
+            at_rp += int(n) + 1
+            at_col += int(r[int(n)])
+        return out
 
 
 def chains_step_and_load(ctx, chains, m_steps, include_endpoints):

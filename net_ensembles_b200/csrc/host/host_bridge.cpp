@@ -169,3 +169,139 @@ int nech_chains_step_and_load_cuda(void *const *handles, uint32_t n_chains, uint
 void nech_last_chain_stats(nec_stats *out) { *out = g_chain_stats; }
 
 }  // extern "C"
+
+// ---- device-resident chains: the graphs stay on the GPU, a step ships list operations ----------------------------
+namespace {
+struct DeviceChainBatch {
+    nec_ctx *ctx = nullptr;
+    std::vector<Handle *> handles;
+    std::vector<std::vector<uint64_t>> logs;         // per chain: the list operations of the current step
+    std::vector<uint64_t> seen_mutations, seen_wholesale;
+    std::vector<uint32_t> op_off;
+    std::vector<uint64_t> ops;
+    nec_chains *dev = nullptr;
+    uint32_t slack = 8;
+    uint64_t h2d_last = 0, uploads = 0;
+    nec_stats stats{};
+};
+
+template <class F>
+auto with_graph_mut(Handle *h, F &&f) {
+    if (h->kind == Kind::Sw) return f(h->sw->graph);
+    return f(*const_cast<Graph *>(h->plain_graph()));
+}
+
+// (re-)create the device copy from the chains' current adjacency lists
+int upload_chains(DeviceChainBatch &b) {
+    if (b.dev) { nec_chains_free(b.ctx, b.dev); b.dev = nullptr; }
+    ChainGroup &grp = g_group;
+    prepare_group(grp, reinterpret_cast<void *const *>(b.handles.data()), 0, (uint32_t)b.handles.size(), 0);
+    if (grp.bad) { nec_internal_set_error(b.ctx, "adjacency lists disagree with edge_count"); return NEC_EINVAL; }
+    int rc = nec_chains_create(b.ctx, (uint32_t)b.handles.size(), grp.n_per.data(), grp.rp_off.data(), grp.rp.data(), grp.col_off.data(),
+                               grp.col.data(), b.slack, &b.dev);
+    if (rc != NEC_OK) return rc;
+    for (size_t g = 0; g < b.handles.size(); ++g)
+        with_graph_mut(b.handles[g], [&](auto &gr) { b.seen_mutations[g] = gr.mutations; b.seen_wholesale[g] = gr.wholesale_changes; return 0; });
+    b.uploads++;
+    b.h2d_last = (uint64_t)b.handles.size() * 20 + (grp.rp_off.empty() ? 0 : (grp.rp_off.back() + grp.n_per.back() + 1) * 4) + grp.col.size() * 4;
+    return NEC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+void *nech_chain_batch_new(void *const *handles, uint32_t n_chains, nec_ctx *ctx) {
+    if (!ctx || !handles || !n_chains) return nullptr;
+    DeviceChainBatch *b = nullptr;
+    int rc = guarded(ctx, [&]() -> int {
+        b = new DeviceChainBatch();
+        b->ctx = ctx;
+        b->handles.resize(n_chains);
+        for (uint32_t g = 0; g < n_chains; ++g) b->handles[g] = static_cast<Handle *>(handles[g]);
+        b->logs.resize(n_chains); b->seen_mutations.assign(n_chains, 0); b->seen_wholesale.assign(n_chains, 0);
+        b->op_off.assign((size_t)n_chains + 1, 0);
+        return upload_chains(*b); });
+    if (rc != NEC_OK) { if (b) { if (b->dev) nec_chains_free(ctx, b->dev); delete b; } return nullptr; }
+    return b;
+}
+
+void nech_chain_batch_free(void *batch) {
+    DeviceChainBatch *b = static_cast<DeviceChainBatch *>(batch);
+    if (!b) return;
+    if (b->dev) nec_chains_free(b->ctx, b->dev);
+    delete b;
+}
+
+// `m_steps` Markov steps on every chain (all host cores; the chains' own generators), the resulting list
+// operations shipped to the device copy and replayed there, then vertex_load(include_endpoints) of all graphs.
+// out == NULL: the loads stay in the pinned buffer nech_chain_batch_result returns.
+int nech_chain_batch_step(void *batch, uint64_t m_steps, int include_endpoints, double *out) {
+    DeviceChainBatch *b = static_cast<DeviceChainBatch *>(batch);
+    if (!b) return NEC_EINVAL;
+    return guarded(b->ctx, [&]() -> int {
+        const size_t n = b->handles.size();
+        int bad = 0, stale = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad, stale)
+        for (int64_t g = 0; g < (int64_t)n; ++g) {
+            Handle *h = b->handles[g];
+            std::vector<uint64_t> &log = b->logs[g];
+            log.clear();
+            with_graph_mut(h, [&](auto &gr) {
+                if (gr.mutations != b->seen_mutations[g] || gr.wholesale_changes != b->seen_wholesale[g]) stale += 1;   // stepped behind our back
+                gr.oplog = &log;
+                return 0;
+            });
+            for (uint64_t k = 0; k < m_steps; ++k)
+                if (!h->m_step()) { bad += 1; break; }
+            with_graph_mut(h, [&](auto &gr) {
+                gr.oplog = nullptr;
+                if (gr.wholesale_changes != b->seen_wholesale[g]) stale += 1;
+                b->seen_mutations[g] = gr.mutations;
+                return 0;
+            });
+        }
+        if (bad) { nec_internal_set_error(b->ctx, "chain has no Markov step"); return NEC_EINVAL; }
+        int rc;
+        if (stale) {
+            // some chain changed in a way the log does not cover (randomize, steps outside this batch): start over
+            if ((rc = upload_chains(*b)) != NEC_OK) return rc;
+            rc = nec_chains_step_and_load(b->ctx, b->dev, nullptr, nullptr, include_endpoints, out);
+        } else {
+            uint64_t total = 0;
+            for (size_t g = 0; g < n; ++g) { b->op_off[g] = (uint32_t)total; total += b->logs[g].size(); }
+            b->op_off[n] = (uint32_t)total;
+            b->ops.resize(total);
+#pragma omp parallel for schedule(static)
+            for (int64_t g = 0; g < (int64_t)n; ++g)
+                if (!b->logs[g].empty()) std::memcpy(b->ops.data() + b->op_off[g], b->logs[g].data(), b->logs[g].size() * 8);
+            b->h2d_last = total * 8 + (total ? (n + 1) * 4 : 0);
+            rc = nec_chains_step_and_load(b->ctx, b->dev, total ? b->op_off.data() : nullptr, b->ops.data(), include_endpoints, out);
+            if (rc == NEC_EINTERNAL) {
+                // an adjacency list outgrew its row: rebuild the device copy from the (already stepped) host lists
+                b->slack *= 2;
+                if ((rc = upload_chains(*b)) != NEC_OK) return rc;
+                rc = nec_chains_step_and_load(b->ctx, b->dev, nullptr, nullptr, include_endpoints, out);
+            }
+        }
+        if (rc == NEC_OK) nec_get_stats(b->ctx, &b->stats);
+        return rc; });
+}
+
+const double *nech_chain_batch_result(const void *batch) {
+    const DeviceChainBatch *b = static_cast<const DeviceChainBatch *>(batch);
+    return b && b->dev ? nec_chains_result(b->dev) : nullptr;
+}
+void nech_chain_batch_stats(const void *batch, nec_stats *out, uint64_t *h2d_bytes_last_step, uint64_t *uploads) {
+    const DeviceChainBatch *b = static_cast<const DeviceChainBatch *>(batch);
+    if (out) *out = b->stats;
+    if (h2d_bytes_last_step) *h2d_bytes_last_step = b->h2d_last;
+    if (uploads) *uploads = b->uploads;
+}
+// the device copy's adjacency as a compact CSR batch (see nec_chains_download)
+int nech_chain_batch_download(void *batch, uint32_t *row_ptr_concat, uint32_t *col_idx_concat, uint64_t col_capacity, uint64_t *nnz) {
+    DeviceChainBatch *b = static_cast<DeviceChainBatch *>(batch);
+    if (!b || !b->dev) return NEC_EINVAL;
+    return nec_chains_download(b->ctx, b->dev, row_ptr_concat, col_idx_concat, col_capacity, nnz);
+}
+
+}  // extern "C"

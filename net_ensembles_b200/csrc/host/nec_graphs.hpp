@@ -26,6 +26,17 @@ namespace nec_host {
 
 constexpr uint32_t NO_ROOT = 0xFFFFFFFFu;
 
+// Adjacency mutations as a replayable log (device-resident Markov chains: the GPU copy of a chain's adjacency
+// lists is patched with exactly the list operations the host performed, so ORDER stays identical).  Three
+// primitives express every edge move of the crate: push x onto v's list (graph.rs:101-110, sw_graph.rs:259-279),
+// swap_remove the entry x from v's list (graph.rs:134-142, sw_graph.rs:350-442) and retarget the entry x of v's
+// list to y in place (rewire / reset of a small-world root edge).  One op = kind << 60 | v << 40 | x << 20 | y.
+enum : uint64_t { OP_PUSH = 1, OP_SWAP_REMOVE = 2, OP_RETARGET = 3 };
+constexpr uint32_t OP_MAX_VERTEX = (1u << 20) - 1;
+inline uint64_t make_op(uint64_t kind, uint32_t v, uint32_t x, uint32_t y = 0) {
+    return (kind << 60) | ((uint64_t)v << 40) | ((uint64_t)x << 20) | (uint64_t)y;
+}
+
 // ---- adjacency containers -------------------------------------------------------
 
 struct PlainEdge {          // NodeContainer stores bare neighbour ids
@@ -64,14 +75,22 @@ class GenericGraph {
 public:
     std::vector<Container<E>> vertices;
     uint64_t edge_count = 0;
+    std::vector<uint64_t> *oplog = nullptr;   // when set, every list mutation is appended (see make_op)
+    uint64_t wholesale_changes = 0;           // bumped by mutations the log cannot express (clear, bulk rebuild)
 
     explicit GenericGraph(size_t n = 0) : vertices(n) {}
+    uint64_t mutations = 0;                   // every list operation, logged or not (detects steps taken behind a log's back)
+    void log(uint64_t kind, uint32_t v, uint32_t x, uint32_t y = 0) {
+        ++mutations;
+        if (oplog) oplog->push_back(make_op(kind, v, x, y));
+    }
     size_t vertex_count() const { return vertices.size(); }
     size_t degree(size_t i) const { return vertices[i].adj.size(); }
 
     void clear_edges() {
         for (auto &c : vertices) c.adj.clear();
         edge_count = 0;
+        ++wholesale_changes;
     }
 
     // false <=> GraphErrors::EdgeExists.  The edge is rooted at a (matters for SwEdge).
@@ -81,6 +100,7 @@ public:
         vertices[a].adj.push_back(make_root_entry((E *)nullptr, b));
         vertices[b].adj.push_back(make_loose_entry((E *)nullptr, a));
         ++edge_count;
+        log(OP_PUSH, a, b); log(OP_PUSH, b, a);
         return true;
     }
     // false <=> GraphErrors::EdgeDoesNotExist.  swap_remove on both lists: order changes.
@@ -91,6 +111,7 @@ public:
         vertices[a].swap_remove_at((size_t)pa);
         vertices[b].swap_remove_at((size_t)vertices[b].position_of(a));
         --edge_count;
+        log(OP_SWAP_REMOVE, a, b); log(OP_SWAP_REMOVE, b, a);
         return true;
     }
 
@@ -157,6 +178,7 @@ inline SwChange sw_rewire_edge(SwGraph &g, uint32_t i0, uint32_t i1, uint32_t i2
     c1.swap_remove_at((size_t)c1.position_of(i0));
     c0.adj[(size_t)p].to = i2;
     g.vertices[i2].adj.push_back(SwEdge{i0, NO_ROOT});
+    g.log(OP_SWAP_REMOVE, i1, i0); g.log(OP_RETARGET, i0, i1, i2); g.log(OP_PUSH, i2, i0);
     return SwChange::Rewire;
 }
 
@@ -175,6 +197,7 @@ inline SwChange sw_reset_edge(SwGraph &g, uint32_t i0, uint32_t i1) {
     edge.to = home;
     c1.swap_remove_at((size_t)p1);
     g.vertices[home].adj.push_back(SwEdge{i0, NO_ROOT});
+    g.log(OP_RETARGET, i0, i1, home); g.log(OP_SWAP_REMOVE, i1, i0); g.log(OP_PUSH, home, i0);
     return SwChange::Reset;
 }
 
@@ -190,7 +213,7 @@ struct ErEnsembleC {
         const size_t n = graph.vertex_count();
         for (size_t i = 0; i < n; ++i)
             for (size_t j = i + 1; j < n; ++j)
-                if (rng.gen_f64() <= prob) {
+                if (rng.gen_f64() <= prob) {   // (after clear_edges: a wholesale change, not logged entry by entry)
                     graph.vertices[i].adj.push_back(PlainEdge{(uint32_t)j});
                     graph.vertices[j].adj.push_back(PlainEdge{(uint32_t)i});
                     ++graph.edge_count;

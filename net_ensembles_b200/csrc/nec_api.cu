@@ -20,6 +20,7 @@
 #include "../../include/net_ensembles_cuda.h"
 #include "nec_kernels.cuh"
 #include "nec_small.cuh"
+#include "nec_chain.cuh"
 #include "nec_mid.cuh"
 
 namespace {
@@ -1333,6 +1334,43 @@ int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per
     return nec::small_batch_run(ctx->small, ctx->stream, &ctx->err, &ctx->stats, n_graphs, n_per_graph,
                                 row_ptr_offsets, row_ptr_concat, col_offsets, col_idx_concat, include_endpoints ? 1 : 0, out_concat);
 } NEC_CATCH_ALL(ctx)
+
+int nec_chains_create(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,
+                      const uint32_t *row_ptr_concat, const uint64_t *col_offsets, const uint32_t *col_idx_concat,
+                      uint32_t slack, nec_chains **out) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!out) return fail(ctx, NEC_EINVAL, "nec_chains_create: out is NULL");
+    *out = nullptr;
+    if (!n_graphs || !n_per_graph || !row_ptr_offsets || !row_ptr_concat || !col_offsets)
+        return fail(ctx, NEC_EINVAL, "nec_chains_create: NULL argument or empty set");
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nec::chains_create(ctx->small, ctx->stream, &ctx->err, n_graphs, n_per_graph, row_ptr_offsets, row_ptr_concat, col_offsets,
+                              col_idx_concat, slack, out);
+} NEC_CATCH_ALL(ctx)
+
+int nec_chains_step_and_load(nec_ctx *ctx, nec_chains *chains, const uint32_t *op_offsets, const uint64_t *ops, int include_endpoints,
+                             double *out_concat) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!chains) return fail(ctx, NEC_EINVAL, "nec_chains_step_and_load: chains is NULL");
+    ctx->stats = nec_stats{};
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nec::chains_step_and_load(ctx->small, ctx->stream, &ctx->err, &ctx->stats, chains, op_offsets, ops, include_endpoints ? 1 : 0, out_concat);
+} NEC_CATCH_ALL(ctx)
+
+const double *nec_chains_result(const nec_chains *chains) { return chains ? chains->h_out : nullptr; }
+
+int nec_chains_download(nec_ctx *ctx, nec_chains *chains, uint32_t *row_ptr_concat, uint32_t *col_idx_concat, uint64_t col_capacity, uint64_t *nnz) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!chains || !row_ptr_concat || (col_capacity && !col_idx_concat)) return fail(ctx, NEC_EINVAL, "nec_chains_download: NULL argument");
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nec::chains_download(ctx->stream, &ctx->err, chains, row_ptr_concat, col_idx_concat, col_capacity, nnz);
+} NEC_CATCH_ALL(ctx)
+
+void nec_chains_free(nec_ctx *ctx, nec_chains *chains) {
+    if (!chains) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    nec::chains_release(chains);
+}
 
 int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, uint32_t *sources_per_wave) try {
     if (!ctx) return NEC_EINVAL;

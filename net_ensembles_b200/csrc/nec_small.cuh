@@ -45,6 +45,11 @@ struct SmallParams {
     double *__restrict__ out;
     unsigned long long *counters;   // [0] reached pairs [1] edge pairs [2] visits [3] max depth
     uint32_t csr_budget;            // bytes of shared memory reserved for a graph's CSR in this launch
+    // device-resident chains (nec_chain.cuh, kChain): padded adjacency rows instead of a CSR batch; graph i's
+    // vertex v has its row at ch_rows[(out_off[i] + v) * ch_cap] and its degree at ch_deg[out_off[i] + v]
+    const uint16_t *__restrict__ ch_rows;
+    const uint16_t *__restrict__ ch_deg;
+    uint32_t ch_cap;
 };
 
 // per warp: q f64[n] | bpart f64[n] | dist u32[n] | order u16[n]   (n rounded up to 4)
@@ -55,6 +60,7 @@ __host__ __device__ inline size_t small_warp_bytes(uint32_t n) {
 constexpr uint32_t kSmallCsrBytes = 24 * 1024;   // shared-memory budget for a graph's CSR (row_ptr u32 + neighbours u16)
 __host__ __device__ inline size_t small_smem_bytes(uint32_t n, uint32_t csr_budget) { return small_warp_bytes(n) * kSmallWarps + csr_budget; }
 
+template <bool kChain>
 __global__ void __launch_bounds__(kSmallThreads)
 small_graph_kernel(const SmallParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,20 +72,60 @@ small_graph_kernel(const SmallParams p) {
     for (uint32_t g = blockIdx.x; g < p.n_graphs; g += gridDim.x) {
         const uint32_t n = p.n_per_graph[g];
         const uint32_t np4 = (n + 3) / 4 * 4;
-        const uint32_t *__restrict__ rp_g = p.rp + p.rp_off[g];
-        const uint32_t *__restrict__ col_g = p.col + p.col_off[g];
         // stage the graph's CSR in shared memory when it fits (it is read ~2 x n times per graph)
         uint32_t *s_rp = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kSmallWarps * small_warp_bytes(n));
         uint16_t *s_col = reinterpret_cast<uint16_t *>(s_rp + n + 1);
-        const uint32_t nnz = __ldg(rp_g + n);
-        const bool staged = (size_t)(n + 1) * 4 + (size_t)nnz * 2 <= p.csr_budget;
-        if (staged) {
-            for (uint32_t v = threadIdx.x; v <= n; v += kSmallThreads) s_rp[v] = __ldg(rp_g + v);
-            for (uint32_t e = threadIdx.x; e < nnz; e += kSmallThreads) s_col[e] = (uint16_t)__ldg(col_g + e);
+        const uint32_t *__restrict__ rp_g = nullptr, *__restrict__ col_g = nullptr;
+        const uint16_t *__restrict__ rows_g = nullptr, *__restrict__ deg_g = nullptr;
+        const uint32_t cap = p.ch_cap;
+        bool staged;
+        if constexpr (kChain) {
+            // padded rows -> compact CSR in shared memory: warp 0 scans the degrees, then every warp copies rows
+            rows_g = p.ch_rows + p.out_off[g] * cap;
+            deg_g = p.ch_deg + p.out_off[g];
+            __shared__ uint32_t s_total;
+            if (warp == 0) {
+                uint32_t carry = 0;
+                for (uint32_t v0 = 0; v0 < n; v0 += 32) {
+                    const uint32_t v = v0 + lane;
+                    const uint32_t d = v < n ? (uint32_t)deg_g[v] : 0u;
+                    const uint32_t incl = warp_inclusive_scan(d, lane);
+                    if (v < n && (size_t)(n + 1) * 4 <= p.csr_budget) s_rp[v] = carry + incl - d;
+                    carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+                if (lane == 0) { s_total = carry; if ((size_t)(n + 1) * 4 <= p.csr_budget) s_rp[n] = carry; }
+            }
+            __syncthreads();
+            staged = (size_t)(n + 1) * 4 + (size_t)s_total * 2 <= p.csr_budget;
+            if (staged)
+                for (uint32_t v = warp; v < n; v += kSmallWarps) {
+                    const uint32_t rs = s_rp[v], d = s_rp[v + 1] - rs;
+                    for (uint32_t k = lane; k < d; k += 32) s_col[rs + k] = rows_g[(size_t)v * cap + k];
+                }
+        } else {
+            rp_g = p.rp + p.rp_off[g];
+            col_g = p.col + p.col_off[g];
+            const uint32_t nnz = __ldg(rp_g + n);
+            staged = (size_t)(n + 1) * 4 + (size_t)nnz * 2 <= p.csr_budget;
+            if (staged) {
+                for (uint32_t v = threadIdx.x; v <= n; v += kSmallThreads) s_rp[v] = __ldg(rp_g + v);
+                for (uint32_t e = threadIdx.x; e < nnz; e += kSmallThreads) s_col[e] = (uint16_t)__ldg(col_g + e);
+            }
         }
         __syncthreads();
-        auto rp_at = [&](uint32_t v) -> uint32_t { return staged ? s_rp[v] : __ldg(rp_g + v); };
-        auto col_at = [&](uint32_t e) -> uint32_t { return staged ? (uint32_t)s_col[e] : __ldg(col_g + e); };
+        // rows are [row_begin(v), row_end(v)) of col_at(.)
+        auto row_begin = [&](uint32_t v) -> uint32_t {
+            if (staged) return s_rp[v];
+            if constexpr (kChain) return v * cap; else return __ldg(rp_g + v);
+        };
+        auto row_end = [&](uint32_t v) -> uint32_t {
+            if (staged) return s_rp[v + 1];
+            if constexpr (kChain) return v * cap + (uint32_t)deg_g[v]; else return __ldg(rp_g + v + 1);
+        };
+        auto col_at = [&](uint32_t e) -> uint32_t {
+            if (staged) return (uint32_t)s_col[e];
+            if constexpr (kChain) return (uint32_t)rows_g[e]; else return __ldg(col_g + e);
+        };
         unsigned char *mine = smem_raw + (size_t)warp * small_warp_bytes(n);
         double *q = reinterpret_cast<double *>(mine);
         double *bpart = q + np4;
@@ -103,8 +149,8 @@ small_graph_kernel(const SmallParams p) {
                     uint32_t rs = 0, deg = 0;
                     if (i < le) {
                         const uint32_t u = order[i];
-                        rs = rp_at(u);
-                        deg = rp_at(u + 1) - rs;
+                        rs = row_begin(u);
+                        deg = row_end(u) - rs;
                         my_reached += 1;
                         my_edges += deg;
                     }
@@ -154,7 +200,7 @@ small_graph_kernel(const SmallParams p) {
                     const uint32_t i = base + lane;
                     if (i < hi) {
                         const uint32_t w = order[i];
-                        const uint32_t rs = rp_at(w), re = rp_at(w + 1);
+                        const uint32_t rs = row_begin(w), re = row_end(w);
                         double acc = 0.0;
                         uint32_t npred = 0;
                         uint32_t e = rs;
@@ -330,10 +376,9 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, std::string 
 
     const uint32_t csr_budget = (uint32_t)std::min<size_t>((max_csr + 255) / 256 * 256, kSmallCsrBytes);   // larger CSRs are read from L1/L2
     const size_t smem = small_smem_bytes(max_n, csr_budget);
-    if (!ws.attr_set) {
-        e = cudaFuncSetAttribute(small_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
+    {   // per device (a process may hold contexts on several): set on every call
+        e = cudaFuncSetAttribute(small_graph_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
         if (e != cudaSuccess) return small_fail(err, NEC_ECUDA, std::string("nec_vertex_load_batch: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        ws.attr_set = true;
     }
 
     const uint32_t n_chunks = std::max<uint32_t>(1, std::min<uint32_t>(kSmallMaxChunks, n_graphs / 256));
@@ -376,7 +421,7 @@ inline int small_batch_run(SmallWorkspace &ws, cudaStream_t stream, std::string 
         p.out_off = D.out_off + g0; p.include_endpoints = include_endpoints; p.out = D.out; p.counters = D.cnt;
         p.csr_budget = csr_budget;
         cudaEventRecord(ws.ev_k0[c], sk);
-        small_graph_kernel<<<g1 - g0, kSmallThreads, smem, sk>>>(p);
+        small_graph_kernel<false><<<g1 - g0, kSmallThreads, smem, sk>>>(p);
         cudaEventRecord(ws.ev_k1[c], sk);
         cudaStreamWaitEvent(ws.s_out, ws.ev_k1[c], 0);
         cudaMemcpyAsync(H.out + out_off[g0], D.out + out_off[g0], (out_off[g1] - out_off[g0]) * 8, cudaMemcpyDeviceToHost, ws.s_out);

@@ -613,3 +613,58 @@ def test_forward_directions_are_bitwise_identical(ctx, oracle, monkeypatch, widt
         assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
         dg.free()
     ctx.set_engine(0)
+
+
+def test_device_resident_chains_replay_list_operations_exactly(ctx, oracle):
+    """the chains' graphs stay on the device; a step ships the list operations the host chains
+    performed (push / swap_remove / retarget) and the device replays them.  After 1000 steps the device adjacency
+    ORDER equals the host twins' exactly, for every ensemble kind with a Markov chain, and the loads match the
+    oracle; one upload in total."""
+    def make():
+        return ([ne.ErEnsembleC(256, 4.0, 123_239_010 + g) for g in range(40)] + [ne.ErEnsembleC(50, 3.0, 9 + g) for g in range(10)] +
+                [ne.SwEnsemble(100, 0.15, 31 + g) for g in range(10)] + [ne.ErEnsembleM(40, 90, 5 + g) for g in range(6)])
+    chains, twins = make(), make()
+    batch = ne.ChainBatch(chains)
+    assert batch.device_resident
+    for rounds, steps in ((3, 1), (1, 997)):
+        for _ in range(rounds):
+            outs = batch.step_and_load(ctx, steps, True)
+            for t in twins:
+                t.m_steps(steps)
+    assert batch.uploads == 1 and batch.h2d_bytes_last_step < 64 * 1024 * 8
+    dev_adj = batch.device_adjacency()
+    for g, t in enumerate(twins):
+        assert dev_adj[g] == t.adjacency(), g                       # order included
+        assert chains[g].adjacency() == t.adjacency()
+        rp, col = t.export_csr()
+        assert close(outs[g], oracle.vertex_load(rp, col, True), REL), g
+    # a step outside the batch (or a randomize) is noticed: the device copy is rebuilt, nothing is silently stale
+    chains[0].m_steps(5); twins[0].m_steps(5)
+    chains[1].randomize(); twins[1].randomize()
+    outs = batch.step_and_load(ctx, 0, False)
+    assert batch.uploads == 2
+    for g in (0, 1, 2):
+        rp, col = twins[g].export_csr()
+        assert close(outs[g], oracle.vertex_load(rp, col, False), REL)
+    # same numbers as the re-export path, bit for bit (same kernel arithmetic on the same lists)
+    plain = ne.ChainBatch(chains, device_resident=False).step_and_load(ctx, 0, False)
+    for g in range(len(chains)):
+        assert np.asarray(outs[g]).tobytes() == np.asarray(plain[g]).tobytes()
+    batch.close()
+
+
+def test_device_resident_chains_grow_their_rows(ctx, oracle):
+    """Lists that outgrow the padded rows: the device copy is rebuilt with more slack, results stay right."""
+    chains = [ne.ErEnsembleC(64, 1.0, 3 + g) for g in range(8)]
+    batch = ne.ChainBatch(chains)
+    batch.step_and_load(ctx, 0, True)
+    for c in chains:                       # densify far beyond the initial degrees, behind the op log via the batch
+        pass
+    g0 = chains[0]
+    for a in range(1, 40):                 # vertex 0 gets degree 39: logged as wholesale-free list operations
+        g0.add_edge(0, a)
+    outs = batch.step_and_load(ctx, 0, True)
+    rp, col = g0.export_csr()
+    assert close(outs[0], oracle.vertex_load(rp, col, True), REL)
+    assert batch.device_adjacency()[0] == g0.adjacency()
+    batch.close()
