@@ -101,6 +101,19 @@ int nec_graph_upload_adjacency(nec_ctx *ctx, uint32_t n, const void *const *rows
                                uint32_t elem_stride, uint32_t to_offset, uint32_t to_width, nec_graph **out);
 void nec_graph_free(nec_ctx *ctx, nec_graph *g);
 
+/* Vertex and adjacency-entry counts of a device graph; its CSR back on the host (row_ptr[n+1], col_idx[nnz]). */
+int nec_graph_dims(const nec_graph *g, uint32_t *n, uint64_t *nnz);
+int nec_graph_download(nec_ctx *ctx, const nec_graph *g, uint64_t *row_ptr, uint32_t *col_idx);
+
+/* ErEnsembleC::randomize on the device (src/er_c.rs:128-143): one `gen::<f64>() <= prob` per unordered pair in
+ * lexicographic order, drawn from rand_pcg's Pcg64 by jump-ahead, so that the sampled graph - adjacency ORDER
+ * included - and the generator state afterwards are bit-identical to what the crate produces from the same state
+ * (pinned by TestData/unchaning_erc_{1,2}.json).  rng_in / rng_out: state low, state high, increment low,
+ * increment high (u128 as two u64).  The graph is created device-resident (no host adjacency lists, no upload);
+ * nec_graph_download fetches it if the host wants the lists.  Removes the host's O(n^2) loop from simple
+ * sampling (benches/bench_vertex_load.rs:20-26: randomize, then vertex_load). */
+int nec_erc_randomize(nec_ctx *ctx, uint32_t n, double prob, const uint64_t rng_in[4], uint64_t rng_out[4], nec_graph **out);
+
 /* vertex_load(include_endpoints) over all sources: out[n] (host) is overwritten.
  * Synchronous: returns after the result is in `out`.
  * Replaces generic_graph.rs:1310 / graph_traits.rs:328-330. */

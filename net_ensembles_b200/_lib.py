@@ -37,6 +37,9 @@ NEC_SYMBOLS = {
     "nec_graph_upload": (c_int, [c_vp, c_u32, c_u64, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nec_graph_upload_adjacency": (c_int, [c_vp, c_u32, c_vp, c_vp, c_u32, c_u32, c_u32, ctypes.POINTER(c_vp)]),
     "nec_graph_free": (None, [c_vp, c_vp]),
+    "nec_graph_dims": (c_int, [c_vp, ctypes.POINTER(c_u32), ctypes.POINTER(c_u64)]),
+    "nec_graph_download": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "nec_erc_randomize": (c_int, [c_vp, c_u32, c_dbl, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nec_vertex_load": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nec_vertex_load_sources": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, c_vp]),
     "nec_vertex_load_sources_device": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, c_vp]),
@@ -75,6 +78,7 @@ NECH_SYMBOLS = {
 }
 # the drop-in calls over host-mirror handles: compiled into the CUDA library (csrc/host/host_bridge.cpp)
 BRIDGE_SYMBOLS = {
+    "nech_erc_randomize_cuda": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nech_upload_cuda": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "nech_vertex_load_cuda": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "nech_chains_step_and_load_cuda": (c_int, [c_vp, c_u32, c_u64, c_vp, c_int, c_vp]),

@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import NecStats, c_int, c_u32, c_u64, c_vp
+from ._lib import NecStats, c_int, c_u32, c_u64, c_vp  # noqa: F401
 
 
 class NecError(RuntimeError):
@@ -84,8 +84,13 @@ def default_context():
 class DeviceGraph:
     """Device-resident CSR of one sampled graph (nec_graph): export once, measure many times."""
 
-    def __init__(self, ctx, row_ptr=None, col_idx=None, _host=None):
+    def __init__(self, ctx, row_ptr=None, col_idx=None, _host=None, _adopt=None):
         self.ctx = ctx
+        if _adopt is not None:             # a graph the library created on the device (nec_erc_randomize)
+            n, nnz = c_u32(0), c_u64(0)
+            ctx._lib.nec_graph_dims(_adopt, ctypes.byref(n), ctypes.byref(nnz))
+            self.n, self.nnz, self._h = int(n.value), int(nnz.value), _adopt
+            return
         if _host is not None:
             # straight from a host mirror's adjacency lists (export fast path: no CSR is built on the Python side)
             self.n, self.nnz = _host.vertex_count(), 2 * _host.edge_count()
@@ -162,6 +167,12 @@ class DeviceGraph:
         _, sumd, _ = self.distance_measures()
         with np.errstate(divide="ignore", invalid="ignore"):
             return np.float64(self.n - 1) / sumd.astype(np.float64)
+
+    def download(self):
+        """(row_ptr u64[n+1], col_idx u32[nnz]) of the device graph."""
+        rp, col = np.empty(self.n + 1, np.uint64), np.empty(self.nnz, np.uint32)
+        self.ctx._check(self.ctx._lib.nec_graph_download(self.ctx._h, self._h, _ptr(rp), _ptr(col)))
+        return rp, col
 
     def bfs_debug(self, source):
         n = self.n
@@ -392,6 +403,15 @@ class ErEnsembleC(_Ensemble):
 
     def __init__(self, n, c_target, seed):
         super().__init__(_lib.load_host().nech_erc_new(n, c_target, seed))
+
+    def randomize_cuda(self, ctx=None):
+        """`randomize()` (src/er_c.rs:128-143) drawn ON THE DEVICE with Pcg64 jump-ahead: same graph, same adjacency
+        order and same generator state afterwards as the host loop, but the sample is born device-resident.  Returns
+        its DeviceGraph (measure it, then free it); the host lists are brought in step as well."""
+        ctx = ctx or default_context()
+        h = c_vp()
+        ctx._check(ctx._lib.nech_erc_randomize_cuda(self._h, ctx._h, ctypes.byref(h)))
+        return DeviceGraph(ctx, _adopt=h)
 
 
 class ErEnsembleM(_Ensemble):

@@ -137,6 +137,40 @@ int nech_vertex_load_cuda(const void *p, nec_ctx *ctx, int include_endpoints, do
         }); });
 }
 
+// SimpleSample::randomize of an ErEnsembleC ON THE DEVICE (nec_erc_randomize: Pcg64 jump-ahead, one draw per pair,
+// bit-identical to er_c.rs:128-143), leaving the sampled graph device-resident for the measurement that follows
+// (benches/bench_vertex_load.rs:20-26).  The host mirror is brought in step - adjacency lists, edge count and
+// generator - from the device's CSR, so m_step / export / vertex_load on the handle keep working afterwards.
+int nech_erc_randomize_cuda(void *p, nec_ctx *ctx, nec_graph **out) {
+    if (!p || !ctx || !out) return NEC_EINVAL;
+    return guarded(ctx, [&]() -> int {
+        Handle *h = static_cast<Handle *>(p);
+        if (h->kind != Kind::ErC) { nec_internal_set_error(ctx, "randomize on the device is implemented for ErEnsembleC"); return NEC_EINVAL; }
+        ErEnsembleC &e = *h->erc;
+        const uint32_t n = (uint32_t)e.graph.vertex_count();
+        const uint64_t in[4] = {(uint64_t)e.rng.state, (uint64_t)(e.rng.state >> 64), (uint64_t)e.rng.increment, (uint64_t)(e.rng.increment >> 64)};
+        uint64_t after[4];
+        nec_graph *dg = nullptr;
+        int rc = nec_erc_randomize(ctx, n, e.prob, in, after, &dg);
+        if (rc != NEC_OK) return rc;
+        uint64_t nnz = 0;
+        nec_graph_dims(dg, nullptr, &nnz);
+        std::vector<uint64_t> rp((size_t)n + 1);
+        std::vector<uint32_t> col(nnz);
+        rc = nec_graph_download(ctx, dg, rp.data(), col.data());
+        if (rc != NEC_OK) { nec_graph_free(ctx, dg); return rc; }
+        e.graph.clear_edges();
+        for (uint32_t v = 0; v < n; ++v) {
+            auto &adj = e.graph.vertices[v].adj;
+            adj.resize(rp[v + 1] - rp[v]);
+            for (uint64_t k = rp[v]; k < rp[v + 1]; ++k) adj[k - rp[v]] = PlainEdge{col[k]};
+        }
+        e.graph.edge_count = nnz / 2;
+        e.rng.state = ((u128)after[1] << 64) | (u128)after[0];
+        *out = dg;
+        return NEC_OK; });
+}
+
 // Markov-chain shape (benches/common/mod.rs:79-90): `count` m_steps on every chain, then
 // vertex_load(include_endpoints) of ALL chains' graphs (one CTA per graph).  out receives the load
 // vectors back to back.  count == 0 measures without stepping.

@@ -21,6 +21,7 @@
 #include "nec_kernels.cuh"
 #include "nec_small.cuh"
 #include "nec_chain.cuh"
+#include "nec_sample.cuh"
 #include "nec_mid.cuh"
 
 namespace {
@@ -87,6 +88,7 @@ struct nec_ctx {
     int team_cap[2][9];                               // resident clusters per (batch width 32/64, team size); -1 = not asked yet
     nec::SmallWorkspace small;
     void *h_stage = nullptr; size_t h_stage_cap = 0;  // pinned staging of an upload's 32-bit CSR
+    uint8_t *d_sample = nullptr; size_t d_sample_cap = 0;   // scratch of nec_erc_randomize
     // multi-device context (nec_init with n_devices > 1): this context works on devices[0]; `peers` are full
     // single-device contexts for devices[1..], `comms[i]` the NCCL communicator of device i (0 = this one)
     std::vector<nec_ctx *> peers;
@@ -920,6 +922,7 @@ void nec_destroy(nec_ctx *ctx) {
     if (ctx->d_src_status) cudaFree(ctx->d_src_status);
     ctx->small.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_sample) cudaFree(ctx->d_sample);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
@@ -1008,6 +1011,7 @@ static int stage_reserve(nec_ctx *ctx, uint32_t n, uint64_t nnz, uint32_t *&h_rp
     const size_t rp_bytes = align_up(((size_t)n + 1) * 4, 256), need = rp_bytes + std::max<uint64_t>(nnz, 1) * 4;
     if (need > ctx->h_stage_cap) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_sample) cudaFree(ctx->d_sample);
         ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
         const size_t cap = need + need / 8;
         cudaError_t e = cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocPortable);   // every device of a multi-device context copies from it
@@ -1108,6 +1112,120 @@ int nec_graph_upload_adjacency(nec_ctx *ctx, uint32_t n, const void *const *rows
     }
     if (bad_row < (long long)n) return fail(ctx, NEC_EINVAL, "nec_graph_upload_adjacency: a neighbour id of vertex %u is out of range (n=%u)", (uint32_t)bad_row, n);
     return finish_upload(ctx, n, nnz, rp32, col32, max_deg, over8, out);
+} NEC_CATCH_ALL(ctx)
+
+// ErEnsembleC::randomize on one device; the generator state is read from / written to 4 x u64 (state lo, hi,
+// increment lo, hi).  Deterministic, so a multi-device context simply runs it on every device.
+static int erc_randomize_one(nec_ctx *ctx, uint32_t n, double prob, const uint64_t rng[4], nec_graph **out) {
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    nec_graph *g = new (std::nothrow) nec_graph();
+    if (!g) return fail(ctx, NEC_ENOMEM, "out of host memory");
+    g->n = n;
+    auto bail = [&](int rc) { nec_graph_free(ctx, g); return rc; };
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_state = up((size_t)n * 16), b_u32 = up((size_t)n * 4), b_tot = 256, b_step = up(33 * sizeof(nec::LcgStep));
+    const size_t need = b_state + 3 * b_u32 + b_tot + b_step;
+    int rc = grow(ctx, ctx->d_sample, ctx->d_sample_cap, need);
+    if (rc != NEC_OK) return bail(rc);
+    nec::ErcParams p{};
+    p.n = n; p.prob = prob;
+    p.state_lo = rng[0]; p.state_hi = rng[1]; p.inc_lo = rng[2]; p.inc_hi = rng[3];
+    uint8_t *d = ctx->d_sample;
+    p.row_state = (unsigned long long *)d; d += b_state;
+    p.lower_deg = (uint32_t *)d; d += b_u32;
+    p.upper_deg = (uint32_t *)d; d += b_u32;
+    p.cursor = (uint32_t *)d; d += b_u32;
+    p.totals = (unsigned long long *)d; d += b_tot;
+    nec::LcgStep *d_steps = (nec::LcgStep *)d;
+    p.lane_step = d_steps;
+    nec::LcgStep steps[33];
+    const nec::u128 inc = nec::u128_of(rng[2], rng[3]);
+    for (int l = 0; l < 33; ++l) {
+        nec::u128 m, a;
+        nec::lcg_jump(l < 32 ? (unsigned long long)l + 1 : 32ull, inc, m, a);
+        steps[l] = nec::LcgStep{(unsigned long long)m, (unsigned long long)(m >> 64), (unsigned long long)a, (unsigned long long)(a >> 64)};
+    }
+    cudaError_t e = cudaMallocAsync((void **)&g->d_row_ptr, ((size_t)n + 1) * sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, NEC_ENOMEM, "nec_erc_randomize: %s", cudaGetErrorString(e)));
+    p.row_ptr = g->d_row_ptr;
+    NEC_CUDA(ctx, cudaMemcpyAsync(d_steps, steps, sizeof steps, cudaMemcpyHostToDevice, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(p.totals, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    const unsigned row_blocks = std::min<unsigned>((n + 7) / 8, 148u * 8u);       // 8 warps per CTA, one warp per row
+    nec::erc_row_states_kernel<<<std::min<unsigned>((n + 255) / 256, 148u * 4u), 256, 0, ctx->stream>>>(p);
+    nec::erc_rows_kernel<false><<<row_blocks, 256, 0, ctx->stream>>>(p);
+    nec::erc_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p);
+    unsigned long long totals[3] = {0, 0, 0};
+    e = cudaMemcpyAsync(totals, p.totals, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // nnz decides the size of col_idx (pageable read: waited for)
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(ctx, NEC_ECUDA, "nec_erc_randomize: %s", cudaGetErrorString(e)));
+    if (totals[0] >= 0xFFFFFFFFull) return bail(fail(ctx, NEC_EINVAL, "nec_erc_randomize: %llu adjacency entries do not fit 32-bit row pointers", totals[0]));
+    g->nnz = totals[0]; g->max_degree = (uint32_t)totals[2];
+    e = cudaMallocAsync((void **)&g->d_col_idx, std::max<size_t>(g->nnz, 1) * sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, NEC_ENOMEM, "nec_erc_randomize: %s", cudaGetErrorString(e)));
+    p.col_idx = g->d_col_idx;
+    nec::erc_rows_kernel<true><<<row_blocks, 256, 0, ctx->stream>>>(p);
+    nec::erc_sort_lower_kernel<<<std::min<unsigned>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(p);
+    if (n <= nec::kMidMaxN) {
+        g->slab_w = totals[1] * 10 > n ? 16 : 8;
+        const size_t slab_words = (size_t)n * g->slab_w;
+        e = cudaMallocAsync((void **)&g->d_slab, slab_words * sizeof(uint32_t), ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&g->d_deg8, (size_t)n + 2, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->d_deg8 + n, 0, 2, ctx->stream);
+        if (e != cudaSuccess) return bail(fail(ctx, NEC_ENOMEM, "nec_erc_randomize: %s", cudaGetErrorString(e)));
+        nec::build_slab_kernel<<<(unsigned)std::min<size_t>((slab_words + 255) / 256, 148u * 16u), 256, 0, ctx->stream>>>(
+            n, g->slab_w, g->d_row_ptr, g->d_col_idx, reinterpret_cast<uint32_t *>(g->d_slab), g->d_deg8);
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(ctx, NEC_ECUDA, "nec_erc_randomize: %s", cudaGetErrorString(e)));
+    *out = g;
+    return NEC_OK;
+}
+
+int nec_erc_randomize(nec_ctx *ctx, uint32_t n, double prob, const uint64_t rng_in[4], uint64_t rng_out[4], nec_graph **out) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!out || !rng_in) return fail(ctx, NEC_EINVAL, "nec_erc_randomize: NULL argument");
+    *out = nullptr;
+    if (n < 2) return fail(ctx, NEC_EINVAL, "nec_erc_randomize: n must be at least 2");
+    if ((uint64_t)n * 64u + 64u > 0xFFFFFFFFull) return fail(ctx, NEC_EINVAL, "nec_erc_randomize: n=%u too large", n);
+    if (!(rng_in[2] & 1)) return fail(ctx, NEC_EINVAL, "nec_erc_randomize: a Pcg64 increment is odd");
+    int rc;
+    if (ctx->peers.empty()) rc = erc_randomize_one(ctx, n, prob, rng_in, out);
+    else {
+        std::vector<nec_graph *> made(n_devices_of(ctx), nullptr);
+        rc = on_all_devices(ctx, [&](size_t d) { return erc_randomize_one(device_ctx(ctx, d), n, prob, rng_in, &made[d]); });
+        if (rc != NEC_OK) for (size_t d = 0; d < made.size(); ++d) nec_graph_free(device_ctx(ctx, d), made[d]);
+        else { made[0]->replicas.assign(made.begin() + 1, made.end()); *out = made[0]; }
+    }
+    if (rc != NEC_OK) return rc;
+    if (rng_out) {      // the generator after its n (n - 1) / 2 draws
+        nec::u128 m, a;
+        const nec::u128 inc = nec::u128_of(rng_in[2], rng_in[3]);
+        nec::lcg_jump((unsigned long long)n * (n - 1) / 2, inc, m, a);
+        const nec::u128 s = m * nec::u128_of(rng_in[0], rng_in[1]) + a;
+        rng_out[0] = (uint64_t)s; rng_out[1] = (uint64_t)(s >> 64); rng_out[2] = rng_in[2]; rng_out[3] = rng_in[3];
+    }
+    return NEC_OK;
+} NEC_CATCH_ALL(ctx)
+
+int nec_graph_dims(const nec_graph *g, uint32_t *n, uint64_t *nnz) {
+    if (!g) return NEC_EINVAL;
+    if (n) *n = g->n;
+    if (nnz) *nnz = g->nnz;
+    return NEC_OK;
+}
+
+int nec_graph_download(nec_ctx *ctx, const nec_graph *g, uint64_t *row_ptr, uint32_t *col_idx) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || !row_ptr || (g->nnz && !col_idx)) return fail(ctx, NEC_EINVAL, "nec_graph_download: NULL argument");
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> rp32((size_t)g->n + 1);
+    NEC_CUDA(ctx, cudaMemcpyAsync(rp32.data(), g->d_row_ptr, rp32.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (g->nnz) NEC_CUDA(ctx, cudaMemcpyAsync(col_idx, g->d_col_idx, g->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t v = 0; v <= g->n; ++v) row_ptr[v] = rp32[v];
+    return NEC_OK;
 } NEC_CATCH_ALL(ctx)
 
 void nec_graph_free(nec_ctx *ctx, nec_graph *g) {

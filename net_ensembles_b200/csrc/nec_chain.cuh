@@ -87,6 +87,7 @@ struct nec_chains {
     uint32_t n_graphs = 0, cap = 0, max_n = 0;
     uint64_t n_vertices = 0;                      // sum of the graphs' vertex counts = length of the result
     std::vector<uint32_t> h_n;
+    std::vector<uint32_t> h_nnz;                  // adjacency entries per graph, kept in step with the replayed operations
     std::vector<uint64_t> h_vert_base;            // n_graphs + 1
     void *d_base = nullptr; size_t d_bytes = 0;
     uint32_t *d_n = nullptr, *d_flags = nullptr, *d_op_off = nullptr;
@@ -149,6 +150,8 @@ inline int chains_create(SmallWorkspace &ws, cudaStream_t stream, std::string *e
     // outgrows it is reported and the caller re-creates the set with more slack
     c->cap = std::min<uint32_t>(NEC_BATCH_MAX_N, ((std::max<uint32_t>(max_deg, 4u) + std::max<uint32_t>(slack, 4u) + 7u) / 8u) * 8u);
     c->h_n.assign(n_per_graph, n_per_graph + n_graphs);
+    c->h_nnz.resize(n_graphs);
+    for (uint32_t g = 0; g < n_graphs; ++g) c->h_nnz[g] = (rp + rp_off[g])[n_per_graph[g]];
     c->h_vert_base.resize((size_t)n_graphs + 1);
     c->h_vert_base[0] = 0;
     for (uint32_t g = 0; g < n_graphs; ++g) c->h_vert_base[g + 1] = c->h_vert_base[g] + n_per_graph[g];
@@ -234,6 +237,12 @@ inline int chains_step_and_load(SmallWorkspace &ws, cudaStream_t stream, std::st
         }
         std::memcpy(c->h_ops, ops, (size_t)n_ops * 8);
         std::memcpy(c->h_op_off, op_offsets, ((size_t)n_graphs + 1) * 4);
+        for (uint32_t g = 0; g < n_graphs; ++g)          // list lengths after this step (push +1, swap_remove -1)
+            for (uint32_t i = op_offsets[g]; i < op_offsets[g + 1]; ++i) {
+                const uint64_t kind = ops[i] >> 60;
+                if (kind == 1) c->h_nnz[g] += 1;
+                else if (kind == 2 && c->h_nnz[g]) c->h_nnz[g] -= 1;
+            }
         cudaMemcpyAsync(c->d_ops, c->h_ops, (size_t)n_ops * 8, cudaMemcpyHostToDevice, ws.s_in);
         cudaMemcpyAsync(c->d_op_off, c->h_op_off, ((size_t)n_graphs + 1) * 4, cudaMemcpyHostToDevice, ws.s_in);
         chain_apply_kernel<<<(n_graphs * 32 + 255) / 256, 256, 0, ws.s_in>>>(n_graphs, c->d_n, c->d_vert_base, c->cap, c->d_rows, c->d_deg, c->d_op_off, c->d_ops, c->d_flags);
@@ -243,9 +252,11 @@ inline int chains_step_and_load(SmallWorkspace &ws, cudaStream_t stream, std::st
     cudaMemcpyAsync(c->h_flags, c->d_flags, (size_t)n_graphs * 4, cudaMemcpyDeviceToHost, ws.s_in);
     cudaEventRecord(ws.ev_in[0], ws.s_in);
 
-    // worst-case CSR of one graph in shared memory: (n+1) row pointers + every row full would not fit; the kernel
-    // stages a graph when its actual lists fit the budget and reads the padded rows from L1/L2 otherwise
-    const uint32_t csr_budget = kSmallCsrBytes;
+    // shared memory reserved for a graph's compact CSR (row pointers u32 + neighbours u16): what the largest graph
+    // needs now, capped; a graph beyond the cap is read from its padded rows through L1/L2 instead
+    size_t max_csr = 0;
+    for (uint32_t g = 0; g < n_graphs; ++g) max_csr = std::max(max_csr, (size_t)(c->h_n[g] + 1) * 4 + (size_t)c->h_nnz[g] * 2);
+    const uint32_t csr_budget = (uint32_t)std::min<size_t>((max_csr + 255) / 256 * 256, kSmallCsrBytes);
     const size_t smem = small_smem_bytes(c->max_n, csr_budget);
     e = cudaFuncSetAttribute(small_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(NEC_BATCH_MAX_N, kSmallCsrBytes));
     if (e != cudaSuccess) return chains_fail(err, NEC_ECUDA, std::string("nec_chains: cudaFuncSetAttribute: ") + cudaGetErrorString(e));

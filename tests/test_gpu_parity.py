@@ -415,7 +415,7 @@ def test_chain_batch_pipeline_many_chunks(ctx, oracle):
     batch = ne.ChainBatch(chains)
     for step in range(2):
         outs = batch.step_and_load(ctx, 3, True)
-        assert batch.stats["kernel_launches"] == 4 and batch.stats["engine"] == 3    # 1100 graphs -> 4 chunks
+        assert batch.stats["kernel_launches"] == 4 + 1 and batch.stats["engine"] == 3    # 1100 graphs -> 4 chunks, + the replay of the step's list operations
         assert batch.stats["n_sources"] == int(sizes.sum())
         for t in twins:
             t.m_steps(3)
@@ -668,3 +668,41 @@ def test_device_resident_chains_grow_their_rows(ctx, oracle):
     assert close(outs[0], oracle.vertex_load(rp, col, True), REL)
     assert batch.device_adjacency()[0] == g0.adjacency()
     batch.close()
+
+
+def test_erc_randomize_on_device_matches_the_fixtures_bit_for_bit(ctx, oracle, golden):
+    """SURVEY 8(f) rank 4: ErEnsembleC::randomize drawn on the device by Pcg64 jump-ahead.  From the fixture's
+    seed the reference's constructor is new() = one randomize; the device sample must reproduce the fixture's
+    adjacency lists (order included) and final generator state, and keep doing so sample after sample."""
+    for name in ("erc_1", "erc_2"):
+        fx = golden["graphs"][name]
+        n, c, seed = fx["n"], fx["c"], fx["seed"]
+        host = ne.ErEnsembleC(n, c, seed)                      # host loop: equals the fixture (tests/test_generators.py)
+        assert host.adjacency() == fx["adj"]
+        # a second ensemble whose FIRST randomize we redo on the device from the seed state
+        lib = ne._lib.load_host() if hasattr(ne, "_lib") else None
+        dev = ne.ErEnsembleC(n, c, seed)
+        # rewind: construct the seed state by hand is not exposed, so compare sample k+1 instead: both ensembles
+        # sit after the constructor's randomize; the next sample comes from the host loop on one, the device on the other
+        for _ in range(3):
+            host.randomize()
+            dg = dev.randomize_cuda(ctx)
+            assert dev.adjacency() == host.adjacency()
+            assert dev.rng_state() == host.rng_state()
+            rp, col = dg.download()
+            hrp, hcol = host.export_csr()
+            assert rp.tolist() == hrp.tolist() and col.tolist() == hcol.tolist()
+            assert close(dg.vertex_load(True), oracle.vertex_load(hrp, hcol, True), REL)
+            dg.free()
+    # the fixture itself: state after the constructor == fixture's recorded generator, so the chain of equalities
+    # above starts from a pinned point
+    fx = golden["graphs"]["erc_1"]
+    assert ne.ErEnsembleC(fx["n"], fx["c"], fx["seed"]).rng_state() == (int(fx["rng_state"]), int(fx["rng_increment"]))
+    # larger and denser samples (rows longer than a warp's 32 pairs; lower parts that need sorting)
+    for n, c, seed in ((1000, 4.0, 123_239_010), (700, 40.0, 5), (64, 63.0, 2), (2, 1.0, 1)):
+        a, b = ne.ErEnsembleC(n, c, seed), ne.ErEnsembleC(n, c, seed)
+        a.randomize()
+        dg = b.randomize_cuda(ctx)
+        assert a.adjacency() == b.adjacency() and a.rng_state() == b.rng_state()
+        assert dg.n == n and dg.nnz == 2 * a.edge_count()
+        dg.free()
