@@ -53,6 +53,18 @@ def build_cuda(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(tag, defines):
+    """A/B build of the CUDA library with extra -D flags (scripts/exp_r2.py --lib <tag>); lives next to the product library."""
+    out = os.path.join(LIB_DIR, tag + ".so")
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + CUDA_SOURCES + ["-o", out]
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    return out
+
+
 def build_host(force=False):
     if not force and not _stale(HOST_LIB_PATH, HOST_SOURCES + HOST_HEADERS):
         return HOST_LIB_PATH

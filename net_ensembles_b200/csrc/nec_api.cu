@@ -82,6 +82,7 @@ struct nec_ctx {
     uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
     bool mid_attr_set = false;
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
+    double *dbg_sigma = nullptr;                      // nec_bfs_debug: plane for the path counts of the debug instantiation
     uint32_t pull_mode = 1;                           // batched forward pass: 0 push only, 1 per-level cost model, 2 pull only (NEC_PULL, tests)
     bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
     uint32_t team_size = 1;                           // batched engine: CTAs per slot (thread-block cluster), set per call
@@ -262,6 +263,7 @@ template <typename DistT, int kMode, int kSrc = 32>
 int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const uint32_t *d_worklist,
                   uint32_t n_work, int include_endpoints, uint32_t slots, uint32_t *dbg_npred, double *dbg_bk,
                   const MeasureOut *mo = nullptr) {
+    double *dbg_sigma = ctx->dbg_sigma;
     const Arena &a = ctx->arena;
     nec::EngineParams p{};
     p.n = g->n; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
@@ -278,7 +280,7 @@ int launch_engine(nec_ctx *ctx, const nec_graph *g, uint32_t n_sources, const ui
     p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride;
     p.max_levels = a.max_levels;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
-    p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk;
+    p.dbg_npred = dbg_npred; p.dbg_bk = dbg_bk; p.dbg_sigma = dbg_npred ? dbg_sigma : nullptr;
     if (mo) { p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
     int rc;
     if constexpr (kMode == 0 && sizeof(DistT) == 1) {
@@ -1325,17 +1327,20 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
     // Runs the PRODUCTION engine (debug instantiation: identical code plus two plane stores)
     // on a one-source batch and reads lane 0 of the slot's planes.
     uint32_t *d_np_plane = nullptr, *d_u32 = nullptr;
-    double *d_bk_plane = nullptr, *d_f64 = nullptr, *d_load = nullptr;
+    double *d_bk_plane = nullptr, *d_sig_plane = nullptr, *d_f64 = nullptr, *d_load = nullptr;
     const size_t plane = (size_t)n * nec::kLanes;
-    auto cleanup = [&]() { cudaFree(d_np_plane); cudaFree(d_bk_plane); cudaFree(d_u32); cudaFree(d_f64); cudaFree(d_load); };
+    auto cleanup = [&]() { cudaFree(d_np_plane); cudaFree(d_bk_plane); cudaFree(d_sig_plane); cudaFree(d_u32); cudaFree(d_f64); cudaFree(d_load); ctx->dbg_sigma = nullptr; };
     cudaError_t e = cudaMalloc((void **)&d_np_plane, plane * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_bk_plane, plane * 8);
+    if (e == cudaSuccess && sigma) e = cudaMalloc((void **)&d_sig_plane, plane * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_u32, (size_t)n * 4 * 2);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_f64, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_f64, (size_t)n * 8 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_load, (size_t)n * 8);
     if (e != cudaSuccess) { cleanup(); return fail(ctx, NEC_ENOMEM, "nec_bfs_debug: %s", cudaGetErrorString(e)); }
     cudaMemsetAsync(d_np_plane, 0, plane * 4, ctx->stream);
+    if (d_sig_plane) cudaMemsetAsync(d_sig_plane, 0, plane * 8, ctx->stream);      // unreached vertices: 0 paths
     nec::fill_f64_kernel<<<std::min<size_t>((plane + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(d_bk_plane, plane, 1.0);
+    ctx->dbg_sigma = d_sig_plane;
     int rc = run_sources(ctx, g, &source, 1, 1, d_load, true, d_np_plane, d_bk_plane);
     if (rc != NEC_OK) { cleanup(); return rc; }
     const Arena &a = ctx->arena;
@@ -1346,13 +1351,11 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
     if (a.dist_bytes == 1) nec::widen_inf_kernel<<<blocks, 256, 0, ctx->stream>>>(d_dist32, n);
     nec::extract_lane_kernel<uint32_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>(d_np_plane, n, 0, d_np);
     nec::extract_lane_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>(d_bk_plane, n, 0, d_f64);
+    if (d_sig_plane) nec::extract_lane_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>(d_sig_plane, n, 0, d_f64 + n);
     if (dist) cudaMemcpyAsync(dist, d_dist32, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (npred) cudaMemcpyAsync(npred, d_np, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (bk) cudaMemcpyAsync(bk, d_f64, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (sigma) {
-        nec::sigma_debug_kernel<<<1, 1024, 0, ctx->stream>>>(n, g->d_row_ptr, g->d_col_idx, d_dist32, ctx->stats.max_depth, d_load);
-        cudaMemcpyAsync(sigma, d_load, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    }
+    if (sigma) cudaMemcpyAsync(sigma, d_f64 + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();

@@ -49,6 +49,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef NEC_LEAF_MARKS
+#define NEC_LEAF_MARKS 1      // 0: A/B builds without the leaf marks of the backward pass
+#endif
+
 namespace nec {
 
 constexpr int kLanes = 32;            // lanes per warp = sources per narrow batch (debug planes, small-graph kernel)
@@ -93,6 +97,7 @@ struct EngineParams {
     // optional per-(vertex,lane) debug planes of slot 0 (nec_bfs_debug)
     uint32_t *dbg_npred;
     double *dbg_bk;
+    double *dbg_sigma;                          // f64 shortest-path counts (not used by the load: the crate splits equally)
     // distance-measure outputs, indexed like `sources` (kMode 2)
     uint32_t *out_ecc;
     unsigned long long *out_sumdist;
@@ -100,7 +105,7 @@ struct EngineParams {
 };
 
 template <typename DistT> struct DistTraits;
-template <> struct DistTraits<uint8_t>  { static constexpr uint32_t kInf = 0xFFu;        static constexpr uint32_t kMaxLevel = 253u; };
+template <> struct DistTraits<uint8_t>  { static constexpr uint32_t kInf = 0xFFu;        static constexpr uint32_t kMaxLevel = 126u; };   // bytes >= 0x80: 'finished' marks of the backward pass
 template <> struct DistTraits<uint32_t> { static constexpr uint32_t kInf = 0xFFFFFFFFu;  static constexpr uint32_t kMaxLevel = 0xFFFFFFF0u; };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -263,6 +268,17 @@ vertex_load_engine(const EngineParams p) {
         if constexpr (kTeam) return *(volatile uint32_t *)fail_p != 0;
         else return s_fail != 0;
     };
+    // LEAF MARKS (byte distance rows, vertex_load mode): when the backward pass finishes (w, source k) it overwrites
+    // w's distance byte with 0x80 | parity(level) << 6 | info.  info = npred for a BFS leaf (no successors: bk = 1
+    // exactly, so q = 1 / npred and neither a q store nor - for the vertices that pull from it - a random 8-byte q
+    // load is needed: the puller has the byte in its staged row already and takes 1 / npred from a 64-entry table);
+    // info = 0 for everything else (q is read as before).  About half of all BFS-DAG edges of an expander end in a
+    // leaf.  Readers on level l see successors as marks of parity(l + 1), predecessors as plain bytes l - 1 and
+    // same-level vertices as plain l or marks of parity(l), whichever wins the race: all three stay distinct.
+    constexpr bool kLeafMarks = NEC_LEAF_MARKS && sizeof(DistT) == 1 && kMode == 0;
+    constexpr uint32_t kMaxLeafPred = 62;
+    __shared__ double s_rcp[64];
+    if (kLeafMarks && threadIdx.x < 64) s_rcp[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
     __shared__ unsigned long long s_msum[kSrc];          // kMode 2: per source of the batch
     __shared__ uint32_t s_mreach[kSrc], s_mecc[kSrc];
     __shared__ unsigned long long s_cnt[3];
@@ -581,6 +597,7 @@ vertex_load_engine(const EngineParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             const uint32_t lb = lvl[l], le = lvl[l + 1];
             const uint32_t d_succ = l + 1, d_pred = l - 1;
+            const uint32_t succ_tag = 0x80u | (((l + 1) & 1u) << 6), mark_tag = 0x80u | ((l & 1u) << 6);
             for (uint32_t tile = lb + warp_t * 32; tile < le; tile += warps_t * 32) {
                 const uint32_t idx = tile + lane;
                 uint32_t w = 0, rs = 0, deg = 0;
@@ -608,11 +625,17 @@ vertex_load_engine(const EngineParams p) {
                     for (int h = 0; h < kH; ++h) {
                         const double bk = 1.0 + acc[h];
                         if ((uint32_t)(m_c >> (h * 32 + lane)) & 1u) {
-                            q[(size_t)w_c * kSrc + h * 32 + lane] = bk / (double)npred[h];
+                            const size_t at = (size_t)w_c * kSrc + h * 32 + lane;
+                            if constexpr (kLeafMarks) {
+                                // q values are positive, so acc == 0 <=> no successor <=> bk == 1 exactly
+                                const bool leaf = acc[h] == 0.0 && npred[h] <= kMaxLeafPred;
+                                if (!leaf) q[at] = bk / (double)npred[h];
+                                dist[at] = (DistT)(mark_tag | (leaf ? npred[h] : 0u));
+                            } else q[at] = bk / (double)npred[h];
                             contrib += p.include_endpoints ? bk : bk - 1.0;
                             if (kDebug) {
-                                p.dbg_npred[(size_t)w_c * kSrc + h * 32 + lane] = npred[h];
-                                p.dbg_bk[(size_t)w_c * kSrc + h * 32 + lane] = bk;
+                                p.dbg_npred[at] = npred[h];
+                                p.dbg_bk[at] = bk;
                             }
                         }
                     }
@@ -690,7 +713,14 @@ vertex_load_engine(const EngineParams p) {
                             const uint32_t xj = s_stage[warp][buf][(c0 + jj) & 31].x;
 #pragma unroll
                             for (int h = 0; h < kH; ++h) {
-                                qv[jj][h] = (dx[jj][h] == d_succ) ? q[(size_t)xj * kSrc + h * 32 + lane] : 0.0;
+                                if constexpr (kLeafMarks) {
+                                    // inactive lanes carry kInf = 0xFF, which only parity-1 tags could match: excluded
+                                    const uint32_t b = dx[jj][h];
+                                    const bool succ = (b & 0xC0u) == succ_tag && b != kInf;
+                                    const uint32_t info = b & 0x3Fu;
+                                    qv[jj][h] = succ ? (info ? s_rcp[info] : __ldcg(&q[(size_t)xj * kSrc + h * 32 + lane])) : 0.0;
+                                } else
+                                    qv[jj][h] = (dx[jj][h] == d_succ) ? q[(size_t)xj * kSrc + h * 32 + lane] : 0.0;
                                 pred_bits[h] |= (dx[jj][h] == d_pred ? 1u : 0u) << jj;
                             }
                         }
@@ -735,6 +765,28 @@ vertex_load_engine(const EngineParams p) {
                 if (active) {
                     p.dbg_npred[(size_t)ex * kSrc + lane] = 0;
                     p.dbg_bk[(size_t)ex * kSrc + lane] = 1.0 + acc;
+                    if (p.dbg_sigma) p.dbg_sigma[(size_t)ex * kSrc + lane] = 1.0;
+                }
+            }
+            // SIGMA: f64 shortest-path counts, levels ascending over the same queues, pull form like the backward
+            // pass (warp per queue entry, lane per source, one writer per (vertex, source), neighbours in CSR order):
+            // sigma(x) = sum of sigma(u) over the neighbours one level closer.  Counts are integers, exact in f64
+            // below 2^53 whatever the order; beyond that they round (nec_bfs_debug).  The load never reads them.
+            if (p.dbg_sigma) {
+                for (uint32_t l = 1; l <= depth; ++l) {
+                    __syncthreads();
+                    const uint32_t b0 = lvl[l], b1 = lvl[l + 1];
+                    for (uint32_t idx = b0 + warp; idx < b1; idx += kWarps) {
+                        const uint32_t ex = queue_v[idx];
+                        const bool active = (uint32_t)(queue_m[idx] >> lane) & 1u;
+                        const uint32_t rs = p.row_ptr[ex], re = p.row_ptr[ex + 1];
+                        double acc = 0.0;
+                        for (uint32_t e = rs; e < re; ++e) {
+                            const uint32_t u = p.col_idx[e];
+                            if (active && (uint32_t)dist[(size_t)u * kSrc + lane] == l - 1) acc += p.dbg_sigma[(size_t)u * kSrc + lane];
+                        }
+                        if (active) p.dbg_sigma[(size_t)ex * kSrc + lane] = acc;
+                    }
                 }
             }
         }
@@ -809,27 +861,6 @@ template <typename T, typename U>
 __global__ void extract_lane_kernel(const T *__restrict__ plane, uint32_t n, int lane, U *__restrict__ out) {
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
         out[v] = (U)plane[(size_t)v * kLanes + lane];
-}
-
-// Shortest-path counts from given distances, one CTA, level by level (debug only; sigma is
-// not part of the load value).  sigma[v] = sum of sigma over neighbours one level closer.
-__global__ void sigma_debug_kernel(uint32_t n, const uint32_t *__restrict__ row_ptr,
-                                   const uint32_t *__restrict__ col_idx, const uint32_t *__restrict__ dist,
-                                   uint32_t max_depth, double *sigma) {
-    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) sigma[v] = dist[v] == 0 ? 1.0 : 0.0;
-    __syncthreads();
-    for (uint32_t l = 1; l <= max_depth; ++l) {
-        for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
-            if (dist[v] != l) continue;
-            double acc = 0.0;
-            for (uint32_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
-                const uint32_t x = col_idx[e];
-                if (dist[x] == l - 1) acc += sigma[x];
-            }
-            sigma[v] = acc;
-        }
-        __syncthreads();
-    }
 }
 
 }  // namespace nec

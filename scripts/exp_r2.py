@@ -17,6 +17,10 @@ import net_ensembles_b200 as ne  # noqa: E402
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "erm"
+    if len(sys.argv) > 3 and sys.argv[2] == "--lib":          # another build of the library (lib/<tag>.so): child process
+        import subprocess
+        env = dict(os.environ, NEC_LIB_PATH=os.path.join(ROOT, "net_ensembles_b200", "lib", sys.argv[3] + ".so"), AB_LIB_TAG=sys.argv[3])
+        raise SystemExit(subprocess.run([sys.executable, __file__, which] + sys.argv[4:], env=env).returncode)
     specs = sys.argv[2:] or ["push:NEC_PULL=0", "auto:NEC_PULL=1", "pull:NEC_PULL=2"]
     g = ne.gnm_scalable(1 << 20, 1 << 22, 7) if which == "erm" else ne.ba_scalable(1 << 22, 4, 5, 7)
     rp, col = g.export_csr()
@@ -40,10 +44,10 @@ def main():
         same = "first" if ref is None else ("bitwise-equal" if out.tobytes() == ref.tobytes() else "DIFFERS max rel %.3g" % float(np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1.0))))
         if ref is None:
             ref = out.copy()
-        print("%-4s %-10s ns %d engine_ms %s width %d slots %d team %s fwd %.3f bwd %.3f GTEPS %.2f frac %.3f  %s" % (
+        print(os.environ.get("AB_LIB_TAG", "product") + " %-4s %-10s ns %d engine_ms %s width %d slots %d team %s fwd %.3f bwd %.3f GTEPS %.2f frac %.3f  %s sha %s" % (
             which, tag, ns, ["%.1f" % t for t in ts], st.get("batch_width", 0), st["n_slots"], st.get("team_size", "?"),
             st["frac_forward"], st["frac_backward"], st["edge_pairs"] / 2 / (min(ts) * 1e-3) / 1e9,
-            (24.0 * st["edge_pairs"] + 40.0 * st["reached_pairs"]) / (min(ts) * 1e-3) / 1e9 / 6547.2, same), flush=True)
+            (24.0 * st["edge_pairs"] + 40.0 * st["reached_pairs"]) / (min(ts) * 1e-3) / 1e9 / 6547.2, same, __import__('hashlib').sha1(out.tobytes()).hexdigest()[:10]), flush=True)
         for k, _ in pairs:
             os.environ.pop(k, None)
     dg.free()

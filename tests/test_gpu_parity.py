@@ -706,3 +706,28 @@ def test_erc_randomize_on_device_matches_the_fixtures_bit_for_bit(ctx, oracle, g
         assert a.adjacency() == b.adjacency() and a.rng_state() == b.rng_state()
         assert dg.n == n and dg.nnz == 2 * a.edge_count()
         dg.free()
+
+
+def test_path_counts_exact_on_larger_graphs(ctx, oracle):
+    """f64 shortest-path counts (sigma) from the engine's own level queues (pull, lane per source), exact while
+    they fit in f64 - on graphs far beyond the fixtures: an expander, a hub-heavy BA graph, a grid whose counts are
+    binomials (large but < 2^53), and a deep path (32-bit distance rows).  sigma never enters the load."""
+    side = 26                                                      # C(50, 25) ~ 1.26e14 < 2^53
+    grid = adj_from_edges(side * side, [(r * side + c, r * side + c + 1) for r in range(side) for c in range(side - 1)] +
+                          [(r * side + c, (r + 1) * side + c) for r in range(side - 1) for c in range(side)])
+    cases = [ne.gnm_scalable(1 << 15, 1 << 17, 9).export_csr(), ne.ba_scalable(20000, 4, 5, 2).export_csr(), csr_from_adj(grid),
+             csr_from_adj(adj_from_edges(400, [(i, i + 1) for i in range(399)]))]
+    for rp, col in cases:
+        n = len(rp) - 1
+        dg = ctx.upload(rp, col)
+        for s in (0, n // 2, n - 1):
+            dist, npred, sigma, bk = dg.bfs_debug(s)
+            rd, rn, rs, rb = oracle.bfs_debug(rp, col, s)
+            assert dist.tolist() == rd.tolist() and npred.tolist() == rn.tolist()
+            assert sigma.tolist() == rs.tolist()                  # bit-exact
+            assert close(bk, rb, REL)
+        dg.free()
+    import math
+    dg = ctx.upload(*csr_from_adj(grid))
+    assert dg.bfs_debug(0)[2][side * side - 1] == float(math.comb(2 * (side - 1), side - 1))
+    dg.free()
