@@ -49,6 +49,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #ifndef NEC_LEAF_MARKS
 #define NEC_LEAF_MARKS 1      // 0: A/B builds without the leaf marks of the backward pass
 #endif
@@ -278,6 +280,7 @@ vertex_load_engine(const EngineParams p) {
     constexpr bool kLeafMarks = NEC_LEAF_MARKS && sizeof(DistT) == 1 && kMode == 0;
     constexpr uint32_t kMaxLeafPred = 62;
     __shared__ double s_rcp[64];
+    __shared__ unsigned char s_klist[kWarps][64];      // backward: the live sources of the entry a warp is consuming
     if (kLeafMarks && threadIdx.x < 64) s_rcp[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
     __shared__ unsigned long long s_msum[kSrc];          // kMode 2: per source of the batch
     __shared__ uint32_t s_mreach[kSrc], s_mecc[kSrc];
@@ -610,22 +613,48 @@ vertex_load_engine(const EngineParams p) {
                 const uint32_t incl = warp_inclusive_scan(deg, lane);
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 const uint32_t off = incl - deg;
-                // running state of the entry whose row is being consumed (warp-uniform `cur`)
-                int cur = -1;
-                uint32_t cur_end = 0, npred[kH];
+                // COMPACT LANES.  While queue entry (w, mask) is being consumed, lane j works for the j-th LIVE source
+                // of the mask (and, for masks with more than 32 sources, also for the (j+32)-th): a batch's entries
+                // carry about a quarter of the batch's sources on an expander, so one lane per source of the batch
+                // would leave three lanes in four idle on every neighbour row.  The j-th set bit is found once per
+                // entry (ballot-style ranks through a 64-byte list in shared memory); every neighbour row then costs
+                // one distance-byte read, two compares and a predicated q load per lane.  Sums over a vertex's
+                // successors are still taken by ONE lane in adjacency order: results do not depend on the mapping.
+                int cur = -1;                                       // entry whose rows are being consumed (warp-uniform)
+                uint32_t cur_end = 0, c_cur = 0, npred[kH], ks[kH], succ_key[kH], pred_key[kH];
                 double acc[kH], my_total = 0.0;
 #pragma unroll
-                for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; }
+                for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; ks[h] = 0; succ_key[h] = 0x100u; pred_key[h] = 0x100u; }
 
+                auto begin_entry = [&]() {
+                    const Mask m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
+                    const uint32_t lo = (uint32_t)m_c;
+                    uint32_t hi = 0;
+                    if constexpr (kH == 2) hi = (uint32_t)(m_c >> 32);
+                    const uint32_t clo = __popc(lo);
+                    c_cur = clo + __popc(hi);
+                    __syncwarp();                                   // the previous entry's list has been read by every lane
+                    if ((lo >> lane) & 1u) s_klist[warp][__popc(lo & lane_lt)] = (unsigned char)lane;
+                    if (kH == 2 && ((hi >> lane) & 1u)) s_klist[warp][clo + __popc(hi & lane_lt)] = (unsigned char)(lane + 32);
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) {
+                        const bool on = (uint32_t)lane + 32u * h < c_cur;
+                        ks[h] = on ? (uint32_t)s_klist[warp][lane + 32 * h] : 0u;
+                        // lanes without a source compare against keys no byte (or 32-bit distance) can equal
+                        succ_key[h] = on ? (kLeafMarks ? succ_tag : d_succ) : 0xFFFFFF00u;
+                        pred_key[h] = on ? d_pred : 0xFFFFFF00u;
+                        acc[h] = 0.0; npred[h] = 0;
+                    }
+                };
                 auto finish_entry = [&]() {
                     const uint32_t w_c = __shfl_sync(0xFFFFFFFFu, w, cur);
-                    const Mask m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
                     double contrib = 0.0;
 #pragma unroll
                     for (int h = 0; h < kH; ++h) {
-                        const double bk = 1.0 + acc[h];
-                        if ((uint32_t)(m_c >> (h * 32 + lane)) & 1u) {
-                            const size_t at = (size_t)w_c * kSrc + h * 32 + lane;
+                        if ((uint32_t)lane + 32u * h < c_cur) {
+                            const double bk = 1.0 + acc[h];
+                            const size_t at = (size_t)w_c * kSrc + ks[h];
                             if constexpr (kLeafMarks) {
                                 // q values are positive, so acc == 0 <=> no successor <=> bk == 1 exactly
                                 const bool leaf = acc[h] == 0.0 && npred[h] <= kMaxLeafPred;
@@ -641,6 +670,43 @@ vertex_load_engine(const EngineParams p) {
                     }
                     const double tot = warp_sum(contrib);
                     if (lane == cur) my_total = tot;
+                };
+                // kRows neighbour rows of the current entry, starting at row r of the staged chunk, for kSlots
+                // source slots per lane: every q load of the group is issued before the first one is consumed
+                auto consume = [&](auto rows_tag, auto slots_tag, int buf, uint32_t r, uint32_t nrows) {
+                    constexpr int kRows = decltype(rows_tag)::value, kSlots = decltype(slots_tag)::value;
+                    double qv[kRows][kSlots];
+#pragma unroll
+                    for (int jj = 0; jj < kRows; ++jj) {
+                        if ((uint32_t)jj < nrows) {                 // warp-uniform
+                            const uint32_t xj = s_stage[warp][buf][r + jj].x;
+#pragma unroll
+                            for (int h = 0; h < kSlots; ++h) {
+                                uint32_t b;
+                                if constexpr (kStageRows) b = (uint32_t)s_rows[warp][buf][r + jj][ks[h]];
+                                else b = (uint32_t)dist[(size_t)xj * kSrc + ks[h]];
+                                bool succ;
+                                if constexpr (kLeafMarks) {
+                                    succ = (b & 0xC0u) == succ_key[h];
+                                    const uint32_t info = b & 0x3Fu;
+                                    qv[jj][h] = succ ? (info ? s_rcp[info] : __ldcg(&q[(size_t)xj * kSrc + ks[h]])) : 0.0;
+                                } else {
+                                    succ = b == succ_key[h];
+                                    qv[jj][h] = succ ? __ldcg(&q[(size_t)xj * kSrc + ks[h]]) : 0.0;
+                                }
+                                npred[h] += b == pred_key[h] ? 1u : 0u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < kSlots; ++h) qv[jj][h] = 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < kRows; ++jj)              // adjacency (CSR) order: fixes the rounding
+                        if ((uint32_t)jj < nrows) {
+#pragma unroll
+                            for (int h = 0; h < kSlots; ++h) acc[h] += qv[jj][h];
+                        }
                 };
 
                 // Flattened adjacency entries are consumed in chunks of 32.  Two-deep pipeline per warp:
@@ -689,57 +755,22 @@ vertex_load_engine(const EngineParams p) {
                     asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk sc's rows have landed (this lane's copies)
                     __syncwarp();                                          // ... and every other lane's
                     const uint32_t cnt = min(32u, total - t0);
-                    for (uint32_t c0 = 0; c0 < cnt; c0 += kUnrollB) {
-                        uint32_t dx[kUnrollB][kH];
-                        double qv[kUnrollB][kH];
-#pragma unroll
-                        for (int jj = 0; jj < kUnrollB; ++jj) {
-                            const Stage e = s_stage[warp][buf][(c0 + jj) & 31];   // broadcast read; mask 0 past the end
-#pragma unroll
-                            for (int h = 0; h < kH; ++h) {
-                                const bool act = (ST::half(e, h) >> lane) & 1u;
-                                if constexpr (kStageRows) {
-                                    // unconditional shared-memory read, then select: faster than a predicated read
-                                    const uint32_t raw = (uint32_t)s_rows[warp][buf][(c0 + jj) & 31][h * 32 + lane];
-                                    dx[jj][h] = act ? raw : kInf;
-                                } else dx[jj][h] = act ? (uint32_t)dist[(size_t)e.x * kSrc + h * 32 + lane] : kInf;
-                            }
+                    for (uint32_t r = 0; r < cnt;) {
+                        const uint32_t tt = t0 + r;
+                        if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start
+                            if (cur >= 0) finish_entry();
+                            do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
+                            begin_entry();
                         }
-                        uint32_t pred_bits[kH];                                  // bit jj: neighbour jj is a predecessor
-#pragma unroll
-                        for (int h = 0; h < kH; ++h) pred_bits[h] = 0;
-#pragma unroll
-                        for (int jj = 0; jj < kUnrollB; ++jj) {
-                            const uint32_t xj = s_stage[warp][buf][(c0 + jj) & 31].x;
-#pragma unroll
-                            for (int h = 0; h < kH; ++h) {
-                                if constexpr (kLeafMarks) {
-                                    // inactive lanes carry kInf = 0xFF, which only parity-1 tags could match: excluded
-                                    const uint32_t b = dx[jj][h];
-                                    const bool succ = (b & 0xC0u) == succ_tag && b != kInf;
-                                    const uint32_t info = b & 0x3Fu;
-                                    qv[jj][h] = succ ? (info ? s_rcp[info] : __ldcg(&q[(size_t)xj * kSrc + h * 32 + lane])) : 0.0;
-                                } else
-                                    qv[jj][h] = (dx[jj][h] == d_succ) ? q[(size_t)xj * kSrc + h * 32 + lane] : 0.0;
-                                pred_bits[h] |= (dx[jj][h] == d_pred ? 1u : 0u) << jj;
-                            }
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < kUnrollB; ++jj) {  // CSR order: fixes the rounding
-                            const uint32_t tt = t0 + c0 + jj;
-                            if (c0 + jj < cnt) {
-                                if (tt >= cur_end) {              // warp-uniform: next entry's row starts
-                                    if (cur >= 0) finish_entry();
-                                    do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
-#pragma unroll
-                                    for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; }
-                                }
-#pragma unroll
-                                for (int h = 0; h < kH; ++h) {
-                                    acc[h] += qv[jj][h];
-                                    npred[h] += (pred_bits[h] >> jj) & 1u;
-                                }
-                            }
+                        const uint32_t left = min(cur_end - tt, cnt - r);      // rows of this entry inside this chunk
+                        if (kH == 2 && c_cur > 32) {
+                            const uint32_t nrows = min(left, (uint32_t)(kUnroll / 2));
+                            consume(std::integral_constant<int, kUnroll / 2>{}, std::integral_constant<int, kH>{}, buf, r, nrows);
+                            r += nrows;
+                        } else {
+                            const uint32_t nrows = min(left, (uint32_t)kUnroll);
+                            consume(std::integral_constant<int, kUnroll>{}, std::integral_constant<int, 1>{}, buf, r, nrows);
+                            r += nrows;
                         }
                     }
                     __syncwarp();                                 // buffer `buf` may be refilled next iteration

@@ -29,6 +29,19 @@ def test_header_symbols_are_exported_and_bound(built):
     assert b"sm_100a" in lib.nec_version()
 
 
+def test_rust_shim_declares_every_header_function():
+    """rust/net_ensembles_cuda.rs cannot be compiled here (no rustc); at least its extern block must name every
+    function of the header, and nothing the header lacks."""
+    text = open(os.path.join(ROOT, "rust", "net_ensembles_cuda.rs")).read()
+    block = text[text.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    declared = set(re.findall(r"\bfn (nec_[a-z_0-9]+)\s*\(", block))
+    assert declared == set(_declared_functions()), declared ^ set(_declared_functions())
+    fields = re.findall(r"pub (\w+): (?:u64|u32|f32)", text[text.index("pub struct NecStats"):text.index('extern "C" {')])
+    from net_ensembles_b200 import _lib
+    assert fields == [name for name, _ in _lib.NecStats._fields_]
+
+
 def test_host_mirror_is_a_separate_library_without_cuda(built):
     """The graph / ensemble mirror (input producers) lives in libnec_host.so, which links neither the CUDA
     runtime nor the product library: harness code that only builds graphs (bench.py's CPU baseline arm) never
