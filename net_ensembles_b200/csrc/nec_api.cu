@@ -568,15 +568,26 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.n_sources = n_sources;
     ctx->stats.n_batches = n_sources;
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = nec::mid_smem_bytes(n, g->slab_w);
-    if (!ctx->mid_attr_set) {
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
-        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
-        ctx->mid_attr_set = true;
+    // CTA shape: 2 x 512 threads per SM, or - small graphs, whose levels hold a few hundred vertices - 8 x 128:
+    // a source's time is a chain of per-level latencies there, so sources in flight matter, not threads per source
+    uint32_t small_n = 4096;
+    if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
+    const bool small_ctas = n <= small_n;
+    const int threads = small_ctas ? nec::kMidThreadsSmall : nec::kMidThreads;
+    const size_t smem = nec::mid_smem_bytes(n, g->slab_w, threads);
+    {   // per device (a process may hold contexts on several devices): set on every call
+        const int big = (int)(227 * 1024 - 4096);
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
     int occ = 0;
-    if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8>, nec::kMidThreads, smem));
-    else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16>, nec::kMidThreads, smem));
+    if (small_ctas) {
+        if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8, nec::kMidThreadsSmall>, threads, smem));
+        else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16, nec::kMidThreadsSmall>, threads, smem));
+    } else {
+        if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8>, threads, smem));
+        else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16>, threads, smem));
+    }
     if (occ < 1) return fail(ctx, NEC_ECUDA, "mid engine cannot be resident for n=%u (%zu B shared memory)", n, smem);
     if (const char *env = getenv("NEC_MID_CTAS_PER_SM")) {       // profiling knob
         const int v = atoi(env);
@@ -621,8 +632,13 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
     if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (g->slab_w == 8) nec::mid_engine<8><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
-    else nec::mid_engine<16><<<slots, nec::kMidThreads, smem, ctx->stream>>>(p);
+    if (small_ctas) {
+        if (g->slab_w == 8) nec::mid_engine<8, nec::kMidThreadsSmall><<<slots, threads, smem, ctx->stream>>>(p);
+        else nec::mid_engine<16, nec::kMidThreadsSmall><<<slots, threads, smem, ctx->stream>>>(p);
+    } else {
+        if (g->slab_w == 8) nec::mid_engine<8><<<slots, threads, smem, ctx->stream>>>(p);
+        else nec::mid_engine<16><<<slots, threads, smem, ctx->stream>>>(p);
+    }
     NEC_CUDA(ctx, cudaGetLastError());
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     if (!mo) {
@@ -643,7 +659,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.kernel_launches = 2;
     ctx->stats.engine = 2;
     ctx->stats.team_size = 1;
-    ctx->stats.cta_threads = nec::kMidThreads;
+    ctx->stats.cta_threads = (uint32_t)threads;
     ctx->stats.n_slots = slots;
     ctx->stats.workspace_bytes = ctx->mid_bytes;
     for (uint32_t k = 0; k < n_sources; ++k) {
@@ -661,7 +677,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     ctx->stats.frac_reset = tot > 0 ? (float)(counters[4] / tot) : 0.f;
     ctx->stats.frac_forward = tot > 0 ? (float)(counters[5] / tot) : 0.f;
     ctx->stats.frac_backward = tot > 0 ? (float)(counters[6] / tot) : 0.f;
-    if (getenv("NEC_MID_VERBOSE")) fprintf(stderr, "[nec] mid engine: thread-0 time in levels of <= %d vertices: %.1f %% of CTA time\n", nec::kMidThreads, 100.0 * counters[7] / tot);
+    if (getenv("NEC_MID_VERBOSE")) fprintf(stderr, "[nec] mid engine: thread-0 time in levels of <= %d vertices: %.1f %% of CTA time\n", threads, 100.0 * counters[7] / tot);
     return NEC_OK;
 }
 
@@ -1503,7 +1519,10 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
                         ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
     if (mid_ok) {       // one source per CTA, two CTAs per SM
-        *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, std::min<uint64_t>(ns, 2ull * (uint32_t)ctx->prop.multiProcessorCount) * n_devices_of(ctx));
+        uint32_t small_n = 4096;
+        if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
+        const uint64_t per_sm = g->n <= small_n ? 8ull : 2ull;      // CTAs (= sources in flight) per SM, see run_sources_mid
+        *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, std::min<uint64_t>(ns, per_sm * (uint32_t)ctx->prop.multiProcessorCount) * n_devices_of(ctx));
         return NEC_OK;
     }
     BatchedPlan plan{};

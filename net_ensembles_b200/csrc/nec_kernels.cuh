@@ -51,6 +51,9 @@
 
 #include <type_traits>
 
+#ifndef NEC_Q_PREFETCH
+#define NEC_Q_PREFETCH 1      // backward pass: 0 no prefetch of a chunk's q values, 1 into L2, 2 into L1
+#endif
 #ifndef NEC_LEAF_MARKS
 #define NEC_LEAF_MARKS 1      // 0: A/B builds without the leaf marks of the backward pass
 #endif
@@ -748,13 +751,34 @@ vertex_load_engine(const EngineParams p) {
                 for (uint32_t sc = 0; sc < n_chunks; ++sc) {
                     const int buf = sc & 1;
                     const uint32_t t0 = sc * 32;
+                    const uint32_t cnt = min(32u, total - t0);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's rows have landed (this lane's copies)
+                    __syncwarp();                                          // ... and every other lane's
+                    if constexpr (kStageRows && NEC_Q_PREFETCH != 0) {
+                        // The consumption below pulls q in groups of a few rows, each group one dependent DRAM round
+                        // trip: the pass is bound by that latency, not by bytes or instructions.  So every q value the
+                        // chunk will pull is requested up front (prefetch: no register, no scoreboard) - all 32 rows'
+                        // requests are in flight together and the groups that follow find their values in L2.
+                        // One lane per source of the batch here (the staged mask says which are live): no per-entry state.
+                        for (uint32_t r = 0; r < cnt; ++r) {
+                            const Stage e = s_stage[warp][buf][r];
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) {
+                                const uint32_t b = (uint32_t)s_rows[warp][buf][r][h * 32 + lane];
+                                const bool act = (ST::half(e, h) >> lane) & 1u;
+                                const bool want = act && (kLeafMarks ? (b & 0xFFu) == succ_tag : b == d_succ);   // marked leaves carry their q
+                                if (want) {
+                                    const double *addr = &q[(size_t)e.x * kSrc + h * 32 + lane];
+                                    if (NEC_Q_PREFETCH == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+                                    else asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
+                                }
+                            }
+                        }
+                    }
                     s_stage[warp][buf ^ 1][lane] = st_next;       // chunk sc+1 (zeros past the end); buffer was drained at sc-1
                     __syncwarp();
                     stage_rows(buf ^ 1);
                     st_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : ST::stage(0u, (Mask)0);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk sc's rows have landed (this lane's copies)
-                    __syncwarp();                                          // ... and every other lane's
-                    const uint32_t cnt = min(32u, total - t0);
                     for (uint32_t r = 0; r < cnt;) {
                         const uint32_t tt = t0 + r;
                         if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start

@@ -84,10 +84,12 @@ struct MidParams {
 };
 
 // dynamic shared memory: dist | (claim bitmap, only with kMidAtomicClaims) | slab staging (chunk-major: [W/4][threads] x 16 B)
-__host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
+constexpr int kMidThreadsSmall = 128;     // small graphs: eight 128-thread CTAs per SM (levels hold a few hundred vertices at most;
+                                          // what counts is how many sources are in flight, not threads per source)
+__host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w, int threads = kMidThreads) {
     const size_t n_pad = ((size_t)n + 15) / 16 * 16;
     const size_t claim = kMidAtomicClaims ? (((size_t)n + 31) / 32 * 4 + 15) / 16 * 16 : 0;
-    return n_pad + claim + (size_t)kMidThreads * slab_w * 4;
+    return n_pad + claim + (size_t)threads * slab_w * 4;
 }
 
 // Adjacency "slab": one aligned row of W 32-bit words per vertex = its degree followed by its first
@@ -95,13 +97,13 @@ __host__ __device__ inline size_t mid_smem_bytes(uint32_t n, int slab_w) {
 // row_ptr -> col_idx pair of loads for all low-degree vertices.
 // Staging: thread t's 16-byte chunk k lives at stage[k * kMidThreads + t], so a warp's cp.async
 // writes and LDS.128 reads are 512 contiguous bytes (conflict-free).
-template <int W>
+template <int W, int kT>
 __device__ __forceinline__ void slab_prefetch(uint4 *stage_t, const uint4 *__restrict__ slab, uint32_t v) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_t);
     const uint4 *src = slab + (size_t)v * (W / 4);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * kMidThreads * i), "l"(src + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * kT * i), "l"(src + i) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -121,13 +123,13 @@ __device__ __forceinline__ uint32_t atoms_or_if(bool pred, uint32_t saddr, uint3
     return old;
 }
 
-template <int W>
-__global__ void __launch_bounds__(kMidThreads, 2)
+template <int W, int kT = kMidThreads>
+__global__ void __launch_bounds__(kT, kT == kMidThreads ? 2 : 8)
 mid_engine(const MidParams p) {
     extern __shared__ __align__(16) unsigned char mid_smem[];
-    constexpr int kWarps = kMidThreads / 32;
+    constexpr int kWarps = kT / 32;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
-    constexpr uint32_t kStride = kMidThreads;
+    constexpr uint32_t kStride = kT;
     constexpr uint32_t kSlabNbrs = W - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
@@ -159,7 +161,7 @@ mid_engine(const MidParams p) {
     auto read_stage = [&](uint32_t (&w)[W], bool valid) {
 #pragma unroll
         for (int k = 0; k < W / 4; ++k) {
-            const uint4 t = valid ? stage[(size_t)k * kMidThreads] : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 t = valid ? stage[(size_t)k * kT] : make_uint4(0u, 0u, 0u, 0u);
             w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
         }
     };
@@ -180,8 +182,8 @@ mid_engine(const MidParams p) {
         {
             uint4 *d16 = reinterpret_cast<uint4 *>(dist);
             const uint4 inf4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (uint32_t i = threadIdx.x; i < p.n_pad / 16; i += kMidThreads) d16[i] = inf4;
-            for (uint32_t i = threadIdx.x; i < claim_words; i += kMidThreads) claim[i] = 0;
+            for (uint32_t i = threadIdx.x; i < p.n_pad / 16; i += kT) d16[i] = inf4;
+            for (uint32_t i = threadIdx.x; i < claim_words; i += kT) claim[i] = 0;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -259,7 +261,7 @@ mid_engine(const MidParams p) {
             uint32_t i = lb + threadIdx.x;
             uint32_t v_cur = i < le ? __ldcs(&order[i]) : kNone;
             uint32_t v_nxt = i + kStride < le ? __ldcs(&order[i + kStride]) : kNone;
-            if (v_cur != kNone) slab_prefetch<W>(stage, p.slab, v_cur);
+            if (v_cur != kNone) slab_prefetch<W, kT>(stage, p.slab, v_cur);
             cp_async_commit();
             for (uint32_t wbase = lb + warp * 32; wbase < le; wbase += kStride, i += kStride) {
                 uint32_t row[W];
@@ -267,7 +269,7 @@ mid_engine(const MidParams p) {
                 read_stage(row, v_cur != kNone);
                 const uint32_t u = v_cur;
                 const uint32_t v_nn = i + 2 * kStride < le ? __ldcs(&order[i + 2 * kStride]) : kNone;
-                if (v_nxt != kNone && landed(row)) slab_prefetch<W>(stage, p.slab, v_nxt);
+                if (v_nxt != kNone && landed(row)) slab_prefetch<W, kT>(stage, p.slab, v_nxt);
                 cp_async_commit();
                 v_cur = v_nxt; v_nxt = v_nn;
 
@@ -355,7 +357,7 @@ mid_engine(const MidParams p) {
             // exact per-vertex sums from the distance vector (queue entries may contain duplicates)
             unsigned long long sum = 0;
             uint32_t cnt = 0;
-            for (uint32_t v = threadIdx.x; v < n; v += kMidThreads) {
+            for (uint32_t v = threadIdx.x; v < n; v += kT) {
                 const uint32_t d = dist[v];
                 if (d != 0xFFu) {
                     sum += d; cnt += 1;
@@ -524,12 +526,12 @@ mid_engine(const MidParams p) {
                 }
             };
             const uint32_t n2 = n & ~1u;
-            for (uint32_t base = 2 * threadIdx.x; base < n2; base += 8 * kMidThreads) {
+            for (uint32_t base = 2 * threadIdx.x; base < n2; base += 8 * kT) {
                 double2 qq[4], bb[4];
                 uint32_t dd[4], gg[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t v = base + u * 2 * kMidThreads;
+                    const uint32_t v = base + u * 2 * kT;
                     dd[u] = v < n2 ? (uint32_t)*reinterpret_cast<const uint16_t *>(dist + v) : 0xFFFFu;
                     const bool any = dd[u] != 0xFFFFu;
                     qq[u] = any ? *reinterpret_cast<const double2 *>(q + v) : make_double2(0.0, 0.0);
@@ -538,7 +540,7 @@ mid_engine(const MidParams p) {
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t v = base + u * 2 * kMidThreads;
+                    const uint32_t v = base + u * 2 * kT;
                     if (dd[u] != 0xFFFFu) {
                         one(v, dd[u] & 0xFFu, gg[u] & 0xFFu, qq[u].x, bb[u].x);
                         one(v + 1, dd[u] >> 8, gg[u] >> 8, qq[u].y, bb[u].y);

@@ -570,7 +570,10 @@ def test_cluster_teams_are_bitwise_identical_to_single_ctas(ctx, oracle, monkeyp
 def test_wave_size_matches_what_a_call_uses(ctx):
     sw = ne.SwEnsemble(4096, 0.1, 3)
     dg = sw.to_device(ctx)
-    assert dg.wave_size() == 296 and dg.wave_size(10) == 10           # mid engine: one source per CTA, two CTAs per SM
+    wave = dg.wave_size()
+    assert wave in (296, 1184) and dg.wave_size(10) == 10             # mid engine: one source per CTA; 2 x 512 or (small graphs) 8 x 128 threads per SM
+    dg.vertex_load_sources(np.arange(wave, dtype=np.uint32), True)
+    assert ctx.stats()["n_slots"] == wave and ctx.stats()["cta_threads"] == (128 if wave == 1184 else 512)
     dg.free()
     g = ne.gnm_scalable(200_000, 800_000, 5)                           # beyond the mid engine: batched
     rp, col = g.export_csr()
@@ -731,3 +734,21 @@ def test_path_counts_exact_on_larger_graphs(ctx, oracle):
     dg = ctx.upload(*csr_from_adj(grid))
     assert dg.bfs_debug(0)[2][side * side - 1] == float(math.comb(2 * (side - 1), side - 1))
     dg.free()
+
+
+def test_mid_engine_cta_shapes_agree(ctx, oracle, monkeypatch):
+    """Small graphs run the one-source-per-CTA engine with eight 128-thread CTAs per SM, larger ones with two
+    512-thread CTAs; same arithmetic, same per-source order: identical per-source values, loads equal to rounding
+    of the slot sums."""
+    for e in (ne.ErEnsembleC(1000, 4.0, 123_239_010), ne.SwEnsemble(3000, 0.1, 4), ne.ba_scalable(4000, 3, 4, 6)):
+        rp, col = e.export_csr()
+        dg = ctx.upload(rp, col)
+        monkeypatch.setenv("NEC_MID_SMALL_N", "0")
+        big = dg.vertex_load(False)
+        assert ctx.stats()["cta_threads"] == 512 and ctx.stats()["engine"] & 15 == 2
+        monkeypatch.setenv("NEC_MID_SMALL_N", "100000")
+        small = dg.vertex_load(False)
+        assert ctx.stats()["cta_threads"] == 128
+        monkeypatch.delenv("NEC_MID_SMALL_N")
+        assert close(small, big, 1e-12) and close(small, oracle.vertex_load(rp, col, False, threads=0), REL)
+        dg.free()

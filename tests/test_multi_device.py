@@ -55,7 +55,7 @@ def test_drop_in_call_batch_and_measures_on_two_devices(ctx2, oracle):
     ecc, sumd, reached = dg.distance_measures()
     recc, rsum, rreach = oracle.distance_measures(rp, col)
     assert ecc.tolist() == recc.tolist() and sumd.tolist() == rsum.tolist() and reached.tolist() == rreach.tolist()
-    assert dg.wave_size() == 2 * 296 or dg.wave_size() == 700
+    assert dg.wave_size() in (2 * 296, 700)
     dg.free()
     chains = [ne.ErEnsembleC(64, 4.0, 7 + g).export_csr() for g in range(37)]
     outs = ne.vertex_load_batch(ctx2, [(r.astype(np.uint32), c) for r, c in chains], True)
