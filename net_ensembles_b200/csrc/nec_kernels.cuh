@@ -52,10 +52,10 @@
 #include <type_traits>
 
 #ifndef NEC_Q_PREFETCH
-#define NEC_Q_PREFETCH 1      // backward pass: 0 no prefetch of a chunk's q values, 1 into L2, 2 into L1
+#define NEC_Q_PREFETCH 0      // backward pass: 0 no prefetch of a chunk's q values, 1 into L2, 2 into L1 (A/B: both lose 19-25 %)
 #endif
 #ifndef NEC_LEAF_MARKS
-#define NEC_LEAF_MARKS 1      // 0: A/B builds without the leaf marks of the backward pass
+#define NEC_LEAF_MARKS 0      // 1: leaf marks in the backward pass (A/B: 4-10 % slower although they halve the q loads)
 #endif
 
 namespace nec {
@@ -625,9 +625,10 @@ vertex_load_engine(const EngineParams p) {
                 // successors are still taken by ONE lane in adjacency order: results do not depend on the mapping.
                 int cur = -1;                                       // entry whose rows are being consumed (warp-uniform)
                 uint32_t cur_end = 0, c_cur = 0, npred[kH], ks[kH], succ_key[kH], pred_key[kH];
+                const double *qk[kH];                               // q + ks[h]: a neighbour's value sits at qk[h] + x * kSrc
                 double acc[kH], my_total = 0.0;
 #pragma unroll
-                for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; ks[h] = 0; succ_key[h] = 0x100u; pred_key[h] = 0x100u; }
+                for (int h = 0; h < kH; ++h) { acc[h] = 0.0; npred[h] = 0; ks[h] = 0; succ_key[h] = 0xFFFFFF00u; pred_key[h] = 0xFFFFFF00u; qk[h] = q; }
 
                 auto begin_entry = [&]() {
                     const Mask m_c = __shfl_sync(0xFFFFFFFFu, m, cur);
@@ -638,16 +639,24 @@ vertex_load_engine(const EngineParams p) {
                     c_cur = clo + __popc(hi);
                     __syncwarp();                                   // the previous entry's list has been read by every lane
                     if ((lo >> lane) & 1u) s_klist[warp][__popc(lo & lane_lt)] = (unsigned char)lane;
-                    if (kH == 2 && ((hi >> lane) & 1u)) s_klist[warp][clo + __popc(hi & lane_lt)] = (unsigned char)(lane + 32);
+                    if constexpr (kH == 2) {
+                        if (hi != 0 && ((hi >> lane) & 1u)) s_klist[warp][clo + __popc(hi & lane_lt)] = (unsigned char)(lane + 32);
+                    }
                     __syncwarp();
-#pragma unroll
-                    for (int h = 0; h < kH; ++h) {
-                        const bool on = (uint32_t)lane + 32u * h < c_cur;
-                        ks[h] = on ? (uint32_t)s_klist[warp][lane + 32 * h] : 0u;
-                        // lanes without a source compare against keys no byte (or 32-bit distance) can equal
-                        succ_key[h] = on ? (kLeafMarks ? succ_tag : d_succ) : 0xFFFFFF00u;
-                        pred_key[h] = on ? d_pred : 0xFFFFFF00u;
-                        acc[h] = 0.0; npred[h] = 0;
+                    // lanes without a source compare against keys no byte (or 32-bit distance) can equal
+                    const bool on0 = (uint32_t)lane < c_cur;
+                    ks[0] = on0 ? (uint32_t)s_klist[warp][lane] : 0u;
+                    succ_key[0] = on0 ? (kLeafMarks ? succ_tag : d_succ) : 0xFFFFFF00u;
+                    pred_key[0] = on0 ? d_pred : 0xFFFFFF00u;
+                    qk[0] = q + ks[0];
+                    acc[0] = 0.0; npred[0] = 0;
+                    if constexpr (kH == 2) {
+                        const bool on1 = (uint32_t)lane + 32u < c_cur;
+                        ks[1] = on1 ? (uint32_t)s_klist[warp][lane + 32] : 0u;
+                        succ_key[1] = on1 ? (kLeafMarks ? succ_tag : d_succ) : 0xFFFFFF00u;
+                        pred_key[1] = on1 ? d_pred : 0xFFFFFF00u;
+                        qk[1] = q + ks[1];
+                        acc[1] = 0.0; npred[1] = 0;
                     }
                 };
                 auto finish_entry = [&]() {
@@ -674,42 +683,41 @@ vertex_load_engine(const EngineParams p) {
                     const double tot = warp_sum(contrib);
                     if (lane == cur) my_total = tot;
                 };
-                // kRows neighbour rows of the current entry, starting at row r of the staged chunk, for kSlots
-                // source slots per lane: every q load of the group is issued before the first one is consumed
+                // kRows neighbour rows of the current entry, starting at row r of the staged chunk, for kSlots source
+                // slots per lane.  Straight-line code: every q load of the group is issued (predicated) before the first
+                // value is consumed; rows past the group's end (nrows < kRows) re-read row 31 with their predicates off
+                // and add an exact 0.0, which is cheaper than a branch per row.
                 auto consume = [&](auto rows_tag, auto slots_tag, int buf, uint32_t r, uint32_t nrows) {
                     constexpr int kRows = decltype(rows_tag)::value, kSlots = decltype(slots_tag)::value;
                     double qv[kRows][kSlots];
+                    const Stage *__restrict__ st = &s_stage[warp][buf][0];
+                    const unsigned char *__restrict__ rows0 = &s_rows[warp][buf][0][0];
 #pragma unroll
                     for (int jj = 0; jj < kRows; ++jj) {
-                        if ((uint32_t)jj < nrows) {                 // warp-uniform
-                            const uint32_t xj = s_stage[warp][buf][r + jj].x;
+                        const uint32_t rr = min(r + (uint32_t)jj, 31u);
+                        const bool valid = (uint32_t)jj < nrows;    // warp-uniform
+                        const uint32_t xj = st[rr].x;
 #pragma unroll
-                            for (int h = 0; h < kSlots; ++h) {
-                                uint32_t b;
-                                if constexpr (kStageRows) b = (uint32_t)s_rows[warp][buf][r + jj][ks[h]];
-                                else b = (uint32_t)dist[(size_t)xj * kSrc + ks[h]];
-                                bool succ;
-                                if constexpr (kLeafMarks) {
-                                    succ = (b & 0xC0u) == succ_key[h];
-                                    const uint32_t info = b & 0x3Fu;
-                                    qv[jj][h] = succ ? (info ? s_rcp[info] : __ldcg(&q[(size_t)xj * kSrc + ks[h]])) : 0.0;
-                                } else {
-                                    succ = b == succ_key[h];
-                                    qv[jj][h] = succ ? __ldcg(&q[(size_t)xj * kSrc + ks[h]]) : 0.0;
-                                }
-                                npred[h] += b == pred_key[h] ? 1u : 0u;
+                        for (int h = 0; h < kSlots; ++h) {
+                            uint32_t b;
+                            if constexpr (kStageRows) b = (uint32_t)rows0[rr * kSrc + ks[h]];
+                            else b = valid ? (uint32_t)dist[(size_t)xj * kSrc + ks[h]] : 0xFFFFFF01u;
+                            const double *pq = qk[h] + (size_t)xj * kSrc;
+                            if constexpr (kLeafMarks) {
+                                const bool succ = valid && (b & 0xC0u) == succ_key[h];
+                                const uint32_t info = b & 0x3Fu;
+                                qv[jj][h] = succ ? (info ? s_rcp[info] : __ldcg(pq)) : 0.0;
+                            } else {
+                                const bool succ = valid && b == succ_key[h];
+                                qv[jj][h] = succ ? __ldcg(pq) : 0.0;
                             }
-                        } else {
-#pragma unroll
-                            for (int h = 0; h < kSlots; ++h) qv[jj][h] = 0.0;
+                            if (valid && b == pred_key[h]) npred[h] += 1u;
                         }
                     }
 #pragma unroll
                     for (int jj = 0; jj < kRows; ++jj)              // adjacency (CSR) order: fixes the rounding
-                        if ((uint32_t)jj < nrows) {
 #pragma unroll
-                            for (int h = 0; h < kSlots; ++h) acc[h] += qv[jj][h];
-                        }
+                        for (int h = 0; h < kSlots; ++h) acc[h] += qv[jj][h];
                 };
 
                 // Flattened adjacency entries are consumed in chunks of 32.  Two-deep pipeline per warp:
@@ -791,10 +799,13 @@ vertex_load_engine(const EngineParams p) {
                             const uint32_t nrows = min(left, (uint32_t)(kUnroll / 2));
                             consume(std::integral_constant<int, kUnroll / 2>{}, std::integral_constant<int, kH>{}, buf, r, nrows);
                             r += nrows;
-                        } else {
+                        } else if (left > (uint32_t)(kUnroll / 2)) {
                             const uint32_t nrows = min(left, (uint32_t)kUnroll);
                             consume(std::integral_constant<int, kUnroll>{}, std::integral_constant<int, 1>{}, buf, r, nrows);
                             r += nrows;
+                        } else {                                  // a short tail: the half-size group wastes fewer predicated-off rows
+                            consume(std::integral_constant<int, kUnroll / 2>{}, std::integral_constant<int, 1>{}, buf, r, left);
+                            r += left;
                         }
                     }
                     __syncwarp();                                 // buffer `buf` may be refilled next iteration
