@@ -570,7 +570,8 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     // CTA shape: 2 x 512 threads per SM, or - small graphs, whose levels hold a few hundred vertices - 8 x 128:
     // a source's time is a chain of per-level latencies there, so sources in flight matter, not threads per source
-    uint32_t small_n = 4096;
+    // (same-box A/B on small-world graphs: 1.94x at n = 2048, 1.74x at 4096, 1.50x at 8192, 1.14x at 16384)
+    uint32_t small_n = 16384;
     if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
     const bool small_ctas = n <= small_n;
     const int threads = small_ctas ? nec::kMidThreadsSmall : nec::kMidThreads;
@@ -1519,7 +1520,7 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
                         ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
     if (mid_ok) {       // one source per CTA, two CTAs per SM
-        uint32_t small_n = 4096;
+        uint32_t small_n = 16384;
         if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
         const uint64_t per_sm = g->n <= small_n ? 8ull : 2ull;      // CTAs (= sources in flight) per SM, see run_sources_mid
         *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, std::min<uint64_t>(ns, per_sm * (uint32_t)ctx->prop.multiProcessorCount) * n_devices_of(ctx));
