@@ -80,12 +80,16 @@ int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
 /* Engine selection (tests and profiling; the default 0 chooses by graph size):
  *   NEC_ENGINE_AUTO    0  n in [64, 180000]: one source per CTA, per-source state in shared
- *                         memory; otherwise the batched engine (32 or 64 sources per CTA)
- *   NEC_ENGINE_BATCHED 1  always the batched engine
- *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 180000 */
+ *                         memory; n > 180000: the compact batched engine (64 or 128 sources per
+ *                         batch, a thread-block cluster per batch); n < 64: the source-minor
+ *                         batched engine (32 or 64 sources per CTA)
+ *   NEC_ENGINE_BATCHED 1  always the source-minor batched engine
+ *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 180000
+ *   NEC_ENGINE_WIDE    3  the compact batched engine whatever n */
 #define NEC_ENGINE_AUTO 0
 #define NEC_ENGINE_BATCHED 1
 #define NEC_ENGINE_MID 2
+#define NEC_ENGINE_WIDE 3
 int nec_set_engine(nec_ctx *ctx, int engine);
 
 /* Upload one graph (H2D copy of the CSR; validates row_ptr monotonicity and
@@ -219,8 +223,9 @@ typedef struct nec_stats {
     float frac_backward;      /* ... in the backward (accumulation) pass (clock64, summed over CTAs) */
     uint64_t workspace_bytes; /* scratch arena in use */
     uint32_t engine;          /* traversal kernel that ran: 1 batched (vertex_load_engine), 2 mid (mid_engine),
-                                 3 small-graph batch (small_graph_kernel); batched|mid<<4 if mid handed sources back */
-    uint32_t batch_width;     /* sources per batch of the batched engine in this call: 32 or 64 (0: engine not used) */
+                                 3 small-graph batch (small_graph_kernel), 4 compact batched (wide_engine);
+                                 first | second << 4 if one engine handed sources to another (1 | 2 << 4, 4 | 1 << 4) */
+    uint32_t batch_width;     /* sources per batch of the batched engines in this call: 32, 64 or 128 (0: not used) */
     uint32_t team_size;       /* batched engine: CTAs per batch slot (thread-block cluster size; 1 = one CTA per slot) */
     uint32_t cta_threads;     /* threads per CTA of the traversal kernel that ran */
     uint32_t pull_levels;     /* batched engine: (batch, level) expansions done in pull direction ... */

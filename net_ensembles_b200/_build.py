@@ -17,7 +17,7 @@ HOST_SOURCES = [os.path.join(PKG, "csrc", "host", "host_api.cpp")]
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "nec_api.cu"), os.path.join(PKG, "csrc", "host", "host_bridge.cpp")]
 CUDA_DEPS = CUDA_SOURCES + HOST_HEADERS + [
     os.path.join(PKG, "csrc", "nec_kernels.cuh"), os.path.join(PKG, "csrc", "nec_small.cuh"),
-    os.path.join(PKG, "csrc", "nec_mid.cuh"), os.path.join(PKG, "csrc", "nec_chain.cuh"), os.path.join(PKG, "csrc", "nec_multi.hpp"),
+    os.path.join(PKG, "csrc", "nec_mid.cuh"), os.path.join(PKG, "csrc", "nec_wide.cuh"), os.path.join(PKG, "csrc", "nec_sample.cuh"), os.path.join(PKG, "csrc", "nec_chain.cuh"), os.path.join(PKG, "csrc", "nec_multi.hpp"),
     os.path.join(ROOT, "include", "net_ensembles_cuda.h"),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -23,6 +23,7 @@
 #include "nec_chain.cuh"
 #include "nec_sample.cuh"
 #include "nec_mid.cuh"
+#include "nec_wide.cuh"
 
 namespace {
 
@@ -40,6 +41,19 @@ struct Arena {                       // per-slot scratch of the batched engine
     uint8_t *mask = nullptr; size_t mask_stride = 0;    // bytes per slot
     double *bslot = nullptr; size_t bslot_stride = 0;
     uint32_t *queue_v = nullptr; uint8_t *queue_m = nullptr; size_t queue_stride = 0;   // entries per slot
+    uint32_t *lvl = nullptr; size_t lvl_stride = 0;
+};
+
+struct WideArena {                   // per-slot scratch of the compact (wide) engine, nec_wide.cuh
+    void *base = nullptr;
+    size_t bytes = 0;
+    uint32_t n = 0, n_slots = 0, kw = 0, max_levels = 0;
+    size_t qcap = 0;
+    uint8_t *rec = nullptr;  size_t rec_stride = 0;      // bytes per slot
+    uint8_t *lr = nullptr;   size_t lr_stride = 0;       // bytes per slot
+    double *qc = nullptr;    size_t qc_stride = 0;       // doubles per slot
+    double *bslot = nullptr; size_t bslot_stride = 0;
+    uint32_t *queue_v = nullptr, *queue_p = nullptr; uint8_t *queue_m = nullptr; size_t queue_stride = 0;
     uint32_t *lvl = nullptr; size_t lvl_stride = 0;
 };
 
@@ -65,6 +79,8 @@ struct nec_ctx {
     std::string err;
     uint64_t ws_limit = 0;
     Arena arena;
+    WideArena wide;
+    int wide_cap[2][2][9];                            // resident clusters per (width 64/128, CTA 512/1024 threads, team size); -1 = not asked yet
     // small device buffers reused across calls
     uint32_t *d_sources = nullptr; size_t d_sources_cap = 0;
     uint8_t *d_status = nullptr;   size_t d_status_cap = 0;
@@ -154,7 +170,7 @@ int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slot
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     size_t free_b = 0, total_b = 0;
     NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + ctx->arena.bytes) * 0.8);
+    const size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + ctx->arena.bytes + ctx->wide.bytes) * 0.8);
     // queue capacity: every vertex can sit on at most 32 (64) distinct levels of one batch
     size_t qcap = (size_t)n * ksrc + ksrc;
     uint32_t slots = want_slots;
@@ -175,6 +191,11 @@ int plan_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slot
 // Build (or reuse) the arena for (n, distance width, wanted slots).
 int ensure_arena(nec_ctx *ctx, uint32_t n, uint32_t dist_bytes, uint32_t want_slots, uint32_t ksrc = nec::kLanes, bool full_queue = false) {
     Arena &a = ctx->arena;
+    if (ctx->wide.base) {                // one traversal arena at a time: both are sized from the free memory
+        NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->wide.base);
+        ctx->wide = WideArena{};
+    }
     const uint32_t max_levels = dist_bytes == 1 ? 254u : n + 1;
     ArenaPlan plan{};
     int prc = plan_arena(ctx, n, dist_bytes, want_slots, ksrc, plan, full_queue);
@@ -300,6 +321,7 @@ int engine_occupancy(nec_ctx *ctx) {
     if (o8 < 1 || o32 < 1) return fail(ctx, NEC_ECUDA, "engine kernel cannot be resident (occupancy %d/%d)", o8, o32);
     ctx->occ_u8 = o8; ctx->occ_u32 = o32;
     for (auto &row : ctx->team_cap) for (int &c : row) c = -1;
+    for (auto &a : ctx->wide_cap) for (auto &row : a) for (int &c : row) c = -1;
     return NEC_OK;
 }
 
@@ -558,6 +580,222 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
     return NEC_OK;
 }
 
+// ---- compact (wide) engine, nec_wide.cuh ------------------------------------------------------------------------
+size_t wide_per_slot_bytes(uint32_t n, uint32_t kw, size_t qcap, uint32_t max_levels) {
+    const size_t qpitch = align_up(qcap, 64);
+    size_t b = 0;
+    b += align_up((size_t)n * (kw / 2), 256);                       // forward records
+    b += align_up((size_t)n * kw, 256);                             // level records: 4 slots of kw / 4 bytes
+    b += align_up(((size_t)n * kw + 64) * sizeof(double), 256);     // compact q runs
+    b += align_up((size_t)n * sizeof(double), 256);                 // private partial load
+    b += qpitch * 4 * 2 + qpitch * (kw / 8);                        // queue: vertex, position, mask
+    b += align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);
+    return b;
+}
+
+template <int kW, int kThreads>
+cudaLaunchConfig_t wide_config(cudaLaunchAttribute *attr, uint32_t slots, uint32_t team, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(slots * team);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = nec::wide_smem_bytes<kW, kThreads>();
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+template <int kW, int kThreads>
+int wide_capacity_t(uint32_t team) {
+    auto kern = nec::wide_engine<kW, kThreads>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::wide_smem_bytes<kW, kThreads>()) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = wide_config<kW, kThreads>(attr, 1, team, nullptr);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int wide_capacity(nec_ctx *ctx, uint32_t kw, uint32_t threads, uint32_t team) {
+    int &cached = ctx->wide_cap[kw == 128][threads == 1024][team];
+    if (cached < 0)
+        cached = kw == 128 ? (threads == 1024 ? wide_capacity_t<128, 1024>(team) : wide_capacity_t<128, 512>(team))
+                           : (threads == 1024 ? wide_capacity_t<64, 1024>(team) : wide_capacity_t<64, 512>(team));
+    return cached;
+}
+template <int kW, int kThreads>
+int launch_wide_t(nec_ctx *ctx, const nec::WideParams &p, uint32_t slots, uint32_t team) {
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = wide_config<kW, kThreads>(attr, slots, team, ctx->stream);
+    NEC_CUDA(ctx, cudaFuncSetAttribute(nec::wide_engine<kW, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));   // per device
+    NEC_CUDA(ctx, cudaLaunchKernelEx(&cfg, nec::wide_engine<kW, kThreads>, p));
+    return NEC_OK;
+}
+
+// How the wide engine runs a call: batch width, CTA shape, resident slots and CTAs per slot.
+struct WidePlan { uint32_t kw, threads, slots, team, max_levels; size_t qcap, per_slot; };
+int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + ctx->arena.bytes + ctx->wide.bytes) * 0.8);
+    uint32_t threads = 1024;
+    if (const char *env = getenv("NEC_WIDE_THREADS")) threads = atoi(env) == 512 ? 512u : 1024u;
+    const uint32_t ctas_total = threads == 1024 ? sms : 2 * sms;
+    const uint32_t max_levels = n;
+    // queue entries per vertex the slot has room for: a vertex sits on a handful of distinct levels within one batch
+    // on the graphs this engine is meant for; batches that need more are handed to the source-minor engine
+    size_t per_vertex = 12;
+    if (const char *env = getenv("NEC_WIDE_QUEUE")) per_vertex = (size_t)std::max(1, atoi(env));
+    WidePlan best{};
+    double best_cost = 1e300;
+    for (uint32_t kw : {128u, 64u}) {
+        if (const char *env = getenv("NEC_WIDE_WIDTH")) { if ((uint32_t)atoi(env) != kw) continue; }
+        if ((uint64_t)n * kw + kw >= 0xFFFFFFFFull) continue;           // 32-bit positions and queue indices
+        const size_t qcap = std::min((size_t)n * kw + kw, (size_t)n * per_vertex + kw);
+        const size_t ps = wide_per_slot_bytes(n, kw, qcap, max_levels);
+        const uint32_t n_batches = (n_sources + kw - 1) / kw;
+        uint32_t slots = (uint32_t)std::min<size_t>(std::min<uint32_t>(n_batches, ctas_total), budget / ps);
+        if (slots == 0) continue;
+        uint32_t team = std::min<uint32_t>(8u, std::max<uint32_t>(1u, ctas_total / slots));
+        if (const char *env = getenv("NEC_WIDE_TEAM")) team = (uint32_t)std::min(8, std::max(1, atoi(env)));
+        int cap = 0;
+        for (; team >= 1; --team) {                                       // clusters are placed per GPC: ask how many fit
+            cap = wide_capacity(ctx, kw, threads, team);
+            if (cap > 0) break;
+        }
+        if (cap <= 0) continue;
+        slots = std::min<uint32_t>(slots, (uint32_t)cap);
+        // relative cost: waves x time of one batch; a batch's work grows slower than its width (the forward pass and
+        // the row traffic are per batch), and more threads per batch finish it sooner (~ threads^0.75 measured)
+        const double waves = (double)((n_batches + slots - 1) / slots);
+        const double cost = waves * (kw == 128 ? 1.45 : 1.0) / pow((double)team * threads / 512.0, 0.75);
+        if (cost < best_cost) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps}; }
+    }
+    if (best.slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one wide-engine slot for n=%u", budget, n);
+    out = best;
+    return NEC_OK;
+}
+
+int ensure_wide_arena(nec_ctx *ctx, uint32_t n, const WidePlan &pl) {
+    WideArena &a = ctx->wide;
+    if (ctx->arena.base) {                  // one traversal arena at a time
+        NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->arena.base);
+        ctx->arena = Arena{};
+    }
+    if (a.base && a.n == n && a.kw == pl.kw && a.n_slots >= pl.slots && a.qcap == pl.qcap && a.max_levels == pl.max_levels) return NEC_OK;
+    if (a.base) { NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(a.base); }
+    a = WideArena{};
+    const uint32_t slots = pl.slots, kw = pl.kw;
+    const size_t bytes = pl.per_slot * slots;
+    cudaError_t e = cudaMalloc(&a.base, bytes);
+    if (e != cudaSuccess) { a = WideArena{}; return fail(ctx, NEC_ENOMEM, "cudaMalloc(%zu B wide-engine workspace) failed: %s", bytes, cudaGetErrorString(e)); }
+    a.bytes = bytes; a.n = n; a.n_slots = slots; a.kw = kw; a.qcap = pl.qcap; a.max_levels = pl.max_levels;
+    uint8_t *p = (uint8_t *)a.base;
+    auto carve = [&](size_t per_slot) { uint8_t *r = p; p += align_up(per_slot, 256) * slots; return r; };
+    const size_t qpitch = align_up(pl.qcap, 64);
+    a.rec = carve((size_t)n * (kw / 2));                           a.rec_stride = align_up((size_t)n * (kw / 2), 256);
+    a.lr = carve((size_t)n * kw);                                  a.lr_stride = align_up((size_t)n * kw, 256);
+    a.qc = (double *)carve(((size_t)n * kw + 64) * 8);             a.qc_stride = align_up(((size_t)n * kw + 64) * 8, 256) / 8;
+    a.bslot = (double *)carve((size_t)n * 8);                      a.bslot_stride = align_up((size_t)n * 8, 256) / 8;
+    a.queue_v = (uint32_t *)carve(qpitch * 4);                     a.queue_stride = qpitch;
+    a.queue_p = (uint32_t *)carve(qpitch * 4);
+    a.queue_m = carve(qpitch * (kw / 8));
+    a.lvl = (uint32_t *)carve(((size_t)pl.max_levels + 2) * 4);    a.lvl_stride = align_up(((size_t)pl.max_levels + 2) * 4, 256) / 4;
+    return NEC_OK;
+}
+
+// Wide engine: partial load of `n_sources` sources into device vector d_out (n doubles).  Batches it cannot hold
+// (level queue beyond the slot's room) are re-run by the source-minor engine, never approximated.
+int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources, int include_endpoints, double *d_out) {
+    ctx->stats = nec_stats{};
+    ctx->stats.n_sources = n_sources;
+    const uint32_t n = g->n;
+    NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+    WidePlan pl{};
+    int rc = plan_wide(ctx, n, n_sources, pl);
+    if (rc != NEC_OK) return rc;
+    const uint32_t kw = pl.kw, n_batches = (n_sources + kw - 1) / kw;
+    if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_status, ctx->d_status_cap, n_batches)) != NEC_OK) return rc;
+    if ((rc = ensure_wide_arena(ctx, n, pl)) != NEC_OK) return rc;
+    const WideArena &a = ctx->wide;
+    const uint32_t slots = pl.slots;
+    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, n_batches, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(a.bslot, 0, a.bslot_stride * sizeof(double) * slots, ctx->stream));
+    nec::WideParams p{};
+    p.n = n; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx;
+    p.sources = ctx->d_sources; p.n_sources = n_sources; p.work_list = nullptr; p.n_work = n_batches;
+    p.include_endpoints = include_endpoints;
+    p.pull_mode = ctx->pull_mode;
+    if (const char *env = getenv("NEC_PULL")) p.pull_mode = (uint32_t)std::min(2, std::max(0, atoi(env)));
+    p.avg_deg = (uint32_t)std::max<uint64_t>(1, (g->nnz + g->n - 1) / std::max<uint32_t>(g->n, 1u));
+    p.rec_base = a.rec; p.rec_stride = a.rec_stride;
+    p.lr_base = a.lr; p.lr_stride = a.lr_stride;
+    p.qc_base = a.qc; p.qc_stride = a.qc_stride;
+    p.bslot_base = a.bslot; p.bslot_stride = a.bslot_stride;
+    p.queue_v_base = a.queue_v; p.queue_m_base = a.queue_m; p.queue_p_base = a.queue_p; p.queue_stride = a.queue_stride; p.queue_cap = a.qcap;
+    p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride; p.max_levels = a.max_levels;
+    p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, 512>(ctx, p, slots, pl.team);
+    else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, 512>(ctx, p, slots, pl.team);
+    if (rc != NEC_OK) return rc;
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
+    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
+    NEC_CUDA(ctx, cudaGetLastError());
+    NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    std::vector<uint8_t> status(n_batches);
+    unsigned long long counters[8];
+    NEC_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status, n_batches, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    nec_stats st{};
+    st.n_sources = n_sources; st.n_batches = n_batches; st.batch_width = kw; st.n_slots = slots; st.team_size = pl.team; st.cta_threads = pl.threads;
+    st.workspace_bytes = a.bytes; st.kernel_launches = 2; st.engine = 4;
+    float ms = 0.f;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    st.kernel_ms = ms;
+    NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid));
+    st.engine_ms = ms;
+    st.pull_levels = (uint32_t)(counters[7] >> 32); st.push_levels = (uint32_t)counters[7];
+    st.reached_pairs = counters[0]; st.edge_pairs = counters[1]; st.vertex_visits = counters[2]; st.max_depth = (uint32_t)counters[3];
+    {
+        const double tot = (double)(counters[4] + counters[5] + counters[6]);
+        st.frac_reset = tot > 0 ? (float)(counters[4] / tot) : 0.f;
+        st.frac_forward = tot > 0 ? (float)(counters[5] / tot) : 0.f;
+        st.frac_backward = tot > 0 ? (float)(counters[6] / tot) : 0.f;
+    }
+    std::vector<uint32_t> redo;                     // sources of the batches the slot could not hold
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        if (status[b] == nec::kDone) continue;
+        if (status[b] != nec::kQueueOverflow && status[b] != nec::kTooDeep)
+            return fail(ctx, NEC_EINTERNAL, "wide engine: batch %u was not processed (status %u)", b, (unsigned)status[b]);
+        for (uint32_t k = b * kw; k < std::min<uint64_t>((uint64_t)(b + 1) * kw, n_sources); ++k) redo.push_back(h_sources[k]);
+        st.requeued_batches++;
+    }
+    if (!redo.empty()) {
+        if ((rc = grow(ctx, ctx->d_tmp, ctx->d_tmp_cap, n)) != NEC_OK) return rc;
+        rc = run_sources_batched(ctx, g, redo.data(), (uint32_t)redo.size(), include_endpoints, ctx->d_tmp, false, nullptr, nullptr, nullptr);
+        if (rc != NEC_OK) return rc;
+        nec::add_into_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_out, ctx->d_tmp, n);
+        NEC_CUDA(ctx, cudaGetLastError());
+        const nec_stats second = ctx->stats;
+        st.reached_pairs += second.reached_pairs; st.edge_pairs += second.edge_pairs; st.vertex_visits += second.vertex_visits;
+        st.max_depth = std::max(st.max_depth, second.max_depth);
+        st.kernel_launches += second.kernel_launches + 1;
+        st.kernel_ms += second.kernel_ms; st.engine_ms += second.engine_ms;
+        st.wide_batches += second.wide_batches;
+        st.engine = 4u | (1u << 4);
+        st.workspace_bytes = std::max(st.workspace_bytes, second.workspace_bytes);
+    }
+    ctx->stats = st;
+    return NEC_OK;
+}
+
 // One-source-per-CTA engine (nec_mid.cuh).  Sources it hands back (too deep / predecessor
 // count overflow) are appended to `fallback`.
 int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
@@ -686,10 +924,19 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
 // engine; everything else (and whatever that engine hands back) takes the batched engine.
 int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
+    if (const char *env = getenv("NEC_L2_FETCH")) {       // A/B knob: L2 fetch granularity hint (32 / 64 / 128 B)
+        NEC_CUDA(ctx, cudaSetDevice(ctx->device));
+        NEC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env)));
+    }
     for (uint32_t k = 0; k < n_sources; ++k)
         if (h_sources[k] >= g->n) return fail(ctx, NEC_EINVAL, "source %u (index %u) out of range for n=%u", h_sources[k], k, g->n);
-    const bool mid_ok = !debug && g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u && n_sources > 0 && ctx->force_engine != 1 &&
+    const bool mid_ok = !debug && g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u && n_sources > 0 && ctx->force_engine != 1 && ctx->force_engine != 3 &&
                         (g->n >= nec::kMidMinN || ctx->force_engine == 2) && g->n > 0;
+    // large graphs (and whatever a test forces): the compact engine; tiny graphs, debug planes: the source-minor one
+    bool wide_ok = !debug && !mid_ok && n_sources > 0 && g->n > 0 && (ctx->force_engine == 3 || (ctx->force_engine == 0 && g->n > nec::kMidMaxN)) &&
+                   (uint64_t)g->n * 64 + 64 < 0xFFFFFFFFull;
+    if (const char *env = getenv("NEC_WIDE")) { if (atoi(env) == 0 && ctx->force_engine != 3) wide_ok = false; }
+    if (wide_ok) return run_sources_wide(ctx, g, h_sources, n_sources, include_endpoints, d_out);
     if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
     std::vector<uint32_t> fallback;
     int rc = run_sources_mid(ctx, g, h_sources, n_sources, include_endpoints, d_out, fallback);
@@ -929,6 +1176,7 @@ void nec_destroy(nec_ctx *ctx) {
     ctx->peers.clear();
     cudaSetDevice(ctx->device);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->wide.base) cudaFree(ctx->wide.base);
     if (ctx->d_sources) cudaFree(ctx->d_sources);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
@@ -957,7 +1205,7 @@ int nec_set_stream(nec_ctx *ctx, void *cuda_stream) {
 }
 
 int nec_set_engine(nec_ctx *ctx, int engine) {
-    if (!ctx || engine < 0 || engine > 2) return NEC_EINVAL;
+    if (!ctx || engine < 0 || engine > 3) return NEC_EINVAL;
     ctx->force_engine = engine;
     for (nec_ctx *pc : ctx->peers) pc->force_engine = engine;
     return NEC_OK;
@@ -1518,12 +1766,21 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t ns = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, n_sources_total / n_devices_of(ctx)), 0xFFFFFFFFull);   // per device
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
-                        ctx->force_engine != 1 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
+                        ctx->force_engine != 1 && ctx->force_engine != 3 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
     if (mid_ok) {       // one source per CTA, two CTAs per SM
         uint32_t small_n = 16384;
         if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
         const uint64_t per_sm = g->n <= small_n ? 8ull : 2ull;      // CTAs (= sources in flight) per SM, see run_sources_mid
         *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, std::min<uint64_t>(ns, per_sm * (uint32_t)ctx->prop.multiProcessorCount) * n_devices_of(ctx));
+        return NEC_OK;
+    }
+    bool wide_ok = (ctx->force_engine == 3 || (ctx->force_engine == 0 && g->n > nec::kMidMaxN)) && (uint64_t)g->n * 64 + 64 < 0xFFFFFFFFull;
+    if (const char *env = getenv("NEC_WIDE")) { if (atoi(env) == 0 && ctx->force_engine != 3) wide_ok = false; }
+    if (wide_ok) {
+        WidePlan wp{};
+        const int rcw = plan_wide(ctx, g->n, ns, wp);
+        if (rcw != NEC_OK) return rcw;
+        *sources_per_wave = (uint32_t)std::min<uint64_t>(n_sources_total, (uint64_t)wp.slots * wp.kw * n_devices_of(ctx));
         return NEC_OK;
     }
     BatchedPlan plan{};

@@ -1,0 +1,639 @@
+// Compact batched engine ("wide" engine) for large graphs: vertex_load of B = 64 or 128 sources per batch with
+// the backward pass working on COMPACT per-entry state instead of source-minor rows.
+//
+// Same quantity as nec_kernels.cuh (reference: src/generic_graph/generic_graph.rs:1310-1385, pull form):
+//   bk_s(w) = 1 + sum_{x: w in P_s(x)} bk_s(x)/|P_s(x)|,   b[v] += bk_s(v) (- 1 if !include_endpoints).
+//
+// Why another layout.  ncu on the source-minor engine (profiles/r2_batched_compact_summary.txt) shows the GPU
+// moving 4.5 TB/s of random 32-byte sectors, each costing a 64-byte DRAM burst: per (queue entry, neighbour) row a
+// 64 B distance row plus ~4 scattered sectors of the 512 B q row of the neighbour, and q stores that fill a third
+// of every sector they dirty.  Here
+//   * a queue entry (vertex w on level l with source mask M) owns a CONTIGUOUS run of popc(M) doubles in `qc`
+//     (position assigned by a prefix sum when the level is prepared): q stores are dense and coalesced, and a
+//     puller finds the values of a neighbour's sources packed in a few adjacent 64 B blocks;
+//   * what a puller needs to know about neighbour x is not x's distance row but two masks: M_{l+1}(x) (sources
+//     for which x is one level deeper: successors; their rank in the mask is the index into x's run) and
+//     M_{l-1}(x) (predecessors, counted).  They live in a per-vertex LEVEL RECORD of four slots (level mod 4,
+//     each {mask, position, level tag}), arranged so that the slots of levels l-1 and l+1 share one aligned
+//     64 B (B = 128) or 32 B (B = 64) block: ONE DRAM burst per row, whatever the batch width;
+//   * the forward pass writes no distance rows at all (levels are recorded by the queues only), which also
+//     removes the depth limit of byte distances;
+//   * B = 128 halves the forward pass and the row traffic per source again and fills the lanes: an entry of the
+//     widest level carries ~70 of 128 sources.
+// Lanes are compact as before (lane j = j-th live source of the entry being consumed, up to B/32 per lane), one
+// lane sums one (vertex, source) value over the neighbours in adjacency order: results do not depend on the
+// mapping, on positions or on the team size, and are bit-reproducible run to run.
+//
+// A slot (one batch in flight) is run by a TEAM: the CTAs of one thread-block cluster (1..8), which share the
+// queue tail, position counter and failure flag through rank 0's shared memory and meet at cluster barriers.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "nec_kernels.cuh"
+
+namespace nec {
+
+struct WideParams {
+    uint32_t n;
+    const uint32_t *__restrict__ row_ptr;
+    const uint32_t *__restrict__ col_idx;
+    const uint32_t *__restrict__ sources;
+    uint32_t n_sources;
+    const uint32_t *__restrict__ work_list;   // batch ids to run (nullptr: 0..n_work-1)
+    uint32_t n_work;
+    int include_endpoints;
+    uint32_t pull_mode;                        // 0 push only, 1 cost model, 2 pull only
+    uint32_t avg_deg;
+    // per-slot arenas (slot = cluster index)
+    uint8_t *rec_base;   size_t rec_stride;    // bytes: n forward records {seen, next[even], next[odd], claim}
+    uint8_t *lr_base;    size_t lr_stride;     // bytes: n level records (4 slots {mask, position, tag})
+    double *qc_base;     size_t qc_stride;     // doubles: compact q values, n * B per slot
+    double *bslot_base;  size_t bslot_stride;  // doubles per slot (n)
+    uint32_t *queue_v_base;                    // level queues: vertex ids,
+    uint8_t *queue_m_base;                     // their source masks (B / 8 bytes per entry)
+    uint32_t *queue_p_base;                    // and the position of the entry's run in qc
+    size_t queue_stride;                       // entries per slot (pitch)
+    size_t queue_cap;                          // usable entries per slot
+    uint32_t *lvl_base;  size_t lvl_stride;    // u32 per slot (max_levels + 2)
+    uint32_t max_levels;
+    uint8_t *batch_status;                     // per batch id (BatchStatus)
+    unsigned long long *counters;              // as EngineParams::counters
+};
+
+template <int kW> struct WideTraits;
+template <> struct WideTraits<128> {
+    using Vec = uint4;
+    static __device__ __forceinline__ void unpack(const Vec &v, uint32_t (&w)[4]) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    static __device__ __forceinline__ Vec pack(const uint32_t (&w)[4]) { return make_uint4(w[0], w[1], w[2], w[3]); }
+};
+template <> struct WideTraits<64> {
+    using Vec = uint2;
+    static __device__ __forceinline__ void unpack(const Vec &v, uint32_t (&w)[2]) { w[0] = v.x; w[1] = v.y; }
+    static __device__ __forceinline__ Vec pack(const uint32_t (&w)[2]) { return make_uint2(w[0], w[1]); }
+};
+
+template <int kW, int kThreads>
+constexpr size_t wide_smem_bytes() {
+    // per warp: two buffers of 32 staged rows (kW / 2 bytes each), plus one group of rows of read-ahead padding
+    return (size_t)(kThreads / 32) * 2 * 32 * (kW / 2) + 8 * (kW / 2);
+}
+
+constexpr uint32_t kWideInvalid = 0xFFFFFFFFu;
+
+template <int kW, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 512 ? 2 : 1)
+wide_engine(const WideParams p) {
+    namespace cg = cooperative_groups;
+    using WT = WideTraits<kW>;
+    using Vec = typename WT::Vec;
+    constexpr int kWords = kW / 32;                     // mask words; also the most sources a lane can work for
+    constexpr int kVecB = kW / 8;                       // bytes of a mask
+    constexpr int kRecB = kW / 2;                       // forward record: seen, next[2], claim (+ padding)
+    constexpr int kSlotB = kW / 4;                      // level-record slot: mask, position, tag (+ padding at B = 128)
+    constexpr int kRowB = kW / 2;                       // staged row: the two slots of levels l-1 / l+1 = kWords cooked 16 B cells
+    constexpr int kPieces = kRowB / 16;                 // 16 B pieces per row
+    constexpr int kWarps = kThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t team_size = cluster.num_blocks(), team_rank = cluster.block_rank();
+    const uint32_t slot = blockIdx.x / team_size, n_slots = gridDim.x / team_size;
+    const uint32_t tid_t = team_rank * kThreads + threadIdx.x, threads_t = team_size * kThreads;
+    const uint32_t warp_t = team_rank * kWarps + warp, warps_t = team_size * kWarps;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint32_t n = p.n;
+
+    uint8_t *__restrict__ rec = p.rec_base + (size_t)slot * p.rec_stride;
+    uint8_t *__restrict__ lr = p.lr_base + (size_t)slot * p.lr_stride;
+    double *__restrict__ qc = p.qc_base + (size_t)slot * p.qc_stride;
+    double *__restrict__ bslot = p.bslot_base + (size_t)slot * p.bslot_stride;
+    uint32_t *__restrict__ queue_v = p.queue_v_base + (size_t)slot * p.queue_stride;
+    Vec *__restrict__ queue_m = reinterpret_cast<Vec *>(p.queue_m_base + (size_t)slot * p.queue_stride * kVecB);
+    uint32_t *__restrict__ queue_p = p.queue_p_base + (size_t)slot * p.queue_stride;
+    uint32_t *__restrict__ lvl = p.lvl_base + (size_t)slot * p.lvl_stride;
+    const uint32_t qcap = (uint32_t)p.queue_cap;
+
+    auto seen_of = [&](uint32_t v) -> Vec * { return reinterpret_cast<Vec *>(rec + (size_t)v * kRecB); };
+    auto next_of = [&](uint32_t v, uint32_t parity) -> Vec * { return reinterpret_cast<Vec *>(rec + (size_t)v * kRecB + kVecB * (1 + parity)); };
+    auto claim_of = [&](uint32_t v) -> uint32_t * { return reinterpret_cast<uint32_t *>(rec + (size_t)v * kRecB + 3 * kVecB); };
+
+    // team-shared scalars: rank 0's copies, reached through distributed shared memory
+    __shared__ uint32_t s_tail, s_fail, s_open, s_pos;
+    uint32_t *tail_p = cluster.map_shared_rank(&s_tail, 0);
+    uint32_t *fail_p = cluster.map_shared_rank(&s_fail, 0);
+    uint32_t *open_p = cluster.map_shared_rank(&s_open, 0);
+    uint32_t *pos_p = cluster.map_shared_rank(&s_pos, 0);
+    __shared__ unsigned char s_klist[kWarps][kW];        // backward: the live sources of the entry a warp is consuming
+    __shared__ unsigned long long s_cnt[3];
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    unsigned char *my_rows = wide_smem + (size_t)warp * 2 * 32 * kRowB;   // [2][32][kRowB]
+
+    uint32_t my_depth = 0;
+    long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
+    unsigned long long dir_levels = 0;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+
+    for (uint32_t work = slot; work < p.n_work; work += n_slots) {
+        const uint32_t batch = p.work_list ? p.work_list[work] : work;
+        long long t_phase = clock64();
+        // ---- reset: forward records and level records (tags) of the slot ------------------------------------
+        {
+            uint4 *r16 = reinterpret_cast<uint4 *>(rec);
+            const size_t n16 = (size_t)n * kRecB / 16;
+            for (size_t i = tid_t; i < n16; i += threads_t) __stcg(&r16[i], make_uint4(0u, 0u, 0u, 0u));
+            uint4 *l16 = reinterpret_cast<uint4 *>(lr);
+            const size_t m16 = (size_t)n * 4 * kSlotB / 16;
+            for (size_t i = tid_t; i < m16; i += threads_t) __stcg(&l16[i], make_uint4(0u, 0u, 0u, 0u));
+        }
+        if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; s_open = 0; s_pos = 0; }
+        cluster.sync();
+
+        // ---- seed level 0 -----------------------------------------------------------------------------------
+        uint32_t valid_src[kWords];
+        {
+            const uint32_t first = batch * kW;
+            const uint32_t have = p.n_sources - first < (uint32_t)kW ? p.n_sources - first : (uint32_t)kW;
+#pragma unroll
+            for (int wd = 0; wd < kWords; ++wd) {
+                const uint32_t lo = wd * 32;
+                valid_src[wd] = have >= lo + 32 ? 0xFFFFFFFFu : (have > lo ? (1u << (have - lo)) - 1u : 0u);
+            }
+            if (warp_t == 0) {
+#pragma unroll
+                for (int wd = 0; wd < kWords; ++wd) {
+                    if ((valid_src[wd] >> lane) & 1u) {
+                        const uint32_t s = p.sources[first + wd * 32 + lane];
+                        atomicOr(reinterpret_cast<uint32_t *>(next_of(s, 0)) + wd, 1u << lane);
+                        if (atomicExch(claim_of(s), 1u) != 1u) queue_v[atomicAdd(tail_p, 1u)] = s;
+                    }
+                }
+            }
+        }
+        cluster.sync();
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
+
+        // ---- forward: level-synchronous, bit-parallel, direction chosen per level ---------------------------
+        uint32_t level = 0, qbeg = 0, qend = 0;
+        bool too_deep = false;
+        uint32_t n_open = n, defer_beg = 0, defer_end = 0;
+        bool prev_pull = false;
+        for (;;) {
+            cluster.sync();                              // previous level fully expanded
+            const uint32_t tail_raw = *(volatile uint32_t *)tail_p;
+            const uint32_t open_raw = *(volatile uint32_t *)open_p;
+            const uint32_t tail_now = tail_raw < qcap ? tail_raw : qcap;
+            cluster.sync();                              // every warp sampled the tail before it moves again
+            qbeg = qend;
+            qend = tail_now;
+            if (prev_pull) n_open = open_raw;
+            if (tid_t == 0) lvl[level] = qbeg;
+            if (qend == qbeg) break;
+            if (level >= p.max_levels) { too_deep = true; break; }
+            const uint32_t par_c = level & 1u, par_n = par_c ^ 1u;
+            const uint32_t entries = qend - qbeg;
+            const bool pull = p.pull_mode == 2 ||
+                              (p.pull_mode == 1 && 2ull * entries * p.avg_deg > (9ull * n) / 16 + (unsigned long long)n_open * p.avg_deg);
+            // mark: the level's vertices become `seen` for their sources before anything is expanded; the entry's
+            // mask moves to the queue and next[] cleans itself (one level later if this level is pulled: the scan
+            // reads the masks from the records)
+            for (uint32_t idx = qbeg + tid_t; idx < qend; idx += threads_t) {
+                const uint32_t u = queue_v[idx];
+                const Vec m = __ldcg(next_of(u, par_c));
+                const Vec sn = __ldcg(seen_of(u));
+                uint32_t mw[kWords], sw[kWords];
+                WT::unpack(m, mw); WT::unpack(sn, sw);
+#pragma unroll
+                for (int wd = 0; wd < kWords; ++wd) sw[wd] |= mw[wd];
+                __stcg(seen_of(u), WT::pack(sw));
+                if (!pull) {
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) sw[wd] = 0;
+                    __stcg(next_of(u, par_c), WT::pack(sw));
+                }
+                queue_m[idx] = m;
+            }
+            {
+                uint32_t zero[kWords];
+#pragma unroll
+                for (int wd = 0; wd < kWords; ++wd) zero[wd] = 0;
+                for (uint32_t idx = defer_beg + tid_t; idx < defer_end; idx += threads_t)
+                    __stcg(next_of(queue_v[idx], par_n), WT::pack(zero));     // the pulled level-1's masks: same parity as level+1
+            }
+            defer_beg = pull ? qbeg : 0u;
+            defer_end = pull ? qend : 0u;
+            if (pull && threadIdx.x == 0) s_open = 0;
+            cluster.sync();
+
+            if (!pull) {
+                // ---- push: one lane per adjacency entry of the frontier ----
+                const uint32_t tag = level + 2u;         // claim tag of the level being built
+                for (uint32_t tile = qbeg + warp_t * 32; tile < qend; tile += warps_t * 32) {
+                    const uint32_t idx = tile + lane;
+                    uint32_t m[kWords], rs = 0, deg = 0;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) m[wd] = 0;
+                    if (idx < qend) {
+                        const uint32_t u = queue_v[idx];
+                        WT::unpack(queue_m[idx], m);
+                        rs = __ldg(p.row_ptr + u);
+                        deg = __ldg(p.row_ptr + u + 1) - rs;
+                    }
+                    const uint32_t incl = warp_inclusive_scan(deg, lane);
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const uint32_t off = incl - deg;
+                    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                        const uint32_t t = t0 + lane;
+                        const int o = tile_owner(incl, t);
+                        const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
+                        const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
+                        uint32_t fresh[kWords];
+#pragma unroll
+                        for (int wd = 0; wd < kWords; ++wd) fresh[wd] = __shfl_sync(0xFFFFFFFFu, m[wd], o);
+                        bool enqueue = false;
+                        uint32_t x = 0;
+                        if (t < total) {
+                            x = __ldg(p.col_idx + rs_o + (t - off_o));
+                            uint32_t sv[kWords], nv[kWords];
+                            WT::unpack(__ldcg(seen_of(x)), sv);
+                            WT::unpack(__ldcg(next_of(x, par_n)), nv);
+                            bool cand = false;
+#pragma unroll
+                            for (int wd = 0; wd < kWords; ++wd) {
+                                fresh[wd] &= ~(sv[wd] | nv[wd]);
+                                if (fresh[wd]) cand |= atomicOr(reinterpret_cast<uint32_t *>(next_of(x, par_n)) + wd, fresh[wd]) == 0u;
+                            }
+                            // several lanes can each be first on a different word: the claim decides who enqueues x
+                            if (cand) enqueue = atomicExch(claim_of(x), tag) != tag;
+                        }
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, enqueue);
+                        if (bal) {
+                            uint32_t base = 0;
+                            const int leader = __ffs(bal) - 1;
+                            if (lane == leader) base = atomicAdd(tail_p, (uint32_t)__popc(bal));
+                            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                            if (enqueue) {
+                                const uint32_t pos = base + __popc(bal & lane_lt);
+                                if (pos < qcap) queue_v[pos] = x;
+                                else *(volatile uint32_t *)fail_p = 1;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ---- pull scan: thread per vertex (id order: streams), neighbours' frontier masks gathered ----
+                uint32_t my_open = 0;
+                for (uint32_t base = warp_t * 32; base < n; base += warps_t * 32) {
+                    const uint32_t x = base + lane;
+                    uint32_t unseen[kWords], acc[kWords];
+                    uint32_t any_unseen = 0;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) { unseen[wd] = 0; acc[wd] = 0; }
+                    uint32_t rs = 0, deg = 0;
+                    if (x < n) {
+                        WT::unpack(__ldcg(seen_of(x)), unseen);
+#pragma unroll
+                        for (int wd = 0; wd < kWords; ++wd) { unseen[wd] = ~unseen[wd] & valid_src[wd]; any_unseen |= unseen[wd]; }
+                        if (any_unseen) {
+                            rs = __ldg(p.row_ptr + x);
+                            deg = __ldg(p.row_ptr + x + 1) - rs;
+                        }
+                    }
+                    const bool hub = deg > kPullHubDeg;
+                    if (!hub) {
+                        for (uint32_t e = 0; e < deg; e += kPullUnroll) {
+                            uint32_t un[kPullUnroll];
+                            Vec mm[kPullUnroll];
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : kWideInvalid;
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) {
+                                uint32_t z[kWords];
+#pragma unroll
+                                for (int wd = 0; wd < kWords; ++wd) z[wd] = 0;
+                                mm[j] = un[j] != kWideInvalid ? __ldcg(next_of(un[j], par_c)) : WT::pack(z);
+                            }
+                            uint32_t missing = 0;
+#pragma unroll
+                            for (int j = 0; j < kPullUnroll; ++j) {
+                                uint32_t w4[kWords];
+                                WT::unpack(mm[j], w4);
+#pragma unroll
+                                for (int wd = 0; wd < kWords; ++wd) acc[wd] |= w4[wd];
+                            }
+#pragma unroll
+                            for (int wd = 0; wd < kWords; ++wd) missing |= unseen[wd] & ~acc[wd];
+                            if (!missing) break;             // nothing left to find for this vertex
+                        }
+                    }
+                    // hubs: the whole warp gathers one adjacency list
+                    for (uint32_t hub_bal = __ballot_sync(0xFFFFFFFFu, hub); hub_bal; hub_bal &= hub_bal - 1) {
+                        const int o = __ffs(hub_bal) - 1;
+                        const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o), deg_o = __shfl_sync(0xFFFFFFFFu, deg, o);
+                        uint32_t a[kWords];
+#pragma unroll
+                        for (int wd = 0; wd < kWords; ++wd) a[wd] = 0;
+                        for (uint32_t e = lane; e < deg_o; e += 32) {
+                            uint32_t w4[kWords];
+                            WT::unpack(__ldcg(next_of(__ldg(p.col_idx + rs_o + e), par_c)), w4);
+#pragma unroll
+                            for (int wd = 0; wd < kWords; ++wd) a[wd] |= w4[wd];
+                        }
+#pragma unroll
+                        for (int wd = 0; wd < kWords; ++wd) {
+                            a[wd] = __reduce_or_sync(0xFFFFFFFFu, a[wd]);
+                            if (lane == o) acc[wd] = a[wd];
+                        }
+                    }
+                    uint32_t fresh[kWords], any_fresh = 0, still = 0;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) { fresh[wd] = acc[wd] & unseen[wd]; any_fresh |= fresh[wd]; still |= unseen[wd] & ~fresh[wd]; }
+                    if (any_fresh) __stcg(next_of(x, par_n), WT::pack(fresh));     // one writer per vertex
+                    my_open += still != 0 ? 1u : 0u;
+                    const bool enqueue = any_fresh != 0;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, enqueue);
+                    if (bal) {
+                        uint32_t qb = 0;
+                        const int leader = __ffs(bal) - 1;
+                        if (lane == leader) qb = atomicAdd(tail_p, (uint32_t)__popc(bal));
+                        qb = __shfl_sync(0xFFFFFFFFu, qb, leader);
+                        if (enqueue) {
+                            const uint32_t pos = qb + __popc(bal & lane_lt);
+                            if (pos < qcap) queue_v[pos] = x;
+                            else *(volatile uint32_t *)fail_p = 1;
+                        }
+                    }
+                }
+                my_open = __reduce_add_sync(0xFFFFFFFFu, my_open);
+                if (lane == 0 && my_open) atomicAdd(open_p, my_open);
+            }
+            prev_pull = pull;
+            if (tid_t == 0) dir_levels += pull ? (1ull << 32) : 1ull;
+            ++level;
+        }
+        // here: levels 0..level-1 are non-empty (if !too_deep), lvl[l] = start of level l, lvl[level] = end of the last
+        cluster.sync();
+        const bool failed = *(volatile uint32_t *)fail_p != 0;
+        if (too_deep || failed) {
+            if (tid_t == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
+            cluster.sync();                              // (the reset of the next batch clears every record)
+            continue;
+        }
+        const uint32_t depth = level - 1;
+        if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
+        if (depth > my_depth) my_depth = depth;
+
+        // ---- backward: levels depth .. 1 ----------------------------------------------------------------------
+        // prepare(L): every entry of level L gets the position of its run in qc (prefix sums per warp, one atomic on
+        // the team's counter) and publishes {mask, position, tag = L + 1} in slot L of its vertex's level record.
+        uint32_t b_reached = 0, b_edges = 0, b_visits = 0;
+        auto prepare = [&](uint32_t L) {
+            const uint32_t lb = lvl[L], le = lvl[L + 1];
+            const uint32_t phys = ((L & 1u) << 1) | ((L >> 1) & 1u);
+            for (uint32_t base = lb + warp_t * 32; base < le; base += warps_t * 32) {
+                const uint32_t idx = base + lane;
+                uint32_t m[kWords], c = 0, u = 0;
+#pragma unroll
+                for (int wd = 0; wd < kWords; ++wd) m[wd] = 0;
+                if (idx < le) {
+                    u = queue_v[idx];
+                    WT::unpack(queue_m[idx], m);
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) c += __popc(m[wd]);
+                }
+                uint32_t pos = 0;
+                if (L >= 1) {                           // the sources themselves (level 0) store no q
+                    const uint32_t incl = warp_inclusive_scan(c, lane);
+                    uint32_t b = 0;
+                    if (lane == 31) b = atomicAdd(pos_p, incl);
+                    b = __shfl_sync(0xFFFFFFFFu, b, 31);
+                    pos = b + incl - c;
+                }
+                if (idx < le) {
+                    queue_p[idx] = pos;
+                    uint4 *dst = reinterpret_cast<uint4 *>(lr + (size_t)u * 4 * kSlotB + phys * kSlotB);
+                    if constexpr (kW == 128) {
+                        __stcg(dst, make_uint4(m[0], m[1], m[2], m[3]));
+                        __stcg(dst + 1, make_uint4(pos, L + 1u, 0u, 0u));
+                    } else
+                        __stcg(dst, make_uint4(m[0], m[1], pos, L + 1u));
+                    if (L == 0) {                       // statistics of the level the sweep below never visits
+                        const uint32_t rs = __ldg(p.row_ptr + u);
+                        b_reached += c; b_edges += c * (__ldg(p.row_ptr + u + 1) - rs); b_visits += 1;
+                    }
+                }
+            }
+        };
+        prepare(depth);
+        for (uint32_t l = depth; l >= 1; --l) {
+            prepare(l - 1);
+            cluster.sync();                              // level l+1 fully processed (its q values stored), levels l and l-1 prepared
+            const uint32_t lb = lvl[l], le = lvl[l + 1];
+            const uint32_t pair_off = ((l + 1u) & 1u) * 2u * kSlotB;       // block of the slots of levels l+1 and l-1
+            const uint32_t sub_s = ((l + 1u) >> 1) & 1u;                   // which of the two is level l+1's
+            const uint32_t tag_s = l + 2u, tag_p = l;
+            for (uint32_t tile = lb + warp_t * 32; tile < le; tile += warps_t * 32) {
+                const uint32_t idx = tile + lane;
+                uint32_t w = 0, rs = 0, deg = 0, mypos = 0, m[kWords];
+#pragma unroll
+                for (int wd = 0; wd < kWords; ++wd) m[wd] = 0;
+                if (idx < le) {
+                    w = queue_v[idx];
+                    WT::unpack(queue_m[idx], m);
+                    mypos = queue_p[idx];
+                    rs = __ldg(p.row_ptr + w);
+                    deg = __ldg(p.row_ptr + w + 1) - rs;
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) c += __popc(m[wd]);
+                    b_reached += c; b_edges += c * deg; b_visits += 1;
+                }
+                const uint32_t incl = warp_inclusive_scan(deg, lane);
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t off = incl - deg;
+                // per-entry state of this lane: up to kWords sources (ranks lane, lane + 32, ...)
+                int cur = -1;
+                uint32_t cur_end = 0, c_cur = 0, pos_cur = 0;
+                uint32_t cell[kWords], sel[kWords], npred[kWords];     // byte offset of the source's cell in a cooked row, its bit, predecessors so far
+                double acc[kWords], my_total = 0.0;
+#pragma unroll
+                for (int h = 0; h < kWords; ++h) { cell[h] = 0; sel[h] = 0; npred[h] = 0; acc[h] = 0.0; }
+
+                auto begin_entry = [&]() {
+                    uint32_t mc[kWords], pre[kWords + 1];
+                    pre[0] = 0;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) {
+                        mc[wd] = __shfl_sync(0xFFFFFFFFu, m[wd], cur);
+                        pre[wd + 1] = pre[wd] + __popc(mc[wd]);
+                    }
+                    c_cur = pre[kWords];
+                    pos_cur = __shfl_sync(0xFFFFFFFFu, mypos, cur);
+                    __syncwarp();                                   // the previous entry's list has been read by every lane
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd)
+                        if ((mc[wd] >> lane) & 1u) s_klist[warp][pre[wd] + __popc(mc[wd] & lane_lt)] = (unsigned char)(wd * 32 + lane);
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < kWords; ++h) {
+                        const bool on = (uint32_t)lane + 32u * h < c_cur;
+                        const uint32_t ks = on ? (uint32_t)s_klist[warp][lane + 32 * h] : 0u;
+                        cell[h] = (ks >> 5) * 16u;
+                        sel[h] = on ? 1u << (ks & 31u) : 0u;
+                        acc[h] = 0.0; npred[h] = 0;
+                    }
+                };
+                auto finish_entry = [&]() {
+                    double contrib = 0.0;
+#pragma unroll
+                    for (int h = 0; h < kWords; ++h) {
+                        if ((uint32_t)lane + 32u * h < c_cur) {
+                            const double bk = 1.0 + acc[h];
+                            __stcg(&qc[(size_t)pos_cur + lane + 32 * h], bk / (double)npred[h]);    // dense, coalesced
+                            contrib += p.include_endpoints ? bk : bk - 1.0;
+                        }
+                    }
+                    const double tot = warp_sum(contrib);
+                    if (lane == cur) my_total = tot;
+                };
+                // kRows rows of the current entry starting at row r of the cooked chunk in `rows`, kSlots sources per
+                // lane.  Straight-line: every q load of the group is issued (predicated) before the first is consumed.
+                auto consume = [&](auto rows_tag, auto slots_tag, const unsigned char *rows, uint32_t r, uint32_t nrows) {
+                    constexpr int kRows = decltype(rows_tag)::value, kSlots = decltype(slots_tag)::value;
+                    double qv[kRows][kSlots];
+                    const unsigned char *rp = rows + r * kRowB;
+#pragma unroll
+                    for (int jj = 0; jj < kRows; ++jj) {
+                        const bool valid = (uint32_t)jj < nrows;    // warp-uniform
+#pragma unroll
+                        for (int h = 0; h < kSlots; ++h) {
+                            const uint4 cl = *reinterpret_cast<const uint4 *>(rp + jj * kRowB + cell[h]);   // {succ word, pred word, base, -}
+                            const bool succ = valid && (cl.x & sel[h]) != 0u;
+                            const uint32_t at = cl.z + __popc(cl.x & (sel[h] - 1u));
+                            qv[jj][h] = succ ? __ldcg(qc + at) : 0.0;
+                            if (valid && (cl.y & sel[h]) != 0u) npred[h] += 1u;
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < kRows; ++jj)              // adjacency (CSR) order: fixes the rounding
+#pragma unroll
+                        for (int h = 0; h < kSlots; ++h) acc[h] += qv[jj][h];
+                };
+
+                auto edge_of = [&](uint32_t t0) -> uint32_t {     // neighbour id of flattened entry t0 + lane
+                    const uint32_t t = t0 + lane;
+                    const int o = tile_owner(incl, t);
+                    const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
+                    const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
+                    return t < total ? __ldg(p.col_idx + rs_o + (t - off_o)) : kWideInvalid;
+                };
+                auto stage_rows = [&](int buf, uint32_t xs) {     // level-record blocks of the chunk whose neighbour ids are `xs` (lane r: row r)
+#pragma unroll
+                    for (int it = 0; it < kPieces; ++it) {
+                        const int r = it * (32 / kPieces) + lane / kPieces;
+                        const int part = lane % kPieces;
+                        const uint32_t x = __shfl_sync(0xFFFFFFFFu, xs, r);
+                        if (x != kWideInvalid) {
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + ((size_t)buf * 32 + r) * kRowB + part * 16);
+                            const unsigned char *src = lr + (size_t)x * 4 * kSlotB + pair_off + part * 16;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                // lane r turns the landed block of row r into kWords cells {succ mask word, pred mask word, index of the
+                // word's first value in the neighbour's run, -}; slots with another level's tag count as empty
+                auto cook = [&](int buf, bool row_valid) {
+                    uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * 32 + lane) * kRowB);
+                    uint32_t ms[kWords], mp[kWords], pos_s, ts, tp;
+                    if constexpr (kW == 128) {
+                        const uint4 a0 = rp[0], a1 = rp[1], b0 = rp[2], b1 = rp[3];
+                        const uint4 s0 = sub_s ? b0 : a0, s1 = sub_s ? b1 : a1, p0 = sub_s ? a0 : b0, p1 = sub_s ? a1 : b1;
+                        ms[0] = s0.x; ms[1] = s0.y; ms[2] = s0.z; ms[3] = s0.w; pos_s = s1.x; ts = s1.y;
+                        mp[0] = p0.x; mp[1] = p0.y; mp[2] = p0.z; mp[3] = p0.w; tp = p1.y;
+                    } else {
+                        const uint4 a = rp[0], b = rp[1];
+                        const uint4 s = sub_s ? b : a, q = sub_s ? a : b;
+                        ms[0] = s.x; ms[1] = s.y; pos_s = s.z; ts = s.w;
+                        mp[0] = q.x; mp[1] = q.y; tp = q.w;
+                    }
+                    const bool s_ok = row_valid && ts == tag_s, p_ok = row_valid && tp == tag_p;
+                    uint32_t at = pos_s;
+#pragma unroll
+                    for (int wd = 0; wd < kWords; ++wd) {
+                        const uint32_t a = s_ok ? ms[wd] : 0u, b = p_ok ? mp[wd] : 0u;
+                        rp[wd] = make_uint4(a, b, at, 0u);
+                        at += __popc(a);
+                    }
+                };
+
+                const uint32_t n_chunks = (total + 31) / 32;
+                uint32_t x_next = edge_of(0);
+                stage_rows(0, x_next);
+                x_next = n_chunks > 1 ? edge_of(32) : kWideInvalid;
+                for (uint32_t sc = 0; sc < n_chunks; ++sc) {
+                    const int buf = sc & 1;
+                    const uint32_t t0 = sc * 32;
+                    const uint32_t cnt = min(32u, total - t0);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's blocks have landed (this lane's copies)
+                    __syncwarp();                                          // ... and every other lane's
+                    stage_rows(buf ^ 1, x_next);                           // chunk sc+1 (nothing past the end); buffer drained at sc-1
+                    x_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : kWideInvalid;
+                    cook(buf, (uint32_t)lane < cnt);
+                    __syncwarp();
+                    const unsigned char *rows = my_rows + (size_t)buf * 32 * kRowB;
+                    for (uint32_t r = 0; r < cnt;) {
+                        const uint32_t tt = t0 + r;
+                        if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start
+                            if (cur >= 0) finish_entry();
+                            do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
+                            begin_entry();
+                        }
+                        const uint32_t left = min(cur_end - tt, cnt - r);      // rows of this entry inside this chunk
+                        if (kWords == 4 && c_cur > 64) {
+                            const uint32_t nrows = min(left, 2u);
+                            consume(std::integral_constant<int, 2>{}, std::integral_constant<int, kWords>{}, rows, r, nrows);
+                            r += nrows;
+                        } else if (c_cur > 32) {
+                            const uint32_t nrows = min(left, 4u);
+                            consume(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{}, rows, r, nrows);
+                            r += nrows;
+                        } else if (left > 4u) {
+                            const uint32_t nrows = min(left, 8u);
+                            consume(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{}, rows, r, nrows);
+                            r += nrows;
+                        } else {                                  // a short tail: the half-size group wastes fewer predicated-off rows
+                            consume(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{}, rows, r, left);
+                            r += left;
+                        }
+                    }
+                    __syncwarp();                                 // buffer `buf` may be refilled next iteration
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (cur >= 0) finish_entry();
+                if (idx < le && deg != 0) bslot[w] += my_total;     // one writer per vertex per level
+            }
+        }
+        atomicAdd(&s_cnt[0], (unsigned long long)b_reached);
+        atomicAdd(&s_cnt[1], (unsigned long long)b_edges);
+        atomicAdd(&s_cnt[2], (unsigned long long)b_visits);
+        if (threadIdx.x == 0) { if (team_rank == 0) p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
+        cluster.sync();
+    }
+
+    // ---- flush counters ---------------------------------------------------------------------------------------
+    cluster.sync();                                      // rank 0's shared memory stays alive until every CTA of the team is done
+    if (threadIdx.x < 3) atomicAdd(&p.counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        atomicMax(&p.counters[3], (unsigned long long)my_depth);
+        atomicAdd(&p.counters[4], (unsigned long long)cyc_reset);
+        atomicAdd(&p.counters[5], (unsigned long long)cyc_fwd);
+        atomicAdd(&p.counters[6], (unsigned long long)cyc_bwd);
+        if (dir_levels) atomicAdd(&p.counters[7], dir_levels);
+    }
+}
+
+}  // namespace nec

@@ -13,20 +13,31 @@ from tests.helpers import adj_from_edges, close, csr_from_adj, edge_case_graphs
 
 pytestmark = pytest.mark.gpu
 REL = 1e-9
-ENGINES = {"auto": 0, "batched": 1, "mid": 2}
+ENGINES = {"auto": 0, "batched": 1, "mid": 2, "wide": 3}
 
 
-@pytest.fixture(params=["batched", "batched64", "batched_pull", "batched64_pull", "batched64_push", "mid"])
+@pytest.fixture(params=["batched", "batched64", "batched_pull", "batched64_pull", "batched64_push", "mid",
+                        "wide128", "wide64", "wide128_pull", "wide128_push", "wide64_pull", "wide128_t512", "wide64_team3"])
 def engine_ctx(ctx, request, monkeypatch):
     """Runs a test once per traversal engine, batch width and forward direction (the C ABI picks by graph size,
-    source count and a per-level cost model by default; NEC_BATCH_WIDTH pins the batched engine's 32 / 64 sources
-    per batch, NEC_PULL its forward pass to push only (0) or pull only (2))."""
-    name, _, direction = request.param.partition("_")
-    ctx.set_engine(ENGINES[name.rstrip("64")])
-    if name.startswith("batched"):
+    source count and a per-level cost model by default; NEC_BATCH_WIDTH pins the source-minor batched engine's 32 / 64
+    sources per batch, NEC_WIDE_WIDTH the compact engine's 64 / 128, NEC_PULL the forward pass to push only (0) or pull
+    only (2); t512 = 512-thread CTAs, team3 = three CTAs per slot)."""
+    name, _, variant = request.param.partition("_")
+    base = name.rstrip("0123456789")
+    ctx.set_engine(ENGINES[base])
+    if base == "batched":
         monkeypatch.setenv("NEC_BATCH_WIDTH", "64" if name.endswith("64") else "32")
-        if direction:
-            monkeypatch.setenv("NEC_PULL", "2" if direction == "pull" else "0")
+    if base == "wide":
+        monkeypatch.setenv("NEC_WIDE_WIDTH", name[4:])
+        monkeypatch.setenv("NEC_WIDE_QUEUE", "128")        # room for every level a vertex can sit on: nothing is handed to the other engine
+    if variant in ("pull", "push"):
+        monkeypatch.setenv("NEC_PULL", "2" if variant == "pull" else "0")
+    if variant == "t512":
+        monkeypatch.setenv("NEC_WIDE_THREADS", "512")
+    if variant == "team3":
+        monkeypatch.setenv("NEC_WIDE_TEAM", "3")
+    ctx.engine_name = base
     yield ctx
     ctx.set_engine(0)
 
@@ -136,7 +147,7 @@ def test_deep_graphs_take_the_wide_distance_path(engine_ctx, oracle):
     rp, col = csr_from_adj(path)
     dg = ctx.upload(rp, col)
     got = dg.vertex_load(True)
-    assert ctx.stats()["wide_batches"] > 0 and ctx.stats()["max_depth"] == n - 1
+    assert (ctx.stats()["wide_batches"] > 0 or ctx.engine_name == "wide") and ctx.stats()["max_depth"] == n - 1
     assert close(got, oracle.vertex_load(rp, col, True), REL)
     # path: a source left of v sends the n-v vertices at/behind v through it, one right of v sends v+1
     v = np.arange(n)
