@@ -116,6 +116,11 @@ wide_engine(const WideParams p) {
     uint32_t *__restrict__ queue_p = p.queue_p_base + (size_t)slot * p.queue_stride;
     uint32_t *__restrict__ lvl = p.lvl_base + (size_t)slot * p.lvl_stride;
     const uint32_t qcap = (uint32_t)p.queue_cap;
+    // the slot's q base lives in a register pair: without this the compiler re-derives it from the kernel
+    // parameters (two constant loads, a 64-bit multiply-add, a 64-bit shift-add) in front of every one of the
+    // hot loop's loads
+    const double *qc_hot = qc;
+    asm volatile("" : "+l"(qc_hot));
 
     auto seen_of = [&](uint32_t v) -> Vec * { return reinterpret_cast<Vec *>(rec + (size_t)v * kRecB); };
     auto next_of = [&](uint32_t v, uint32_t parity) -> Vec * { return reinterpret_cast<Vec *>(rec + (size_t)v * kRecB + kVecB * (1 + parity)); };
@@ -473,9 +478,15 @@ wide_engine(const WideParams p) {
                     c_cur = pre[kWords];
                     pos_cur = __shfl_sync(0xFFFFFFFFu, mypos, cur);
                     __syncwarp();                                   // the previous entry's list has been read by every lane
+                    {
+                        const unsigned kl = (unsigned)__cvta_generic_to_shared(&s_klist[warp][0]);
 #pragma unroll
-                    for (int wd = 0; wd < kWords; ++wd)
-                        if ((mc[wd] >> lane) & 1u) s_klist[warp][pre[wd] + __popc(mc[wd] & lane_lt)] = (unsigned char)(wd * 32 + lane);
+                        for (int wd = 0; wd < kWords; ++wd) {       // predicated byte stores, no branches
+                            const unsigned at = kl + pre[wd] + __popc(mc[wd] & lane_lt);
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}"
+                                         ::"r"(at), "r"((uint32_t)(wd * 32 + lane)), "r"((mc[wd] >> lane) & 1u) : "memory");
+                        }
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int h = 0; h < kWords; ++h) {
@@ -513,7 +524,7 @@ wide_engine(const WideParams p) {
                             const uint4 cl = *reinterpret_cast<const uint4 *>(rp + jj * kRowB + cell[h]);   // {succ word, pred word, base, -}
                             const bool succ = valid && (cl.x & sel[h]) != 0u;
                             const uint32_t at = cl.z + __popc(cl.x & (sel[h] - 1u));
-                            qv[jj][h] = succ ? __ldcg(qc + at) : 0.0;
+                            qv[jj][h] = succ ? __ldcg(qc_hot + at) : 0.0;
                             if (valid && (cl.y & sel[h]) != 0u) npred[h] += 1u;
                         }
                     }
@@ -593,9 +604,13 @@ wide_engine(const WideParams p) {
                             begin_entry();
                         }
                         const uint32_t left = min(cur_end - tt, cnt - r);      // rows of this entry inside this chunk
-                        if (kWords == 4 && c_cur > 64) {
+                        if (kWords == 4 && c_cur > 96) {
                             const uint32_t nrows = min(left, 2u);
                             consume(std::integral_constant<int, 2>{}, std::integral_constant<int, kWords>{}, rows, r, nrows);
+                            r += nrows;
+                        } else if (kWords == 4 && c_cur > 64) {
+                            const uint32_t nrows = min(left, 2u);
+                            consume(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{}, rows, r, nrows);
                             r += nrows;
                         } else if (c_cur > 32) {
                             const uint32_t nrows = min(left, 4u);

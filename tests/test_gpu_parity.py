@@ -488,16 +488,19 @@ def test_full_size_properties_config2_small_world(ctx, oracle):
 
 
 def test_full_size_properties_config4_gnm(ctx, oracle):
-    g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)          # BASELINE configs[3] (scalable generator), sampled sources
+    """BASELINE configs[3] (the north-star target) on the path the bench takes: one resident wave through the DEFAULT
+    plan = the compact engine, 128 sources per batch, one thread-block cluster of two 1024-thread CTAs per batch."""
+    g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)          # (scalable generator), sampled sources
     rp, col = g.export_csr()
     src = (np.arange(9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
-    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 64)
-    assert st["team_size"] == 1 and st["cta_threads"] == 1024 and st["n_slots"] == 148 and st["pull_levels"] > 0
+    st = _full_size_properties(ctx, oracle, rp, col, src, 4, 128)
+    assert st["team_size"] == 2 and st["cta_threads"] == 1024 and st["n_slots"] == 74 and st["pull_levels"] > 0
+    assert st["requeued_batches"] == 0 and st["reached_pairs"] == 9472 * (1 << 20)
 
 
 def test_full_size_properties_config5_barabasi_albert(ctx, oracle):
     """BASELINE configs[4] on the path the bench takes: one resident wave of sources through the DEFAULT plan, which
-    on this graph is 64-wide batches on memory-limited slots, each run by a thread-block cluster of 512-thread CTAs."""
+    on this graph is the compact engine on memory-limited slots, each run by a cluster of several CTAs."""
     g = ne.ba_scalable(1 << 22, 4, 5, 20261020)              # (scalable generator), sampled sources
     rp, col = g.export_csr()
 
@@ -506,18 +509,22 @@ def test_full_size_properties_config5_barabasi_albert(ctx, oracle):
         assert wave % 64 == 0 and wave >= 64 * 37
         return (np.arange(wave, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
 
-    st = _full_size_properties(ctx, oracle, rp, col, one_wave, 1, 64)
-    assert st["team_size"] >= 3 and st["cta_threads"] == 512 and st["n_slots"] * 64 == st["n_sources"]
-    assert st["n_slots"] * st["team_size"] <= 148 * 2
+    st = _full_size_properties(ctx, oracle, rp, col, one_wave, 4, None)
+    assert st["batch_width"] in (64, 128) and st["team_size"] >= 3 and st["n_slots"] * st["batch_width"] == st["n_sources"]
+    assert st["n_slots"] * st["team_size"] <= 148 * (2 if st["cta_threads"] == 512 else 1)
     assert st["pull_levels"] > 0 and st["push_levels"] > 0    # direction chosen per level
-    assert st["reached_pairs"] == st["n_sources"] * (1 << 22)  # a BA graph is connected
+    assert st["requeued_batches"] == 0 and st["reached_pairs"] == st["n_sources"] * (1 << 22)  # a BA graph is connected
 
 
-def test_config5_narrow_batches_for_small_calls(ctx, oracle):
+def test_config5_small_calls(ctx, oracle):
     g = ne.ba_scalable(1 << 22, 4, 5, 20261020)
     rp, col = g.export_csr()
     src = (np.arange(1536, dtype=np.uint64) * 2_654_435_761 % (1 << 22)).astype(np.uint32)
-    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)   # too few sources for the 64-wide layout's slots
+    st = _full_size_properties(ctx, oracle, rp, col, src, 4, None)   # a dozen batches: large teams on few slots
+    assert st["reached_pairs"] == 1536 * (1 << 22) and st["n_slots"] == st["n_batches"] and st["team_size"] >= 4
+    ctx.set_engine(1)                                               # the source-minor engine at this size: narrow batches
+    st = _full_size_properties(ctx, oracle, rp, col, src, 1, 32)
+    ctx.set_engine(0)
     assert st["reached_pairs"] == 1536 * (1 << 22)
 
 
@@ -586,14 +593,20 @@ def test_wave_size_matches_what_a_call_uses(ctx):
     dg.vertex_load_sources(np.arange(wave, dtype=np.uint32), True)
     assert ctx.stats()["n_slots"] == wave and ctx.stats()["cta_threads"] == (128 if wave == 1184 else 512)
     dg.free()
-    g = ne.gnm_scalable(200_000, 800_000, 5)                           # beyond the mid engine: batched
+    g = ne.gnm_scalable(200_000, 800_000, 5)                           # beyond the mid engine: compact batched engine
     rp, col = g.export_csr()
     dg = ctx.upload(rp, col)
     wave = dg.wave_size()
     src = np.arange(wave, dtype=np.uint32)
     dg.vertex_load_sources(src, True)
     st = ctx.stats()
+    assert st["engine"] == 4 and st["n_slots"] * st["batch_width"] == wave and st["n_batches"] == st["n_slots"]
+    ctx.set_engine(1)                                                  # and the source-minor one, when asked for
+    wave = dg.wave_size()
+    dg.vertex_load_sources(np.arange(wave, dtype=np.uint32), True)
+    st = ctx.stats()
     assert st["engine"] == 1 and st["n_slots"] * st["batch_width"] == wave and st["n_batches"] == st["n_slots"]
+    ctx.set_engine(0)
     dg.free()
 
 
