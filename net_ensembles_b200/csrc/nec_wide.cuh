@@ -133,6 +133,10 @@ wide_engine(const WideParams p) {
     uint32_t *open_p = cluster.map_shared_rank(&s_open, 0);
     uint32_t *pos_p = cluster.map_shared_rank(&s_pos, 0);
     __shared__ unsigned char s_klist[kWarps][kW];        // backward: the live sources of the entry a warp is consuming
+    __shared__ __align__(16) uint32_t s_tile_m[kWarps][32][kWords];   // backward: masks and run positions of the warp's tile of entries
+    __shared__ uint32_t s_tile_p[kWarps][32];
+    __shared__ uint32_t s_tile_rs[kWarps][32], s_tile_off[kWarps][32], s_tile_end[kWarps][32];   // adjacency row start, first and past-the-end flattened row of each entry
+    __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
     __shared__ unsigned long long s_cnt[3];
     extern __shared__ __align__(16) unsigned char wide_smem[];
     unsigned char *my_rows = wide_smem + (size_t)warp * 2 * 32 * kRowB;   // [2][32][kRowB]
@@ -394,7 +398,19 @@ wide_engine(const WideParams p) {
         // ---- backward: levels depth .. 1 ----------------------------------------------------------------------
         // prepare(L): every entry of level L gets the position of its run in qc (prefix sums per warp, one atomic on
         // the team's counter) and publishes {mask, position, tag = L + 1} in slot L of its vertex's level record.
-        uint32_t b_reached = 0, b_edges = 0, b_visits = 0;
+        // statistics (pairs reached, adjacency entries in reach, queue entries): summed per tile of 32 entries
+        auto count_tile = [&](uint32_t c, uint32_t deg, bool have) {
+            const uint32_t csum = __reduce_add_sync(0xFFFFFFFFu, c);
+            unsigned long long e = (unsigned long long)c * deg;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+            const uint32_t nv = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, have));
+            if (lane == 0) {
+                atomicAdd(&s_cnt[0], (unsigned long long)csum);
+                atomicAdd(&s_cnt[1], e);
+                atomicAdd(&s_cnt[2], (unsigned long long)nv);
+            }
+        };
         auto prepare = [&](uint32_t L) {
             const uint32_t lb = lvl[L], le = lvl[L + 1];
             const uint32_t phys = ((L & 1u) << 1) | ((L >> 1) & 1u);
@@ -425,10 +441,11 @@ wide_engine(const WideParams p) {
                         __stcg(dst + 1, make_uint4(pos, L + 1u, 0u, 0u));
                     } else
                         __stcg(dst, make_uint4(m[0], m[1], pos, L + 1u));
-                    if (L == 0) {                       // statistics of the level the sweep below never visits
-                        const uint32_t rs = __ldg(p.row_ptr + u);
-                        b_reached += c; b_edges += c * (__ldg(p.row_ptr + u + 1) - rs); b_visits += 1;
-                    }
+                }
+                if (L == 0) {                           // statistics of the level the sweep below never visits
+                    uint32_t deg0 = 0;
+                    if (idx < le) deg0 = __ldg(p.row_ptr + u + 1) - __ldg(p.row_ptr + u);
+                    count_tile(c, deg0, idx < le);
                 }
             }
         };
@@ -442,41 +459,46 @@ wide_engine(const WideParams p) {
             const uint32_t tag_s = l + 2u, tag_p = l;
             for (uint32_t tile = lb + warp_t * 32; tile < le; tile += warps_t * 32) {
                 const uint32_t idx = tile + lane;
-                uint32_t w = 0, rs = 0, deg = 0, mypos = 0, m[kWords];
+                __syncwarp();                                       // the previous tile's staged state is no longer read
+                uint32_t total;
+                {
+                    uint32_t rs = 0, deg = 0, c = 0;
+                    if (idx < le) {
+                        const uint32_t w = queue_v[idx];
+                        uint32_t m[kWords];
+                        WT::unpack(queue_m[idx], m);
+                        *reinterpret_cast<Vec *>(&s_tile_m[warp][lane][0]) = WT::pack(m);
+                        s_tile_p[warp][lane] = queue_p[idx];
+                        rs = __ldg(p.row_ptr + w);
+                        deg = __ldg(p.row_ptr + w + 1) - rs;
 #pragma unroll
-                for (int wd = 0; wd < kWords; ++wd) m[wd] = 0;
-                if (idx < le) {
-                    w = queue_v[idx];
-                    WT::unpack(queue_m[idx], m);
-                    mypos = queue_p[idx];
-                    rs = __ldg(p.row_ptr + w);
-                    deg = __ldg(p.row_ptr + w + 1) - rs;
-                    uint32_t c = 0;
-#pragma unroll
-                    for (int wd = 0; wd < kWords; ++wd) c += __popc(m[wd]);
-                    b_reached += c; b_edges += c * deg; b_visits += 1;
+                        for (int wd = 0; wd < kWords; ++wd) c += __popc(m[wd]);
+                    }
+                    count_tile(c, deg, idx < le);
+                    const uint32_t incl = warp_inclusive_scan(deg, lane);
+                    total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    s_tile_rs[warp][lane] = rs;
+                    s_tile_off[warp][lane] = incl - deg;
+                    s_tile_end[warp][lane] = incl;
+                    s_tile_t[warp][lane] = 0.0;
                 }
-                const uint32_t incl = warp_inclusive_scan(deg, lane);
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                const uint32_t off = incl - deg;
+                __syncwarp();
                 // per-entry state of this lane: up to kWords sources (ranks lane, lane + 32, ...)
                 int cur = -1;
                 uint32_t cur_end = 0, c_cur = 0, pos_cur = 0;
                 uint32_t cell[kWords], sel[kWords], npred[kWords];     // byte offset of the source's cell in a cooked row, its bit, predecessors so far
-                double acc[kWords], my_total = 0.0;
+                double acc[kWords];
 #pragma unroll
                 for (int h = 0; h < kWords; ++h) { cell[h] = 0; sel[h] = 0; npred[h] = 0; acc[h] = 0.0; }
 
                 auto begin_entry = [&]() {
                     uint32_t mc[kWords], pre[kWords + 1];
                     pre[0] = 0;
+                    WT::unpack(*reinterpret_cast<const Vec *>(&s_tile_m[warp][cur][0]), mc);      // broadcast reads
 #pragma unroll
-                    for (int wd = 0; wd < kWords; ++wd) {
-                        mc[wd] = __shfl_sync(0xFFFFFFFFu, m[wd], cur);
-                        pre[wd + 1] = pre[wd] + __popc(mc[wd]);
-                    }
+                    for (int wd = 0; wd < kWords; ++wd) pre[wd + 1] = pre[wd] + __popc(mc[wd]);
                     c_cur = pre[kWords];
-                    pos_cur = __shfl_sync(0xFFFFFFFFu, mypos, cur);
+                    pos_cur = s_tile_p[warp][cur];
                     __syncwarp();                                   // the previous entry's list has been read by every lane
                     {
                         const unsigned kl = (unsigned)__cvta_generic_to_shared(&s_klist[warp][0]);
@@ -508,7 +530,7 @@ wide_engine(const WideParams p) {
                         }
                     }
                     const double tot = warp_sum(contrib);
-                    if (lane == cur) my_total = tot;
+                    if (lane == 0) s_tile_t[warp][cur] = tot;
                 };
                 // kRows rows of the current entry starting at row r of the cooked chunk in `rows`, kSlots sources per
                 // lane.  Straight-line: every q load of the group is issued (predicated) before the first is consumed.
@@ -536,10 +558,12 @@ wide_engine(const WideParams p) {
 
                 auto edge_of = [&](uint32_t t0) -> uint32_t {     // neighbour id of flattened entry t0 + lane
                     const uint32_t t = t0 + lane;
-                    const int o = tile_owner(incl, t);
-                    const uint32_t rs_o = __shfl_sync(0xFFFFFFFFu, rs, o);
-                    const uint32_t off_o = __shfl_sync(0xFFFFFFFFu, off, o);
-                    return t < total ? __ldg(p.col_idx + rs_o + (t - off_o)) : kWideInvalid;
+                    if (t >= total) return kWideInvalid;
+                    int o = 0;                                    // first entry whose rows end beyond t (zero-row entries are skipped)
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1)
+                        if (s_tile_end[warp][o + step - 1] <= t) o += step;
+                    return __ldg(p.col_idx + s_tile_rs[warp][o] + (t - s_tile_off[warp][o]));
                 };
                 auto stage_rows = [&](int buf, uint32_t xs) {     // level-record blocks of the chunk whose neighbour ids are `xs` (lane r: row r)
 #pragma unroll
@@ -600,7 +624,7 @@ wide_engine(const WideParams p) {
                         const uint32_t tt = t0 + r;
                         if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start
                             if (cur >= 0) finish_entry();
-                            do { ++cur; cur_end = __shfl_sync(0xFFFFFFFFu, incl, cur); } while (tt >= cur_end);
+                            do { ++cur; cur_end = s_tile_end[warp][cur]; } while (tt >= cur_end);
                             begin_entry();
                         }
                         const uint32_t left = min(cur_end - tt, cnt - r);      // rows of this entry inside this chunk
@@ -629,12 +653,10 @@ wide_engine(const WideParams p) {
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 if (cur >= 0) finish_entry();
-                if (idx < le && deg != 0) bslot[w] += my_total;     // one writer per vertex per level
+                __syncwarp();
+                if (idx < le) bslot[queue_v[idx]] += s_tile_t[warp][lane];     // one writer per vertex per level
             }
         }
-        atomicAdd(&s_cnt[0], (unsigned long long)b_reached);
-        atomicAdd(&s_cnt[1], (unsigned long long)b_edges);
-        atomicAdd(&s_cnt[2], (unsigned long long)b_visits);
         if (threadIdx.x == 0) { if (team_rank == 0) p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
         cluster.sync();
     }
