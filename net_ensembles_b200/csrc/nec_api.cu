@@ -655,22 +655,29 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
         const size_t qcap = std::min((size_t)n * kw + kw, (size_t)n * per_vertex + kw);
         const size_t ps = wide_per_slot_bytes(n, kw, qcap, max_levels);
         const uint32_t n_batches = (n_sources + kw - 1) / kw;
-        uint32_t slots = (uint32_t)std::min<size_t>(std::min<uint32_t>(n_batches, ctas_total), budget / ps);
-        if (slots == 0) continue;
-        uint32_t team = std::min<uint32_t>(8u, std::max<uint32_t>(1u, ctas_total / slots));
-        if (const char *env = getenv("NEC_WIDE_TEAM")) team = (uint32_t)std::min(8, std::max(1, atoi(env)));
-        int cap = 0;
-        for (; team >= 1; --team) {                                       // clusters are placed per GPC: ask how many fit
-            cap = wide_capacity(ctx, kw, threads, team);
-            if (cap > 0) break;
+        const uint32_t fit = (uint32_t)std::min<size_t>(n_batches, budget / ps);
+        if (fit == 0) continue;
+        // every team size the slots allow: `team` CTAs per slot fill the GPU from ctas_total / team slots (clusters are
+        // placed per GPC, so the driver is asked how many of each size can be resident)
+        uint32_t t_lo = 1, t_hi = 8;
+        if (const char *env = getenv("NEC_WIDE_TEAM")) {                 // tests / A-B runs: this team size, or the largest below it that fits
+            t_hi = (uint32_t)std::min(8, std::max(1, atoi(env)));
+            while (t_hi > 1 && wide_capacity(ctx, kw, threads, t_hi) <= 0) --t_hi;
+            t_lo = t_hi;
         }
-        if (cap <= 0) continue;
-        slots = std::min<uint32_t>(slots, (uint32_t)cap);
-        // relative cost: waves x time of one batch; a batch's work grows slower than its width (the forward pass and
-        // the row traffic are per batch), and more threads per batch finish it sooner (~ threads^0.75 measured)
-        const double waves = (double)((n_batches + slots - 1) / slots);
-        const double cost = waves * (kw == 128 ? 1.45 : 1.0) / pow((double)team * threads / 512.0, 0.75);
-        if (cost < best_cost) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps}; }
+        for (uint32_t team = t_lo; team <= t_hi; ++team) {
+            const int cap = wide_capacity(ctx, kw, threads, team);
+            if (cap <= 0) continue;
+            const uint32_t slots = std::min<uint32_t>(std::min<uint32_t>(fit, (uint32_t)cap), std::max<uint32_t>(1u, ctas_total / team));
+            // relative cost: waves x time of one batch.  Measured (scripts/exp_wide_teams.py): a batch's time is
+            // inversely proportional to the threads working on it (12 batches alone on the GPU: 2321 / 1178 / 809 /
+            // 615 / 429 / 337 ms with 1 / 2 / 3 / 4 / 6 / 8 CTAs each), with the GPU full the throughput does not depend
+            // on the team size, and a 128-wide batch costs 1.5 x a 64-wide one (its forward pass and row traffic are
+            // per batch).  Equal costs keep the smaller team: more slots, finer last wave.
+            const double waves = (double)((n_batches + slots - 1) / slots);
+            const double cost = waves * (kw == 128 ? 1.5 : 1.0) / ((double)team * threads / 512.0);
+            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps}; }
+        }
     }
     if (best.slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one wide-engine slot for n=%u", budget, n);
     out = best;
