@@ -1635,27 +1635,10 @@ int nec_bfs_debug(nec_ctx *ctx, const nec_graph *g, uint32_t source, uint32_t *d
     return NEC_OK;
 } NEC_CATCH_ALL(ctx)
 
-int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
-                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) try {
-    if (!ctx) return NEC_EINVAL;
-    if (!g || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_distance_measures: NULL argument");
+// Distance measures of `sources` on ONE device (the context's own): forward pass of the engine the graph size selects.
+static int distance_measures_one_device(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                                        uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) {
     ctx->stats = nec_stats{};
-    if (n_sources == 0 || g->n == 0) return NEC_OK;
-    if (!ctx->peers.empty()) {
-        // per-source outputs: contiguous shares of the source list, one per device, nothing to combine
-        const size_t nd = n_devices_of(ctx);
-        if (g->replicas.size() + 1 != nd) return fail(ctx, NEC_EINVAL, "graph was not uploaded through this multi-device context");
-        int rcm = on_all_devices(ctx, [&](size_t d) {
-            const uint32_t k0 = (uint32_t)((uint64_t)n_sources * d / nd), k1 = (uint32_t)((uint64_t)n_sources * (d + 1) / nd);
-            nec_ctx *c = device_ctx(ctx, d);
-            nec_graph shallow = *device_graph(g, d);          // a single-device view of this device's replica
-            shallow.replicas.clear();
-            return nec_distance_measures(c, &shallow, sources + k0, k1 - k0, ecc ? ecc + k0 : nullptr,
-                                         sum_dist ? sum_dist + k0 : nullptr, reached ? reached + k0 : nullptr);
-        });
-        if (rcm == NEC_OK) merge_device_stats(ctx);
-        return rcm;
-    }
     NEC_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = grow(ctx, ctx->d_mecc, ctx->d_mecc_cap, n_sources)) != NEC_OK) return rc;
@@ -1698,6 +1681,31 @@ int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sour
     if (reached) NEC_CUDA(ctx, cudaMemcpyAsync(reached, mo.reached, (size_t)n_sources * 4, cudaMemcpyDeviceToHost, ctx->stream));
     NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NEC_OK;
+}
+
+int nec_distance_measures(nec_ctx *ctx, const nec_graph *g, const uint32_t *sources, uint32_t n_sources,
+                          uint32_t *ecc, uint64_t *sum_dist, uint32_t *reached) try {
+    if (!ctx) return NEC_EINVAL;
+    if (!g || (n_sources && !sources)) return fail(ctx, NEC_EINVAL, "nec_distance_measures: NULL argument");
+    ctx->stats = nec_stats{};
+    if (n_sources == 0 || g->n == 0) return NEC_OK;
+    if (!ctx->peers.empty()) {
+        // per-source outputs: contiguous shares of the source list, one per device, nothing to combine
+        const size_t nd = n_devices_of(ctx);
+        if (g->replicas.size() + 1 != nd) return fail(ctx, NEC_EINVAL, "graph was not uploaded through this multi-device context");
+        int rcm = on_all_devices(ctx, [&](size_t d) {
+            const uint32_t k0 = (uint32_t)((uint64_t)n_sources * d / nd), k1 = (uint32_t)((uint64_t)n_sources * (d + 1) / nd);
+            nec_ctx *c = device_ctx(ctx, d);
+            nec_graph shallow = *device_graph(g, d);          // a single-device view of this device's replica
+            shallow.replicas.clear();
+            if (k1 == k0) { c->stats = nec_stats{}; return (int)NEC_OK; }
+            return distance_measures_one_device(c, &shallow, sources + k0, k1 - k0, ecc ? ecc + k0 : nullptr,
+                                                sum_dist ? sum_dist + k0 : nullptr, reached ? reached + k0 : nullptr);
+        });
+        if (rcm == NEC_OK) merge_device_stats(ctx);
+        return rcm;
+    }
+    return distance_measures_one_device(ctx, g, sources, n_sources, ecc, sum_dist, reached);
 } NEC_CATCH_ALL(ctx)
 
 int nec_vertex_load_batch(nec_ctx *ctx, uint32_t n_graphs, const uint32_t *n_per_graph, const uint64_t *row_ptr_offsets,
