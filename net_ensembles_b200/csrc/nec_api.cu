@@ -581,6 +581,9 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
 }
 
 // ---- compact (wide) engine, nec_wide.cuh ------------------------------------------------------------------------
+#ifndef NEC_WIDE_SMALL_CTA
+#define NEC_WIDE_SMALL_CTA 512       // the alternative CTA shape (NEC_WIDE_THREADS selects it): 512 threads, two CTAs per SM
+#endif
 size_t wide_per_slot_bytes(uint32_t n, uint32_t kw, size_t qcap, uint32_t max_levels) {
     const size_t qpitch = align_up(qcap, 64);
     size_t b = 0;
@@ -619,8 +622,8 @@ int wide_capacity_t(uint32_t team) {
 int wide_capacity(nec_ctx *ctx, uint32_t kw, uint32_t threads, uint32_t team) {
     int &cached = ctx->wide_cap[kw == 128][threads == 1024][team];
     if (cached < 0)
-        cached = kw == 128 ? (threads == 1024 ? wide_capacity_t<128, 1024>(team) : wide_capacity_t<128, 512>(team))
-                           : (threads == 1024 ? wide_capacity_t<64, 1024>(team) : wide_capacity_t<64, 512>(team));
+        cached = kw == 128 ? (threads == 1024 ? wide_capacity_t<128, 1024>(team) : wide_capacity_t<128, NEC_WIDE_SMALL_CTA>(team))
+                           : (threads == 1024 ? wide_capacity_t<64, 1024>(team) : wide_capacity_t<64, NEC_WIDE_SMALL_CTA>(team));
     return cached;
 }
 template <int kW, int kThreads>
@@ -640,8 +643,8 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
     NEC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = ctx->ws_limit ? (size_t)ctx->ws_limit : (size_t)((double)(free_b + ctx->arena.bytes + ctx->wide.bytes) * 0.8);
     uint32_t threads = 1024;
-    if (const char *env = getenv("NEC_WIDE_THREADS")) threads = atoi(env) == 512 ? 512u : 1024u;
-    const uint32_t ctas_total = threads == 1024 ? sms : 2 * sms;
+    if (const char *env = getenv("NEC_WIDE_THREADS")) threads = atoi(env) == 1024 ? 1024u : (uint32_t)NEC_WIDE_SMALL_CTA;
+    const uint32_t ctas_total = threads <= 512 ? 2 * sms : sms;
     const uint32_t max_levels = n;
     // queue entries per vertex the slot has room for: a vertex sits on a handful of distinct levels within one batch
     // on the graphs this engine is meant for; batches that need more are handed to the source-minor engine
@@ -748,8 +751,8 @@ int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources
     p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride; p.max_levels = a.max_levels;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, 512>(ctx, p, slots, pl.team);
-    else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, 512>(ctx, p, slots, pl.team);
+    if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
     if (rc != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
