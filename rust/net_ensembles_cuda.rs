@@ -95,7 +95,7 @@ impl CudaContext {
         unsafe { nec_get_stats(self.raw, &mut s) };
         s
     }
-    /// 0 auto, 1 batched engine, 2 one-source-per-CTA engine (tests / profiling).
+    /// 0 auto, 1 source-minor batched engine, 2 one-source-per-CTA engine, 3 compact batched engine (tests / profiling).
     pub fn set_engine(&self, engine: i32) { self.check(unsafe { nec_set_engine(self.raw, engine) }, "nec_set_engine") }
     pub fn set_workspace_limit(&self, bytes: u64) { self.check(unsafe { nec_set_workspace_limit(self.raw, bytes) }, "nec_set_workspace_limit") }
     /// Run on a caller's cudaStream_t (single-device contexts).
