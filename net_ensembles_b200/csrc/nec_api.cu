@@ -95,8 +95,10 @@ struct nec_ctx {
     size_t d_mecc_cap = 0, d_mreach_cap = 0, d_msum_cap = 0, d_pecc_cap = 0, d_preach_cap = 0, d_psum_cap = 0, d_scatter_cap = 0;
     int occ_u8 = 0, occ_u32 = 0;
     void *mid_base = nullptr; size_t mid_bytes = 0;   // arena of the one-source-per-CTA engine
-    uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;
+    uint8_t *d_src_status = nullptr; size_t d_src_status_cap = 0;   // mid engine: [8 counters | per-source status], one memset and one copy back per call
     bool mid_attr_set = false;
+    uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;      // pinned host staging of a call's small transfers (source list in, verdicts + counters out)
+    struct { uint32_t n = 0; int slab_w = 0, threads = 0, occ = 0; } mid_occ;   // occupancy of the last mid-engine shape asked for
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
     double *dbg_sigma = nullptr;                      // nec_bfs_debug: plane for the path counts of the debug instantiation
     uint32_t pull_mode = 1;                           // batched forward pass: 0 push only, 1 per-level cost model, 2 pull only (NEC_PULL, tests)
@@ -148,6 +150,16 @@ int grow(nec_ctx *ctx, T *&ptr, size_t &cap, size_t need) {
     ptr = nullptr; cap = 0;
     NEC_CUDA(ctx, cudaMalloc((void **)&ptr, need * sizeof(T)));
     cap = need;
+    return NEC_OK;
+}
+
+int grow_pinned(nec_ctx *ctx, size_t need) {
+    if (need <= ctx->h_pin_cap) return NEC_OK;
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+    const size_t cap = std::max<size_t>(need + need / 2, 1 << 16);
+    NEC_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, cap));
+    ctx->h_pin_cap = cap;
     return NEC_OK;
 }
 
@@ -824,18 +836,21 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     const bool small_ctas = n <= small_n;
     const int threads = small_ctas ? nec::kMidThreadsSmall : nec::kMidThreads;
     const size_t smem = nec::mid_smem_bytes(n, g->slab_w, threads);
-    {   // per device (a process may hold contexts on several devices): set on every call
+    int occ = 0;
+    if (ctx->mid_occ.occ > 0 && ctx->mid_occ.n == n && ctx->mid_occ.slab_w == g->slab_w && ctx->mid_occ.threads == threads) occ = ctx->mid_occ.occ;
+    else {
+        // the attribute is per device; this context is bound to one device, so once per context (and shape) suffices
         const int big = (int)(227 * 1024 - 4096);
         NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         NEC_CUDA(ctx, cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    }
-    int occ = 0;
-    if (small_ctas) {
-        if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8, nec::kMidThreadsSmall>, threads, smem));
-        else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16, nec::kMidThreadsSmall>, threads, smem));
-    } else {
-        if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8>, threads, smem));
-        else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16>, threads, smem));
+        if (small_ctas) {
+            if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8, nec::kMidThreadsSmall>, threads, smem));
+            else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16, nec::kMidThreadsSmall>, threads, smem));
+        } else {
+            if (g->slab_w == 8) NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<8>, threads, smem));
+            else NEC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nec::mid_engine<16>, threads, smem));
+        }
+        ctx->mid_occ.n = n; ctx->mid_occ.slab_w = g->slab_w; ctx->mid_occ.threads = threads; ctx->mid_occ.occ = occ;
     }
     if (occ < 1) return fail(ctx, NEC_ECUDA, "mid engine cannot be resident for n=%u (%zu B shared memory)", n, smem);
     if (const char *env = getenv("NEC_MID_CTAS_PER_SM")) {       // profiling knob
@@ -863,14 +878,22 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     }
     int rc;
     if ((rc = grow(ctx, ctx->d_sources, ctx->d_sources_cap, n_sources)) != NEC_OK) return rc;
-    if ((rc = grow(ctx, ctx->d_src_status, ctx->d_src_status_cap, n_sources)) != NEC_OK) return rc;
+    // device: [8 counters | status per source] in one buffer (one memset, one copy back); host: pinned staging for the
+    // source list and for that buffer, so that every transfer of the call is asynchronous and the host waits once
+    const size_t ret_bytes = 64 + (size_t)n_sources;
+    if ((rc = grow(ctx, ctx->d_src_status, ctx->d_src_status_cap, ret_bytes)) != NEC_OK) return rc;
+    const size_t src_bytes = align_up((size_t)n_sources * 4, 64);
+    if ((rc = grow_pinned(ctx, src_bytes + ret_bytes)) != NEC_OK) return rc;
+    uint8_t *h_ret = ctx->h_pin + src_bytes;
+    unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(ctx->d_src_status);
+    uint8_t *d_status = ctx->d_src_status + 64;
     double *d_q = (double *)ctx->mid_base;
     double *d_bslot = d_q + q_stride * slots;
     uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
     uint4 *d_pos4 = (uint4 *)(d_order + o_stride * slots);   // o_stride entries per slot; 256 B aligned since o_stride*4 is
-    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, h_sources, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
-    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, n_sources, ctx->stream));
-    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    memcpy(ctx->h_pin, h_sources, (size_t)n_sources * 4);
+    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, ctx->h_pin, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, ret_bytes, ctx->stream));
     NEC_CUDA(ctx, cudaMemsetAsync(d_bslot, 0, q_stride * 8 * slots, ctx->stream));
     nec::MidParams p{};
     p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab; p.deg8 = g->d_deg8;
@@ -878,7 +901,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
     p.pos4_base = d_pos4;
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
-    p.source_status = ctx->d_src_status; p.counters = ctx->d_counters;
+    p.source_status = d_status; p.counters = d_counters;
     if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (small_ctas) {
@@ -895,11 +918,11 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
         NEC_CUDA(ctx, cudaGetLastError());
     }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    std::vector<uint8_t> status(n_sources);
-    unsigned long long counters[8];
-    NEC_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_src_status, n_sources, cudaMemcpyDeviceToHost, ctx->stream));
-    NEC_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    NEC_CUDA(ctx, cudaMemcpyAsync(h_ret, ctx->d_src_status, ret_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long counters[8];
+    memcpy(counters, h_ret, sizeof counters);
+    const uint8_t *status = h_ret + 64;
     float ms = 0.f;
     NEC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms = ms;
@@ -1197,6 +1220,7 @@ void nec_destroy(nec_ctx *ctx) {
         if (ptr) cudaFree(ptr);
     if (ctx->mid_base) cudaFree(ctx->mid_base);
     if (ctx->d_src_status) cudaFree(ctx->d_src_status);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     ctx->small.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_sample) cudaFree(ctx->d_sample);
