@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/net_ensembles_cuda.h"
@@ -113,18 +114,22 @@ small_graph_kernel(const SmallParams p) {
             }
         }
         __syncthreads();
+        // Everything below runs once per graph in one of two instantiations - CSR staged in shared memory (the normal
+        // case) or read from global memory - so that no adjacency access of the hot loops carries a branch.
+        auto run_graph = [&](auto staged_tag) {
+        constexpr bool kStaged = decltype(staged_tag)::value;
         // rows are [row_begin(v), row_end(v)) of col_at(.)
         auto row_begin = [&](uint32_t v) -> uint32_t {
-            if (staged) return s_rp[v];
-            if constexpr (kChain) return v * cap; else return __ldg(rp_g + v);
+            if constexpr (kStaged) return s_rp[v];
+            else if constexpr (kChain) return v * cap; else return __ldg(rp_g + v);
         };
         auto row_end = [&](uint32_t v) -> uint32_t {
-            if (staged) return s_rp[v + 1];
-            if constexpr (kChain) return v * cap + (uint32_t)deg_g[v]; else return __ldg(rp_g + v + 1);
+            if constexpr (kStaged) return s_rp[v + 1];
+            else if constexpr (kChain) return v * cap + (uint32_t)deg_g[v]; else return __ldg(rp_g + v + 1);
         };
         auto col_at = [&](uint32_t e) -> uint32_t {
-            if (staged) return (uint32_t)s_col[e];
-            if constexpr (kChain) return (uint32_t)rows_g[e]; else return __ldg(col_g + e);
+            if constexpr (kStaged) return (uint32_t)s_col[e];
+            else if constexpr (kChain) return (uint32_t)rows_g[e]; else return __ldg(col_g + e);
         };
         unsigned char *mine = smem_raw + (size_t)warp * small_warp_bytes(n);
         double *q = reinterpret_cast<double *>(mine);
@@ -142,7 +147,9 @@ small_graph_kernel(const SmallParams p) {
             __syncwarp();
             // ---- forward: level by level inside the warp -----------------------------------
             uint32_t lb = 0, le = 1, level = 0;
+            uint32_t lvl_start = 0;                         // lane L keeps the queue position where level L starts (levels < 32)
             while (lb < le) {
+                if ((uint32_t)lane == level) lvl_start = lb;
                 uint32_t tail = le;
                 for (uint32_t base = lb; base < le; base += 32) {
                     const uint32_t i = base + lane;
@@ -181,9 +188,11 @@ small_graph_kernel(const SmallParams p) {
             // order[] is sorted by level; level l occupies a contiguous range ending at `hi`
             uint32_t hi = le;                               // == number of reached vertices
             for (uint32_t l = depth; l >= 1; --l) {
-                // find the start of level l: entries [lo, hi) have dist == l
+                // the start of level l: entries [lo, hi) have dist == l.  Kept from the forward pass for the first 32
+                // levels; deeper ones are found by stepping back through the order
                 uint32_t lo = hi;
-                for (;;) {                                  // step back in chunks of 32
+                if (l < 32u) lo = __shfl_sync(0xFFFFFFFFu, lvl_start, (int)l);
+                else for (;;) {                             // step back in chunks of 32
                     const uint32_t probe = lo > 32 ? lo - 32 : 0;
                     const uint32_t j = probe + lane;
                     const bool same = j < lo && dist[order[j]] == l;
@@ -227,6 +236,9 @@ small_graph_kernel(const SmallParams p) {
             }
             __syncwarp();
         }
+        };                                              // run_graph
+        if (staged) run_graph(std::true_type{});
+        else run_graph(std::false_type{});
         __syncthreads();
         // ---- warps' partial loads, summed in warp order ------------------------------------------
         double *out = p.out + p.out_off[g];
