@@ -495,6 +495,17 @@ def test_full_size_properties_config4_gnm(ctx, oracle):
     src = (np.arange(9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
     st = _full_size_properties(ctx, oracle, rp, col, src, 4, 128)
     assert st["team_size"] == 2 and st["cta_threads"] == 1024 and st["n_slots"] == 74 and st["pull_levels"] > 0
+    # the plan must not depend on how many waves a call carries: the full job and a two-wave call get the same shape
+    dg = ctx.upload(rp, col)
+    assert dg.wave_size() == 74 * 128
+    two = (np.arange(2 * 9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
+    both = dg.vertex_load_sources(two, True)
+    st2 = ctx.stats()
+    assert (st2["batch_width"], st2["team_size"], st2["n_slots"], st2["n_batches"]) == (128, 2, 74, 148)
+    first = dg.vertex_load_sources(two[:9472], True)
+    second = dg.vertex_load_sources(two[9472:], True)
+    assert close(both, first + second, 1e-12)
+    dg.free()
     assert st["requeued_batches"] == 0 and 9472 * ((1 << 20) - 2000) < st["reached_pairs"] <= 9472 * (1 << 20)   # a few hundred isolated vertices
 
 
