@@ -55,6 +55,7 @@ struct WideArena {                   // per-slot scratch of the compact (wide) e
     double *bslot = nullptr; size_t bslot_stride = 0;
     uint32_t *queue_v = nullptr, *queue_p = nullptr; uint8_t *queue_m = nullptr; size_t queue_stride = 0;
     uint32_t *lvl = nullptr; size_t lvl_stride = 0;
+    uint32_t *bq = nullptr, *bcnt = nullptr; size_t bq_stride = 0;   // 256 sources per batch: the backward work list and its per-level counts
 };
 
 }  // namespace
@@ -80,7 +81,7 @@ struct nec_ctx {
     uint64_t ws_limit = 0;
     Arena arena;
     WideArena wide;
-    int wide_cap[2][2][9];                            // resident clusters per (width 64/128, CTA 512/1024 threads, team size); -1 = not asked yet
+    int wide_cap[3][2][9];                            // resident clusters per (width 64/128/256, CTA 512/1024 threads, team size); -1 = not asked yet
     // small device buffers reused across calls
     uint32_t *d_sources = nullptr; size_t d_sources_cap = 0;
     uint8_t *d_status = nullptr;   size_t d_status_cap = 0;
@@ -593,6 +594,10 @@ int run_sources_batched(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sour
 }
 
 // ---- compact (wide) engine, nec_wide.cuh ------------------------------------------------------------------------
+#ifndef NEC_WIDE_COST256
+#define NEC_WIDE_COST256 2.6         // planner: time of a 256-wide batch relative to a 64-wide one on the same threads (128-wide: 1.5);
+                                     // measured on config 4: 484 ms on 3 CTAs against 414 ms on 2 CTAs for a 128-wide batch
+#endif
 #ifndef NEC_WIDE_SMALL_CTA
 #define NEC_WIDE_SMALL_CTA 512       // the alternative CTA shape (NEC_WIDE_THREADS selects it): 512 threads, two CTAs per SM
 #endif
@@ -602,9 +607,10 @@ size_t wide_per_slot_bytes(uint32_t n, uint32_t kw, size_t qcap, uint32_t max_le
     b += align_up((size_t)n * (kw / 2), 256);                       // forward records
     b += align_up((size_t)n * kw, 256);                             // level records: 4 slots of kw / 4 bytes
     b += align_up(((size_t)n * kw + 64) * sizeof(double), 256);     // compact q runs
-    b += align_up((size_t)n * sizeof(double), 256);                 // private partial load
+    b += align_up((size_t)n * sizeof(double), 256) * (kw == 256 ? 2 : 1);   // private partial load (256 per batch: one per half of an entry)
     b += qpitch * 4 * 2 + qpitch * (kw / 8);                        // queue: vertex, position, mask
     b += align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);
+    if (kw == 256) b += 2 * qpitch * 4 + align_up(((size_t)max_levels + 2) * sizeof(uint32_t), 256);   // backward work list, per-level counts
     return b;
 }
 
@@ -632,9 +638,10 @@ int wide_capacity_t(uint32_t team) {
     return n;
 }
 int wide_capacity(nec_ctx *ctx, uint32_t kw, uint32_t threads, uint32_t team) {
-    int &cached = ctx->wide_cap[kw == 128][threads == 1024][team];
+    int &cached = ctx->wide_cap[kw == 64 ? 0 : kw == 128 ? 1 : 2][threads == 1024][team];
     if (cached < 0)
-        cached = kw == 128 ? (threads == 1024 ? wide_capacity_t<128, 1024>(team) : wide_capacity_t<128, NEC_WIDE_SMALL_CTA>(team))
+        cached = kw == 256 ? (threads == 1024 ? wide_capacity_t<256, 1024>(team) : wide_capacity_t<256, NEC_WIDE_SMALL_CTA>(team))
+               : kw == 128 ? (threads == 1024 ? wide_capacity_t<128, 1024>(team) : wide_capacity_t<128, NEC_WIDE_SMALL_CTA>(team))
                            : (threads == 1024 ? wide_capacity_t<64, 1024>(team) : wide_capacity_t<64, NEC_WIDE_SMALL_CTA>(team));
     return cached;
 }
@@ -664,7 +671,7 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
     if (const char *env = getenv("NEC_WIDE_QUEUE")) per_vertex = (size_t)std::max(1, atoi(env));
     WidePlan best{};
     double best_cost = 1e300;
-    for (uint32_t kw : {128u, 64u}) {
+    for (uint32_t kw : {256u, 128u, 64u}) {
         if (const char *env = getenv("NEC_WIDE_WIDTH")) { if ((uint32_t)atoi(env) != kw) continue; }
         if ((uint64_t)n * kw + kw >= 0xFFFFFFFFull) continue;           // 32-bit positions and queue indices
         const size_t qcap = std::min((size_t)n * kw + kw, (size_t)n * per_vertex + kw);
@@ -687,10 +694,10 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
             // relative cost: waves x time of one batch.  Measured (scripts/exp_wide_teams.py): a batch's time is
             // inversely proportional to the threads working on it (12 batches alone on the GPU: 2321 / 1178 / 809 /
             // 615 / 429 / 337 ms with 1 / 2 / 3 / 4 / 6 / 8 CTAs each), with the GPU full the throughput does not depend
-            // on the team size, and a 128-wide batch costs 1.5 x a 64-wide one (its forward pass and row traffic are
-            // per batch).  Equal costs keep the smaller team: more slots, finer last wave.
+            // on the team size, and a 128-wide batch costs 1.5 x a 64-wide one, a 256-wide one 2.6 x (the forward pass and
+            // the row traffic are per batch).  Equal costs keep the smaller team: more slots, finer last wave.
             const double waves = (double)((n_batches + slots - 1) / slots);
-            const double cost = waves * (kw == 128 ? 1.5 : 1.0) / ((double)team * threads / 512.0);
+            const double cost = waves * (kw == 256 ? NEC_WIDE_COST256 : kw == 128 ? 1.5 : 1.0) / ((double)team * threads / 512.0);
             if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps}; }
         }
     }
@@ -720,11 +727,16 @@ int ensure_wide_arena(nec_ctx *ctx, uint32_t n, const WidePlan &pl) {
     a.rec = carve((size_t)n * (kw / 2));                           a.rec_stride = align_up((size_t)n * (kw / 2), 256);
     a.lr = carve((size_t)n * kw);                                  a.lr_stride = align_up((size_t)n * kw, 256);
     a.qc = (double *)carve(((size_t)n * kw + 64) * 8);             a.qc_stride = align_up(((size_t)n * kw + 64) * 8, 256) / 8;
-    a.bslot = (double *)carve((size_t)n * 8);                      a.bslot_stride = align_up((size_t)n * 8, 256) / 8;
+    const size_t bhalf = align_up((size_t)n * 8, 256);             // 256 per batch: two partial loads per slot (first / second half of an entry)
+    a.bslot = (double *)carve(kw == 256 ? 2 * bhalf : (size_t)n * 8); a.bslot_stride = (kw == 256 ? 2 * bhalf : bhalf) / 8;
     a.queue_v = (uint32_t *)carve(qpitch * 4);                     a.queue_stride = qpitch;
     a.queue_p = (uint32_t *)carve(qpitch * 4);
     a.queue_m = carve(qpitch * (kw / 8));
     a.lvl = (uint32_t *)carve(((size_t)pl.max_levels + 2) * 4);    a.lvl_stride = align_up(((size_t)pl.max_levels + 2) * 4, 256) / 4;
+    if (kw == 256) {
+        a.bq = (uint32_t *)carve(2 * qpitch * 4);                  a.bq_stride = 2 * qpitch;
+        a.bcnt = (uint32_t *)carve(((size_t)pl.max_levels + 2) * 4);
+    }
     return NEC_OK;
 }
 
@@ -761,13 +773,18 @@ int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources
     p.bslot_base = a.bslot; p.bslot_stride = a.bslot_stride;
     p.queue_v_base = a.queue_v; p.queue_m_base = a.queue_m; p.queue_p_base = a.queue_p; p.queue_stride = a.queue_stride; p.queue_cap = a.qcap;
     p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride; p.max_levels = a.max_levels;
+    p.bq_base = a.bq; p.bq_stride = a.bq_stride; p.bcnt_base = a.bcnt; p.bslot_hi_off = a.bslot_stride / 2;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    if (kw == 256) rc = pl.threads == 1024 ? launch_wide_t<256, 1024>(ctx, p, slots, pl.team) : launch_wide_t<256, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    else if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
     else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
     if (rc != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-    nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
+    if (kw == 256)    // two partial loads per slot, summed in (slot, half) order
+        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride / 2, 2 * slots, n, d_out);
+    else
+        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(a.bslot, a.bslot_stride, slots, n, d_out);
     NEC_CUDA(ctx, cudaGetLastError());
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<uint8_t> status(n_batches);

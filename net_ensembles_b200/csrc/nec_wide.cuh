@@ -60,26 +60,49 @@ struct WideParams {
     size_t queue_cap;                          // usable entries per slot
     uint32_t *lvl_base;  size_t lvl_stride;    // u32 per slot (max_levels + 2)
     uint32_t max_levels;
+    // 256 sources per batch only: the backward pass's work list (entries with more than 128 live sources appear twice:
+    // ranks 0..127 and 128..) with its per-level item counts, and where the second halves' partial load starts
+    uint32_t *bq_base;   size_t bq_stride;     // u32 per slot (2 x queue pitch)
+    uint32_t *bcnt_base;                       // u32 per slot (lvl_stride)
+    size_t bslot_hi_off;                       // doubles
     uint8_t *batch_status;                     // per batch id (BatchStatus)
     unsigned long long *counters;              // as EngineParams::counters
 };
 
+struct alignas(16) WideVec256 { uint4 a, b; };
 template <int kW> struct WideTraits;
 template <> struct WideTraits<128> {
     using Vec = uint4;
     static __device__ __forceinline__ void unpack(const Vec &v, uint32_t (&w)[4]) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
     static __device__ __forceinline__ Vec pack(const uint32_t (&w)[4]) { return make_uint4(w[0], w[1], w[2], w[3]); }
+    static __device__ __forceinline__ Vec ldcg(const Vec *p) { return __ldcg(p); }
+    static __device__ __forceinline__ void stcg(Vec *p, const Vec &v) { __stcg(p, v); }
 };
 template <> struct WideTraits<64> {
     using Vec = uint2;
     static __device__ __forceinline__ void unpack(const Vec &v, uint32_t (&w)[2]) { w[0] = v.x; w[1] = v.y; }
     static __device__ __forceinline__ Vec pack(const uint32_t (&w)[2]) { return make_uint2(w[0], w[1]); }
+    static __device__ __forceinline__ Vec ldcg(const Vec *p) { return __ldcg(p); }
+    static __device__ __forceinline__ void stcg(Vec *p, const Vec &v) { __stcg(p, v); }
+};
+template <> struct WideTraits<256> {
+    using Vec = WideVec256;
+    static __device__ __forceinline__ void unpack(const Vec &v, uint32_t (&w)[8]) {
+        w[0] = v.a.x; w[1] = v.a.y; w[2] = v.a.z; w[3] = v.a.w; w[4] = v.b.x; w[5] = v.b.y; w[6] = v.b.z; w[7] = v.b.w;
+    }
+    static __device__ __forceinline__ Vec pack(const uint32_t (&w)[8]) {
+        Vec v; v.a = make_uint4(w[0], w[1], w[2], w[3]); v.b = make_uint4(w[4], w[5], w[6], w[7]); return v;
+    }
+    static __device__ __forceinline__ Vec ldcg(const Vec *p) { Vec v; v.a = __ldcg(&p->a); v.b = __ldcg(&p->b); return v; }
+    static __device__ __forceinline__ void stcg(Vec *p, const Vec &v) { __stcg(&p->a, v.a); __stcg(&p->b, v.b); }
 };
 
+// Shared-memory layout (dynamic): per warp kBufs buffers of 32 staged rows (kW / 2 bytes each; two buffers, one at 256 sources
+// per batch where two would not fit), one group of rows of read-ahead padding, then the masks of each warp's tile of entries.
+template <int kW> __host__ __device__ constexpr int wide_row_bufs() { return kW == 256 ? 1 : 2; }
 template <int kW, int kThreads>
 constexpr size_t wide_smem_bytes() {
-    // per warp: two buffers of 32 staged rows (kW / 2 bytes each), plus one group of rows of read-ahead padding
-    return (size_t)(kThreads / 32) * 2 * 32 * (kW / 2) + 8 * (kW / 2);
+    return (size_t)(kThreads / 32) * wide_row_bufs<kW>() * 32 * (kW / 2) + 8 * (kW / 2) + (size_t)(kThreads / 32) * 32 * (kW / 8);
 }
 
 constexpr uint32_t kWideInvalid = 0xFFFFFFFFu;
@@ -90,7 +113,11 @@ wide_engine(const WideParams p) {
     namespace cg = cooperative_groups;
     using WT = WideTraits<kW>;
     using Vec = typename WT::Vec;
-    constexpr int kWords = kW / 32;                     // mask words; also the most sources a lane can work for
+    constexpr int kWords = kW / 32;                     // mask words
+    constexpr int kLaneSlots = kWords < 4 ? kWords : 4; // the most sources a lane works for at once (128 per pass of an entry)
+    constexpr bool kVirtual = kW == 256;                // entries with more than 128 live sources are consumed in two passes
+    constexpr int kBufs = wide_row_bufs<kW>();
+    constexpr int kPullU = kW == 256 ? 2 : kPullUnroll; // neighbours' frontier masks in flight per thread (forward, pull)
     constexpr int kVecB = kW / 8;                       // bytes of a mask
     constexpr int kRecB = kW / 2;                       // forward record: seen, next[2], claim (+ padding)
     constexpr int kSlotB = kW / 4;                      // level-record slot: mask, position, tag (+ padding at B = 128)
@@ -133,13 +160,15 @@ wide_engine(const WideParams p) {
     uint32_t *open_p = cluster.map_shared_rank(&s_open, 0);
     uint32_t *pos_p = cluster.map_shared_rank(&s_pos, 0);
     __shared__ unsigned char s_klist[kWarps][kW];        // backward: the live sources of the entry a warp is consuming
-    __shared__ __align__(16) uint32_t s_tile_m[kWarps][32][kWords];   // backward: masks and run positions of the warp's tile of entries
-    __shared__ uint32_t s_tile_p[kWarps][32];
+    __shared__ uint32_t s_tile_p[kWarps][32];             // backward: run positions of the warp's tile of entries (masks: dynamic, below)
     __shared__ uint32_t s_tile_rs[kWarps][32], s_tile_off[kWarps][32], s_tile_end[kWarps][32];   // adjacency row start, first and past-the-end flattened row of each entry
     __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
     __shared__ unsigned long long s_cnt[3];
     extern __shared__ __align__(16) unsigned char wide_smem[];
-    unsigned char *my_rows = wide_smem + (size_t)warp * 2 * 32 * kRowB;   // [2][32][kRowB]
+    unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * 32 * kRowB;   // [kBufs][32][kRowB]
+    uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * 32 * kRowB + 8 * kRowB) + (size_t)warp * 32;   // [32][kWords]
+    uint32_t *__restrict__ bq = kVirtual ? p.bq_base + (size_t)slot * p.bq_stride : nullptr;
+    uint32_t *__restrict__ bcnt = kVirtual ? p.bcnt_base + (size_t)slot * p.lvl_stride : nullptr;
 
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
@@ -211,17 +240,17 @@ wide_engine(const WideParams p) {
             // reads the masks from the records)
             for (uint32_t idx = qbeg + tid_t; idx < qend; idx += threads_t) {
                 const uint32_t u = queue_v[idx];
-                const Vec m = __ldcg(next_of(u, par_c));
-                const Vec sn = __ldcg(seen_of(u));
+                const Vec m = WT::ldcg(next_of(u, par_c));
+                const Vec sn = WT::ldcg(seen_of(u));
                 uint32_t mw[kWords], sw[kWords];
                 WT::unpack(m, mw); WT::unpack(sn, sw);
 #pragma unroll
                 for (int wd = 0; wd < kWords; ++wd) sw[wd] |= mw[wd];
-                __stcg(seen_of(u), WT::pack(sw));
+                WT::stcg(seen_of(u), WT::pack(sw));
                 if (!pull) {
 #pragma unroll
                     for (int wd = 0; wd < kWords; ++wd) sw[wd] = 0;
-                    __stcg(next_of(u, par_c), WT::pack(sw));
+                    WT::stcg(next_of(u, par_c), WT::pack(sw));
                 }
                 queue_m[idx] = m;
             }
@@ -230,7 +259,7 @@ wide_engine(const WideParams p) {
 #pragma unroll
                 for (int wd = 0; wd < kWords; ++wd) zero[wd] = 0;
                 for (uint32_t idx = defer_beg + tid_t; idx < defer_end; idx += threads_t)
-                    __stcg(next_of(queue_v[idx], par_n), WT::pack(zero));     // the pulled level-1's masks: same parity as level+1
+                    WT::stcg(next_of(queue_v[idx], par_n), WT::pack(zero));     // the pulled level-1's masks: same parity as level+1
             }
             defer_beg = pull ? qbeg : 0u;
             defer_end = pull ? qend : 0u;
@@ -267,8 +296,8 @@ wide_engine(const WideParams p) {
                         if (t < total) {
                             x = __ldg(p.col_idx + rs_o + (t - off_o));
                             uint32_t sv[kWords], nv[kWords];
-                            WT::unpack(__ldcg(seen_of(x)), sv);
-                            WT::unpack(__ldcg(next_of(x, par_n)), nv);
+                            WT::unpack(WT::ldcg(seen_of(x)), sv);
+                            WT::unpack(WT::ldcg(next_of(x, par_n)), nv);
                             bool cand = false;
 #pragma unroll
                             for (int wd = 0; wd < kWords; ++wd) {
@@ -303,7 +332,7 @@ wide_engine(const WideParams p) {
                     for (int wd = 0; wd < kWords; ++wd) { unseen[wd] = 0; acc[wd] = 0; }
                     uint32_t rs = 0, deg = 0;
                     if (x < n) {
-                        WT::unpack(__ldcg(seen_of(x)), unseen);
+                        WT::unpack(WT::ldcg(seen_of(x)), unseen);
 #pragma unroll
                         for (int wd = 0; wd < kWords; ++wd) { unseen[wd] = ~unseen[wd] & valid_src[wd]; any_unseen |= unseen[wd]; }
                         if (any_unseen) {
@@ -313,21 +342,21 @@ wide_engine(const WideParams p) {
                     }
                     const bool hub = deg > kPullHubDeg;
                     if (!hub) {
-                        for (uint32_t e = 0; e < deg; e += kPullUnroll) {
-                            uint32_t un[kPullUnroll];
-                            Vec mm[kPullUnroll];
+                        for (uint32_t e = 0; e < deg; e += kPullU) {
+                            uint32_t un[kPullU];
+                            Vec mm[kPullU];
 #pragma unroll
-                            for (int j = 0; j < kPullUnroll; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : kWideInvalid;
+                            for (int j = 0; j < kPullU; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : kWideInvalid;
 #pragma unroll
-                            for (int j = 0; j < kPullUnroll; ++j) {
+                            for (int j = 0; j < kPullU; ++j) {
                                 uint32_t z[kWords];
 #pragma unroll
                                 for (int wd = 0; wd < kWords; ++wd) z[wd] = 0;
-                                mm[j] = un[j] != kWideInvalid ? __ldcg(next_of(un[j], par_c)) : WT::pack(z);
+                                mm[j] = un[j] != kWideInvalid ? WT::ldcg(next_of(un[j], par_c)) : WT::pack(z);
                             }
                             uint32_t missing = 0;
 #pragma unroll
-                            for (int j = 0; j < kPullUnroll; ++j) {
+                            for (int j = 0; j < kPullU; ++j) {
                                 uint32_t w4[kWords];
                                 WT::unpack(mm[j], w4);
 #pragma unroll
@@ -347,7 +376,7 @@ wide_engine(const WideParams p) {
                         for (int wd = 0; wd < kWords; ++wd) a[wd] = 0;
                         for (uint32_t e = lane; e < deg_o; e += 32) {
                             uint32_t w4[kWords];
-                            WT::unpack(__ldcg(next_of(__ldg(p.col_idx + rs_o + e), par_c)), w4);
+                            WT::unpack(WT::ldcg(next_of(__ldg(p.col_idx + rs_o + e), par_c)), w4);
 #pragma unroll
                             for (int wd = 0; wd < kWords; ++wd) a[wd] |= w4[wd];
                         }
@@ -360,7 +389,7 @@ wide_engine(const WideParams p) {
                     uint32_t fresh[kWords], any_fresh = 0, still = 0;
 #pragma unroll
                     for (int wd = 0; wd < kWords; ++wd) { fresh[wd] = acc[wd] & unseen[wd]; any_fresh |= fresh[wd]; still |= unseen[wd] & ~fresh[wd]; }
-                    if (any_fresh) __stcg(next_of(x, par_n), WT::pack(fresh));     // one writer per vertex
+                    if (any_fresh) WT::stcg(next_of(x, par_n), WT::pack(fresh));     // one writer per vertex
                     my_open += still != 0 ? 1u : 0u;
                     const bool enqueue = any_fresh != 0;
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, enqueue);
@@ -384,6 +413,7 @@ wide_engine(const WideParams p) {
             ++level;
         }
         // here: levels 0..level-1 are non-empty (if !too_deep), lvl[l] = start of level l, lvl[level] = end of the last
+        if constexpr (kVirtual) for (uint32_t L = tid_t; L <= level; L += threads_t) bcnt[L] = 0;
         cluster.sync();
         const bool failed = *(volatile uint32_t *)fail_p != 0;
         if (too_deep || failed) {
@@ -436,11 +466,28 @@ wide_engine(const WideParams p) {
                 if (idx < le) {
                     queue_p[idx] = pos;
                     uint4 *dst = reinterpret_cast<uint4 *>(lr + (size_t)u * 4 * kSlotB + phys * kSlotB);
-                    if constexpr (kW == 128) {
+                    if constexpr (kW == 256) {
+                        __stcg(dst, make_uint4(m[0], m[1], m[2], m[3]));
+                        __stcg(dst + 1, make_uint4(m[4], m[5], m[6], m[7]));
+                        __stcg(dst + 2, make_uint4(pos, L + 1u, 0u, 0u));
+                    } else if constexpr (kW == 128) {
                         __stcg(dst, make_uint4(m[0], m[1], m[2], m[3]));
                         __stcg(dst + 1, make_uint4(pos, L + 1u, 0u, 0u));
                     } else
                         __stcg(dst, make_uint4(m[0], m[1], pos, L + 1u));
+                }
+                if constexpr (kVirtual) {
+                    // the level's work list: one item per entry, two (ranks 0..127, ranks 128..) if it carries more than 128 sources
+                    if (L >= 1) {
+                        const uint32_t items = idx < le ? (c > 128u ? 2u : 1u) : 0u;
+                        const uint32_t incl = warp_inclusive_scan(items, lane);
+                        uint32_t b = 0;
+                        if (lane == 31 && incl) b = atomicAdd(&bcnt[L], incl);
+                        b = __shfl_sync(0xFFFFFFFFu, b, 31);
+                        const uint32_t at = 2u * lb + b + incl - items;
+                        if (items >= 1u) bq[at] = idx;
+                        if (items == 2u) bq[at + 1] = idx | 0x80000000u;
+                    }
                 }
                 if (L == 0) {                           // statistics of the level the sweep below never visits
                     uint32_t deg0 = 0;
@@ -453,28 +500,49 @@ wide_engine(const WideParams p) {
         for (uint32_t l = depth; l >= 1; --l) {
             prepare(l - 1);
             cluster.sync();                              // level l+1 fully processed (its q values stored), levels l and l-1 prepared
-            const uint32_t lb = lvl[l], le = lvl[l + 1];
+            uint32_t lb = lvl[l], le = lvl[l + 1];
+            if constexpr (kVirtual) { le = 2u * lb + __ldcg(&bcnt[l]); lb = 2u * lb; }      // items of the level's work list
             const uint32_t pair_off = ((l + 1u) & 1u) * 2u * kSlotB;       // block of the slots of levels l+1 and l-1
             const uint32_t sub_s = ((l + 1u) >> 1) & 1u;                   // which of the two is level l+1's
             const uint32_t tag_s = l + 2u, tag_p = l;
             for (uint32_t tile = lb + warp_t * 32; tile < le; tile += warps_t * 32) {
                 const uint32_t idx = tile + lane;
                 __syncwarp();                                       // the previous tile's staged state is no longer read
-                uint32_t total;
+                uint32_t total, my_qi = 0;                          // my_qi: queue index of this lane's item (bit 31: second half of its entry)
                 {
                     uint32_t rs = 0, deg = 0, c = 0;
+                    bool counted = idx < le;
                     if (idx < le) {
-                        const uint32_t w = queue_v[idx];
+                        uint32_t qi = idx, half = 0;
+                        if constexpr (kVirtual) { const uint32_t it = __ldcg(&bq[idx]); qi = it & 0x7FFFFFFFu; half = it >> 31; }
+                        my_qi = qi | (half << 31);
+                        const uint32_t w = queue_v[qi];
                         uint32_t m[kWords];
-                        WT::unpack(queue_m[idx], m);
-                        *reinterpret_cast<Vec *>(&s_tile_m[warp][lane][0]) = WT::pack(m);
-                        s_tile_p[warp][lane] = queue_p[idx];
-                        rs = __ldg(p.row_ptr + w);
-                        deg = __ldg(p.row_ptr + w + 1) - rs;
+                        WT::unpack(queue_m[qi], m);
+                        uint32_t pos = queue_p[qi];
 #pragma unroll
                         for (int wd = 0; wd < kWords; ++wd) c += __popc(m[wd]);
+                        rs = __ldg(p.row_ptr + w);
+                        deg = __ldg(p.row_ptr + w + 1) - rs;
+                        if constexpr (kVirtual) {
+                            if (c > 128u) {                         // this item's half of the entry: the sources of rank < 128, or the rest
+                                uint32_t cum = 0;
+#pragma unroll
+                                for (int wd = 0; wd < kWords; ++wd) {
+                                    const uint32_t pc = __popc(m[wd]);
+                                    uint32_t rest = m[wd];          // what belongs to the second half
+                                    if (cum + pc <= 128u) rest = 0u;
+                                    else if (cum < 128u) for (uint32_t k = 128u - cum; k; --k) rest &= rest - 1u;   // drop the k lowest set bits
+                                    m[wd] = half ? rest : m[wd] ^ rest;
+                                    cum += pc;
+                                }
+                                if (half) { pos += 128u; counted = false; }
+                            }
+                        }
+                        *reinterpret_cast<Vec *>(&my_tile_m[lane][0]) = WT::pack(m);
+                        s_tile_p[warp][lane] = pos;
                     }
-                    count_tile(c, deg, idx < le);
+                    count_tile(counted ? c : 0u, deg, counted);
                     const uint32_t incl = warp_inclusive_scan(deg, lane);
                     total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                     s_tile_rs[warp][lane] = rs;
@@ -486,15 +554,15 @@ wide_engine(const WideParams p) {
                 // per-entry state of this lane: up to kWords sources (ranks lane, lane + 32, ...)
                 int cur = -1;
                 uint32_t cur_end = 0, c_cur = 0, pos_cur = 0;
-                uint32_t cell[kWords], sel[kWords], npred[kWords];     // byte offset of the source's cell in a cooked row, its bit, predecessors so far
-                double acc[kWords];
+                uint32_t cell[kLaneSlots], sel[kLaneSlots], npred[kLaneSlots];     // byte offset of the source's cell in a cooked row, its bit, predecessors so far
+                double acc[kLaneSlots];
 #pragma unroll
-                for (int h = 0; h < kWords; ++h) { cell[h] = 0; sel[h] = 0; npred[h] = 0; acc[h] = 0.0; }
+                for (int h = 0; h < kLaneSlots; ++h) { cell[h] = 0; sel[h] = 0; npred[h] = 0; acc[h] = 0.0; }
 
                 auto begin_entry = [&]() {
                     uint32_t mc[kWords], pre[kWords + 1];
                     pre[0] = 0;
-                    WT::unpack(*reinterpret_cast<const Vec *>(&s_tile_m[warp][cur][0]), mc);      // broadcast reads
+                    WT::unpack(*reinterpret_cast<const Vec *>(&my_tile_m[cur][0]), mc);      // broadcast reads
 #pragma unroll
                     for (int wd = 0; wd < kWords; ++wd) pre[wd + 1] = pre[wd] + __popc(mc[wd]);
                     c_cur = pre[kWords];
@@ -511,7 +579,7 @@ wide_engine(const WideParams p) {
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int h = 0; h < kWords; ++h) {
+                    for (int h = 0; h < kLaneSlots; ++h) {
                         const bool on = (uint32_t)lane + 32u * h < c_cur;
                         const uint32_t ks = on ? (uint32_t)s_klist[warp][lane + 32 * h] : 0u;
                         cell[h] = (ks >> 5) * 16u;
@@ -522,7 +590,7 @@ wide_engine(const WideParams p) {
                 auto finish_entry = [&]() {
                     double contrib = 0.0;
 #pragma unroll
-                    for (int h = 0; h < kWords; ++h) {
+                    for (int h = 0; h < kLaneSlots; ++h) {
                         if ((uint32_t)lane + 32u * h < c_cur) {
                             const double bk = 1.0 + acc[h];
                             __stcg(&qc[(size_t)pos_cur + lane + 32 * h], bk / (double)npred[h]);    // dense, coalesced
@@ -584,7 +652,13 @@ wide_engine(const WideParams p) {
                 auto cook = [&](int buf, bool row_valid) {
                     uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * 32 + lane) * kRowB);
                     uint32_t ms[kWords], mp[kWords], pos_s, ts, tp;
-                    if constexpr (kW == 128) {
+                    if constexpr (kW == 256) {
+                        const uint4 a0 = rp[0], a1 = rp[1], a2 = rp[2], b0 = rp[4], b1 = rp[5], b2 = rp[6];
+                        const uint4 s0 = sub_s ? b0 : a0, s1 = sub_s ? b1 : a1, s2 = sub_s ? b2 : a2;
+                        const uint4 p0 = sub_s ? a0 : b0, p1 = sub_s ? a1 : b1, p2 = sub_s ? a2 : b2;
+                        ms[0] = s0.x; ms[1] = s0.y; ms[2] = s0.z; ms[3] = s0.w; ms[4] = s1.x; ms[5] = s1.y; ms[6] = s1.z; ms[7] = s1.w; pos_s = s2.x; ts = s2.y;
+                        mp[0] = p0.x; mp[1] = p0.y; mp[2] = p0.z; mp[3] = p0.w; mp[4] = p1.x; mp[5] = p1.y; mp[6] = p1.z; mp[7] = p1.w; tp = p2.y;
+                    } else if constexpr (kW == 128) {
                         const uint4 a0 = rp[0], a1 = rp[1], b0 = rp[2], b1 = rp[3];
                         const uint4 s0 = sub_s ? b0 : a0, s1 = sub_s ? b1 : a1, p0 = sub_s ? a0 : b0, p1 = sub_s ? a1 : b1;
                         ms[0] = s0.x; ms[1] = s0.y; ms[2] = s0.z; ms[3] = s0.w; pos_s = s1.x; ts = s1.y;
@@ -605,17 +679,22 @@ wide_engine(const WideParams p) {
                     }
                 };
 
+                // Two row buffers: chunk sc+1's blocks are in flight while chunk sc is consumed.  One buffer (256 sources per
+                // batch: a row is 128 B): the chunk's blocks are requested and waited for in turn; the neighbour ids are
+                // loaded two chunks ahead either way.
                 const uint32_t n_chunks = (total + 31) / 32;
-                uint32_t x_next = edge_of(0);
-                stage_rows(0, x_next);
-                x_next = n_chunks > 1 ? edge_of(32) : kWideInvalid;
+                uint32_t x_cur = edge_of(0);                               // neighbour ids of chunk sc
+                uint32_t x_next = n_chunks > 1 ? edge_of(32) : kWideInvalid;   // ... and of chunk sc+1
+                if constexpr (kBufs == 2) stage_rows(0, x_cur);
                 for (uint32_t sc = 0; sc < n_chunks; ++sc) {
-                    const int buf = sc & 1;
+                    const int buf = kBufs == 2 ? (int)(sc & 1) : 0;
                     const uint32_t t0 = sc * 32;
                     const uint32_t cnt = min(32u, total - t0);
+                    if constexpr (kBufs == 1) stage_rows(0, x_cur);
                     asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's blocks have landed (this lane's copies)
                     __syncwarp();                                          // ... and every other lane's
-                    stage_rows(buf ^ 1, x_next);                           // chunk sc+1 (nothing past the end); buffer drained at sc-1
+                    if constexpr (kBufs == 2) stage_rows(buf ^ 1, x_next); // chunk sc+1 (nothing past the end); buffer drained at sc-1
+                    x_cur = x_next;
                     x_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : kWideInvalid;
                     cook(buf, (uint32_t)lane < cnt);
                     __syncwarp();
@@ -628,11 +707,11 @@ wide_engine(const WideParams p) {
                             begin_entry();
                         }
                         const uint32_t left = min(cur_end - tt, cnt - r);      // rows of this entry inside this chunk
-                        if (kWords == 4 && c_cur > 96) {
+                        if (kLaneSlots == 4 && c_cur > 96) {
                             const uint32_t nrows = min(left, 2u);
-                            consume(std::integral_constant<int, 2>{}, std::integral_constant<int, kWords>{}, rows, r, nrows);
+                            consume(std::integral_constant<int, 2>{}, std::integral_constant<int, kLaneSlots>{}, rows, r, nrows);
                             r += nrows;
-                        } else if (kWords == 4 && c_cur > 64) {
+                        } else if (kLaneSlots == 4 && c_cur > 64) {
                             const uint32_t nrows = min(left, 2u);
                             consume(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{}, rows, r, nrows);
                             r += nrows;
@@ -654,7 +733,11 @@ wide_engine(const WideParams p) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 if (cur >= 0) finish_entry();
                 __syncwarp();
-                if (idx < le) bslot[queue_v[idx]] += s_tile_t[warp][lane];     // one writer per vertex per level
+                if (idx < le) {                                     // one writer per vertex, level and half
+                    double *b = bslot;
+                    if constexpr (kVirtual) { if (my_qi >> 31) b = bslot + p.bslot_hi_off; }
+                    b[queue_v[my_qi & 0x7FFFFFFFu]] += s_tile_t[warp][lane];
+                }
             }
         }
         if (threadIdx.x == 0) { if (team_rank == 0) p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }

@@ -17,11 +17,12 @@ ENGINES = {"auto": 0, "batched": 1, "mid": 2, "wide": 3}
 
 
 @pytest.fixture(params=["batched", "batched64", "batched_pull", "batched64_pull", "batched64_push", "mid",
-                        "wide128", "wide64", "wide128_pull", "wide128_push", "wide64_pull", "wide128_t512", "wide64_team3"])
+                        "wide128", "wide64", "wide128_pull", "wide128_push", "wide64_pull", "wide128_t512", "wide64_team3",
+                        "wide256", "wide256_pull", "wide256_push", "wide256_team3"])
 def engine_ctx(ctx, request, monkeypatch):
     """Runs a test once per traversal engine, batch width and forward direction (the C ABI picks by graph size,
     source count and a per-level cost model by default; NEC_BATCH_WIDTH pins the source-minor batched engine's 32 / 64
-    sources per batch, NEC_WIDE_WIDTH the compact engine's 64 / 128, NEC_PULL the forward pass to push only (0) or pull
+    sources per batch, NEC_WIDE_WIDTH the compact engine's 64 / 128 / 256, NEC_PULL the forward pass to push only (0) or pull
     only (2); t512 = 512-thread CTAs, team3 = three CTAs per slot)."""
     name, _, variant = request.param.partition("_")
     base = name.rstrip("0123456789")
@@ -30,7 +31,7 @@ def engine_ctx(ctx, request, monkeypatch):
         monkeypatch.setenv("NEC_BATCH_WIDTH", "64" if name.endswith("64") else "32")
     if base == "wide":
         monkeypatch.setenv("NEC_WIDE_WIDTH", name[4:])
-        monkeypatch.setenv("NEC_WIDE_QUEUE", "128")        # room for every level a vertex can sit on: nothing is handed to the other engine
+        monkeypatch.setenv("NEC_WIDE_QUEUE", "256")        # room for every level a vertex can sit on: nothing is handed to the other engine
     if variant in ("pull", "push"):
         monkeypatch.setenv("NEC_PULL", "2" if variant == "pull" else "0")
     if variant == "t512":
@@ -489,24 +490,50 @@ def test_full_size_properties_config2_small_world(ctx, oracle):
 
 def test_full_size_properties_config4_gnm(ctx, oracle):
     """BASELINE configs[3] (the north-star target) on the path the bench takes: one resident wave through the DEFAULT
-    plan = the compact engine, 128 sources per batch, one thread-block cluster of two 1024-thread CTAs per batch."""
+    plan = the compact engine at its widest batch (256 sources, entries with more than 128 live sources consumed in
+    two passes) on clusters of 1024-thread CTAs that fill the GPU; then the 128-wide shape on the same sources."""
     g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)          # (scalable generator), sampled sources
     rp, col = g.export_csr()
-    src = (np.arange(9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
-    st = _full_size_properties(ctx, oracle, rp, col, src, 4, 128)
-    assert st["team_size"] == 2 and st["cta_threads"] == 1024 and st["n_slots"] == 74 and st["pull_levels"] > 0
-    # the plan must not depend on how many waves a call carries: the full job and a two-wave call get the same shape
+
+    def one_wave(dg):
+        wave = dg.wave_size()
+        assert wave % 128 == 0 and wave >= 9000
+        return (np.arange(wave, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
+
+    st = _full_size_properties(ctx, oracle, rp, col, one_wave, 4, None)
+    assert st["batch_width"] in (128, 256) and st["cta_threads"] == 1024 and st["pull_levels"] > 0
+    assert st["n_slots"] * st["batch_width"] == st["n_sources"] and 130 <= st["n_slots"] * st["team_size"] <= 148
+    assert st["requeued_batches"] == 0 and st["n_sources"] * ((1 << 20) - 2000) < st["reached_pairs"] <= st["n_sources"] * (1 << 20)   # a few hundred isolated vertices
+    # the plan must not depend on how many waves a call carries: a two-wave call gets the same shape
     dg = ctx.upload(rp, col)
-    assert dg.wave_size() == 74 * 128
-    two = (np.arange(2 * 9472, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
+    wave = dg.wave_size()
+    two = (np.arange(2 * wave, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
     both = dg.vertex_load_sources(two, True)
     st2 = ctx.stats()
-    assert (st2["batch_width"], st2["team_size"], st2["n_slots"], st2["n_batches"]) == (128, 2, 74, 148)
-    first = dg.vertex_load_sources(two[:9472], True)
-    second = dg.vertex_load_sources(two[9472:], True)
+    assert (st2["batch_width"], st2["team_size"], st2["n_slots"], st2["n_batches"]) == (st["batch_width"], st["team_size"], st["n_slots"], 2 * st["n_slots"])
+    first = dg.vertex_load_sources(two[:wave], True)
+    second = dg.vertex_load_sources(two[wave:], True)
     assert close(both, first + second, 1e-12)
     dg.free()
-    assert st["requeued_batches"] == 0 and 9472 * ((1 << 20) - 2000) < st["reached_pairs"] <= 9472 * (1 << 20)   # a few hundred isolated vertices
+
+
+@pytest.mark.parametrize("width,team", [("128", 2), ("256", 3)])
+def test_config4_batch_widths_agree(ctx, oracle, monkeypatch, width, team):
+    """Both production shapes of the compact engine on config 4 against the oracle on the same sampled sources."""
+    g = ne.gnm_scalable(1 << 20, 1 << 22, 20261020)
+    rp, col = g.export_csr()
+    monkeypatch.setenv("NEC_WIDE_WIDTH", width)
+    dg = ctx.upload(rp, col)
+    src = (np.arange(1536, dtype=np.uint64) * 110_503 % (1 << 20)).astype(np.uint32)
+    got = dg.vertex_load_sources(src, True)
+    st = ctx.stats()
+    assert st["engine"] == 4 and st["batch_width"] == int(width)
+    sub = src[::192]
+    assert close(dg.vertex_load_sources(sub, True), oracle.vertex_load(rp, col, True, sources=sub, threads=0), REL)
+    ecc, sumd, reached = dg.distance_measures(src)
+    dtot = int(sumd.astype(object).sum())
+    assert abs(float(got.sum()) - dtot) <= 1e-9 * dtot and st["reached_pairs"] == int(reached.astype(np.int64).sum())
+    dg.free()
 
 
 def test_full_size_properties_config5_barabasi_albert(ctx, oracle):

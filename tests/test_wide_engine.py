@@ -15,13 +15,13 @@ REL = 1e-9
 @pytest.fixture
 def wide_ctx(ctx, monkeypatch):
     ctx.set_engine(3)
-    monkeypatch.setenv("NEC_WIDE_QUEUE", "128")
+    monkeypatch.setenv("NEC_WIDE_QUEUE", "256")
     yield ctx
     ctx.set_workspace_limit(0)
     ctx.set_engine(0)
 
 
-@pytest.mark.parametrize("width", ["64", "128"])
+@pytest.mark.parametrize("width", ["64", "128", "256"])
 def test_team_sizes_cta_shapes_and_directions_are_bitwise_identical(wide_ctx, oracle, monkeypatch, width):
     ctx = wide_ctx
     monkeypatch.setenv("NEC_WIDE_WIDTH", width)
@@ -51,7 +51,7 @@ def test_team_sizes_cta_shapes_and_directions_are_bitwise_identical(wide_ctx, or
         dg.free()
 
 
-@pytest.mark.parametrize("width", ["64", "128"])
+@pytest.mark.parametrize("width", ["64", "128", "256"])
 def test_slots_are_reused_batch_after_batch(wide_ctx, oracle, monkeypatch, width):
     """Few slots, many batches per slot: records, level records, queues and runs of one batch must not leak into
     the next (only the tags are reset between batches)."""
@@ -63,7 +63,7 @@ def test_slots_are_reused_batch_after_batch(wide_ctx, oracle, monkeypatch, width
         dg = ctx.upload(rp, col)
         free = dg.vertex_load(True)
         slots_free = ctx.stats()["n_slots"]
-        ctx.set_workspace_limit(3 * (n * int(width) * 16 + (1 << 20)))          # room for about two slots
+        ctx.set_workspace_limit(3 * (n * int(width) * 24 + (1 << 21)))          # room for a few slots
         few = dg.vertex_load(True)
         st = ctx.stats()
         assert st["engine"] == 4 and st["n_slots"] < slots_free and st["n_batches"] >= 3 * st["n_slots"]
@@ -87,7 +87,7 @@ def test_batches_that_do_not_fit_are_handed_to_the_source_minor_engine(wide_ctx,
     assert st["engine"] == (4 | 1 << 4) and st["requeued_batches"] > 0
     assert close(got, oracle.vertex_load(rp, col, True), REL)
     assert st["reached_pairs"] >= 1100 * 1100                # (the handed-over batches are counted by both engines' forward passes or only once)
-    monkeypatch.setenv("NEC_WIDE_QUEUE", "128")
+    monkeypatch.setenv("NEC_WIDE_QUEUE", "256")
     full = dg.vertex_load(True)
     assert ctx.stats()["engine"] == 4 and ctx.stats()["requeued_batches"] == 0 and ctx.stats()["max_depth"] == 275
     assert close(full, got, REL)
@@ -100,7 +100,7 @@ def test_ragged_batches_repeated_sources_and_components(wide_ctx, oracle):
     rp, col = g.export_csr()
     dg = ctx.upload(rp, col)
     rng = np.random.default_rng(5)
-    for count in (1, 37, 128, 129, 128 * 5 + 37):
+    for count in (1, 37, 128, 129, 257, 128 * 5 + 37):
         src = rng.integers(0, 3000, count).astype(np.uint32)   # with repeats
         for incl in (True, False):
             got = dg.vertex_load_sources(src, incl)
@@ -127,8 +127,8 @@ def test_differential_fuzz_against_the_oracle(wide_ctx, oracle, monkeypatch):
         rp = np.zeros(n + 1, np.uint64)
         rp[1:] = np.cumsum([len(a) for a in adj])
         col = np.array([x for a in adj for x in a], dtype=np.uint32)
-        monkeypatch.setenv("NEC_WIDE_WIDTH", "128" if trial % 2 else "64")
-        monkeypatch.setenv("NEC_PULL", str(trial % 3))
+        monkeypatch.setenv("NEC_WIDE_WIDTH", ("64", "128", "256")[trial % 3])
+        monkeypatch.setenv("NEC_PULL", str((trial // 3) % 3))
         dg = wide_ctx.upload(rp, col)
         incl = bool(trial & 4)
         assert close(dg.vertex_load(incl), oracle.vertex_load(rp, col, incl), REL), trial
