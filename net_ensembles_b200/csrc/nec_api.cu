@@ -645,6 +645,33 @@ int wide_capacity(nec_ctx *ctx, uint32_t kw, uint32_t threads, uint32_t team) {
                            : (threads == 1024 ? wide_capacity_t<64, 1024>(team) : wide_capacity_t<64, NEC_WIDE_SMALL_CTA>(team));
     return cached;
 }
+// Software teams: any `team` consecutive CTAs of a cooperative launch; what limits them is only how many CTAs are co-resident.
+template <int kW, int kThreads>
+int wide_soft_ctas_t(int sms) {
+    auto kern = nec::wide_engine<kW, kThreads, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::wide_smem_bytes<kW, kThreads>()) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, nec::wide_smem_bytes<kW, kThreads>()) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return occ * sms;
+}
+int wide_soft_ctas(nec_ctx *ctx, uint32_t kw, uint32_t threads) {
+    int &cached = ctx->wide_cap[kw == 64 ? 0 : kw == 128 ? 1 : 2][threads == 1024][0];      // team index 0: resident CTAs of the software-team kernel
+    const int sms = ctx->prop.multiProcessorCount;
+    if (cached < 0)
+        cached = kw == 256 ? (threads == 1024 ? wide_soft_ctas_t<256, 1024>(sms) : wide_soft_ctas_t<256, NEC_WIDE_SMALL_CTA>(sms))
+               : kw == 128 ? (threads == 1024 ? wide_soft_ctas_t<128, 1024>(sms) : wide_soft_ctas_t<128, NEC_WIDE_SMALL_CTA>(sms))
+                           : (threads == 1024 ? wide_soft_ctas_t<64, 1024>(sms) : wide_soft_ctas_t<64, NEC_WIDE_SMALL_CTA>(sms));
+    return cached;
+}
+template <int kW, int kThreads>
+int launch_wide_soft_t(nec_ctx *ctx, const nec::WideParams &p, uint32_t slots, uint32_t team) {
+    auto kern = nec::wide_engine<kW, kThreads, true>;
+    NEC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::wide_smem_bytes<kW, kThreads>()));   // per device
+    void *args[] = {(void *)&p};
+    NEC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(slots * team), dim3(kThreads), args, nec::wide_smem_bytes<kW, kThreads>(), ctx->stream));
+    return NEC_OK;
+}
+
 template <int kW, int kThreads>
 int launch_wide_t(nec_ctx *ctx, const nec::WideParams &p, uint32_t slots, uint32_t team) {
     cudaLaunchAttribute attr[1];
@@ -655,7 +682,7 @@ int launch_wide_t(nec_ctx *ctx, const nec::WideParams &p, uint32_t slots, uint32
 }
 
 // How the wide engine runs a call: batch width, CTA shape, resident slots and CTAs per slot.
-struct WidePlan { uint32_t kw, threads, slots, team, max_levels; size_t qcap, per_slot; };
+struct WidePlan { uint32_t kw, threads, slots, team, max_levels; size_t qcap, per_slot; bool soft; };
 int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
     const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
     size_t free_b = 0, total_b = 0;
@@ -681,14 +708,19 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
         if (fit == 0) continue;
         // every team size the slots allow: `team` CTAs per slot fill the GPU from ctas_total / team slots (clusters are
         // placed per GPC, so the driver is asked how many of each size can be resident)
-        uint32_t t_lo = 1, t_hi = 8;
+        // teams: thread-block clusters (placed per GPC: the driver is asked how many of each size can be resident), or
+        // software teams over a cooperative launch (any size, every SM usable) - the default
+        bool soft = true;
+        if (const char *env = getenv("NEC_WIDE_SOFT")) soft = atoi(env) != 0;
+        auto capacity = [&](uint32_t team) -> int { return soft ? wide_soft_ctas(ctx, kw, threads) / (int)team : wide_capacity(ctx, kw, threads, team); };
+        uint32_t t_lo = 1, t_hi = soft ? 16 : 8;                         // (a portable cluster has at most 8 CTAs)
         if (const char *env = getenv("NEC_WIDE_TEAM")) {                 // tests / A-B runs: this team size, or the largest below it that fits
-            t_hi = (uint32_t)std::min(8, std::max(1, atoi(env)));
-            while (t_hi > 1 && wide_capacity(ctx, kw, threads, t_hi) <= 0) --t_hi;
+            t_hi = (uint32_t)std::min((int)t_hi, std::max(1, atoi(env)));
+            while (t_hi > 1 && capacity(t_hi) <= 0) --t_hi;
             t_lo = t_hi;
         }
         for (uint32_t team = t_lo; team <= t_hi; ++team) {
-            const int cap = wide_capacity(ctx, kw, threads, team);
+            const int cap = capacity(team);
             if (cap <= 0) continue;
             const uint32_t slots = std::min<uint32_t>(std::min<uint32_t>(fit, (uint32_t)cap), std::max<uint32_t>(1u, ctas_total / team));
             // relative cost: waves x time of one batch.  Measured (scripts/exp_wide_teams.py): a batch's time is
@@ -698,7 +730,7 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
             // the row traffic are per batch).  Equal costs keep the smaller team: more slots, finer last wave.
             const double waves = (double)((n_batches + slots - 1) / slots);
             const double cost = waves * (kw == 256 ? NEC_WIDE_COST256 : kw == 128 ? 1.5 : 1.0) / ((double)team * threads / 512.0);
-            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps}; }
+            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = WidePlan{kw, threads, slots, team, max_levels, qcap, ps, soft}; }
         }
     }
     if (best.slots == 0) return fail(ctx, NEC_ENOMEM, "workspace budget %zu B cannot hold one wide-engine slot for n=%u", budget, n);
@@ -775,10 +807,22 @@ int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources
     p.lvl_base = a.lvl; p.lvl_stride = a.lvl_stride; p.max_levels = a.max_levels;
     p.bq_base = a.bq; p.bq_stride = a.bq_stride; p.bcnt_base = a.bcnt; p.bslot_hi_off = a.bslot_stride / 2;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
+    p.team_size = pl.team; p.team_base = nullptr;
+    if (pl.soft) {                                   // the teams' shared scalars and barrier counters (8 u32 per slot)
+        if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, (size_t)slots * 8)) != NEC_OK) return rc;
+        NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_worklist, 0, (size_t)slots * 8 * sizeof(uint32_t), ctx->stream));
+        p.team_base = ctx->d_worklist;
+    }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (kw == 256) rc = pl.threads == 1024 ? launch_wide_t<256, 1024>(ctx, p, slots, pl.team) : launch_wide_t<256, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
-    else if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
-    else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    if (pl.soft) {
+        if (kw == 256) rc = pl.threads == 1024 ? launch_wide_soft_t<256, 1024>(ctx, p, slots, pl.team) : launch_wide_soft_t<256, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+        else if (kw == 128) rc = pl.threads == 1024 ? launch_wide_soft_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_soft_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+        else rc = pl.threads == 1024 ? launch_wide_soft_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_soft_t<64, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    } else {
+        if (kw == 256) rc = pl.threads == 1024 ? launch_wide_t<256, 1024>(ctx, p, slots, pl.team) : launch_wide_t<256, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+        else if (kw == 128) rc = pl.threads == 1024 ? launch_wide_t<128, 1024>(ctx, p, slots, pl.team) : launch_wide_t<128, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+        else rc = pl.threads == 1024 ? launch_wide_t<64, 1024>(ctx, p, slots, pl.team) : launch_wide_t<64, NEC_WIDE_SMALL_CTA>(ctx, p, slots, pl.team);
+    }
     if (rc != NEC_OK) return rc;
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     if (kw == 256)    // two partial loads per slot, summed in (slot, half) order

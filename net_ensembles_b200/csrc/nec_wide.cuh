@@ -67,6 +67,10 @@ struct WideParams {
     size_t bslot_hi_off;                       // doubles
     uint8_t *batch_status;                     // per batch id (BatchStatus)
     unsigned long long *counters;              // as EngineParams::counters
+    // software teams (kSoft): CTAs blockIdx.x in [slot * team_size, (slot + 1) * team_size) run slot `slot`; their shared
+    // scalars and barrier counter live in global memory (8 u32 per slot: tail, fail, open, pos, barrier, -, -, -)
+    uint32_t team_size;
+    uint32_t *team_base;
 };
 
 struct alignas(16) WideVec256 { uint4 a, b; };
@@ -107,7 +111,11 @@ constexpr size_t wide_smem_bytes() {
 
 constexpr uint32_t kWideInvalid = 0xFFFFFFFFu;
 
-template <int kW, int kThreads>
+// kSoft = false: a slot's CTAs are one thread-block cluster (shared scalars in rank 0's shared memory, cluster barriers).
+// kSoft = true : a slot's CTAs are any `team_size` consecutive CTAs of a cooperative launch (all CTAs co-resident); the
+//                shared scalars and a barrier counter live in global memory.  Clusters are placed per GPC, so only 45
+//                clusters of three 1024-thread CTAs (or 33 of four) fit on the 148 SMs; software teams use all of them.
+template <int kW, int kThreads, bool kSoft = false>
 __global__ void __launch_bounds__(kThreads, kThreads == 512 ? 2 : 1)
 wide_engine(const WideParams p) {
     namespace cg = cooperative_groups;
@@ -126,8 +134,9 @@ wide_engine(const WideParams p) {
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    cg::cluster_group cluster = cg::this_cluster();
-    const uint32_t team_size = cluster.num_blocks(), team_rank = cluster.block_rank();
+    uint32_t team_size, team_rank;
+    if constexpr (kSoft) { team_size = p.team_size; team_rank = blockIdx.x % team_size; }
+    else { team_size = cg::this_cluster().num_blocks(); team_rank = cg::this_cluster().block_rank(); }
     const uint32_t slot = blockIdx.x / team_size, n_slots = gridDim.x / team_size;
     const uint32_t tid_t = team_rank * kThreads + threadIdx.x, threads_t = team_size * kThreads;
     const uint32_t warp_t = team_rank * kWarps + warp, warps_t = team_size * kWarps;
@@ -155,10 +164,34 @@ wide_engine(const WideParams p) {
 
     // team-shared scalars: rank 0's copies, reached through distributed shared memory
     __shared__ uint32_t s_tail, s_fail, s_open, s_pos;
-    uint32_t *tail_p = cluster.map_shared_rank(&s_tail, 0);
-    uint32_t *fail_p = cluster.map_shared_rank(&s_fail, 0);
-    uint32_t *open_p = cluster.map_shared_rank(&s_open, 0);
-    uint32_t *pos_p = cluster.map_shared_rank(&s_pos, 0);
+    uint32_t *tail_p, *fail_p, *open_p, *pos_p, *bar_p = nullptr;
+    if constexpr (kSoft) {
+        uint32_t *t = p.team_base + (size_t)slot * 8;
+        tail_p = t; fail_p = t + 1; open_p = t + 2; pos_p = t + 3; bar_p = t + 4;
+    } else {
+        tail_p = cg::this_cluster().map_shared_rank(&s_tail, 0);
+        fail_p = cg::this_cluster().map_shared_rank(&s_fail, 0);
+        open_p = cg::this_cluster().map_shared_rank(&s_open, 0);
+        pos_p = cg::this_cluster().map_shared_rank(&s_pos, 0);
+    }
+    // team barrier.  Software form (as cooperative groups' grid barrier, per team): the CTA's writes are ordered before
+    // thread 0's release by the block barrier, thread 0 takes a ticket on the team's counter and spins with acquire loads
+    // until the whole team has arrived, the second block barrier orders everything after it.
+    auto team_sync = [&]() {
+        if constexpr (kSoft) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                const uint32_t ticket = atomicAdd(bar_p, 1u);
+                const uint32_t target = (ticket / team_size + 1u) * team_size;
+                uint32_t seen;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar_p) : "memory"); } while ((int32_t)(seen - target) < 0);
+                __threadfence();
+            }
+            __syncthreads();
+        } else
+            cg::this_cluster().sync();
+    };
     __shared__ unsigned char s_klist[kWarps][kW];        // backward: the live sources of the entry a warp is consuming
     __shared__ uint32_t s_tile_p[kWarps][32];             // backward: run positions of the warp's tile of entries (masks: dynamic, below)
     __shared__ uint32_t s_tile_rs[kWarps][32], s_tile_off[kWarps][32], s_tile_end[kWarps][32];   // adjacency row start, first and past-the-end flattened row of each entry
@@ -187,8 +220,9 @@ wide_engine(const WideParams p) {
             const size_t m16 = (size_t)n * 4 * kSlotB / 16;
             for (size_t i = tid_t; i < m16; i += threads_t) __stcg(&l16[i], make_uint4(0u, 0u, 0u, 0u));
         }
-        if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; s_open = 0; s_pos = 0; }
-        cluster.sync();
+        if constexpr (kSoft) { if (tid_t == 0) { *(volatile uint32_t *)tail_p = 0; *(volatile uint32_t *)fail_p = 0; *(volatile uint32_t *)open_p = 0; *(volatile uint32_t *)pos_p = 0; } }
+        else if (threadIdx.x == 0) { s_tail = 0; s_fail = 0; s_open = 0; s_pos = 0; }
+        team_sync();
 
         // ---- seed level 0 -----------------------------------------------------------------------------------
         uint32_t valid_src[kWords];
@@ -211,7 +245,7 @@ wide_engine(const WideParams p) {
                 }
             }
         }
-        cluster.sync();
+        team_sync();
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_reset += t - t_phase; t_phase = t; }
 
         // ---- forward: level-synchronous, bit-parallel, direction chosen per level ---------------------------
@@ -220,11 +254,11 @@ wide_engine(const WideParams p) {
         uint32_t n_open = n, defer_beg = 0, defer_end = 0;
         bool prev_pull = false;
         for (;;) {
-            cluster.sync();                              // previous level fully expanded
+            team_sync();                              // previous level fully expanded
             const uint32_t tail_raw = *(volatile uint32_t *)tail_p;
             const uint32_t open_raw = *(volatile uint32_t *)open_p;
             const uint32_t tail_now = tail_raw < qcap ? tail_raw : qcap;
-            cluster.sync();                              // every warp sampled the tail before it moves again
+            team_sync();                              // every warp sampled the tail before it moves again
             qbeg = qend;
             qend = tail_now;
             if (prev_pull) n_open = open_raw;
@@ -263,8 +297,9 @@ wide_engine(const WideParams p) {
             }
             defer_beg = pull ? qbeg : 0u;
             defer_end = pull ? qend : 0u;
-            if (pull && threadIdx.x == 0) s_open = 0;
-            cluster.sync();
+            if constexpr (kSoft) { if (pull && tid_t == 0) *(volatile uint32_t *)open_p = 0; }
+            else if (pull && threadIdx.x == 0) s_open = 0;
+            team_sync();
 
             if (!pull) {
                 // ---- push: one lane per adjacency entry of the frontier ----
@@ -414,11 +449,11 @@ wide_engine(const WideParams p) {
         }
         // here: levels 0..level-1 are non-empty (if !too_deep), lvl[l] = start of level l, lvl[level] = end of the last
         if constexpr (kVirtual) for (uint32_t L = tid_t; L <= level; L += threads_t) bcnt[L] = 0;
-        cluster.sync();
+        team_sync();
         const bool failed = *(volatile uint32_t *)fail_p != 0;
         if (too_deep || failed) {
             if (tid_t == 0) p.batch_status[batch] = failed ? kQueueOverflow : kTooDeep;
-            cluster.sync();                              // (the reset of the next batch clears every record)
+            team_sync();                              // (the reset of the next batch clears every record)
             continue;
         }
         const uint32_t depth = level - 1;
@@ -499,7 +534,7 @@ wide_engine(const WideParams p) {
         prepare(depth);
         for (uint32_t l = depth; l >= 1; --l) {
             prepare(l - 1);
-            cluster.sync();                              // level l+1 fully processed (its q values stored), levels l and l-1 prepared
+            team_sync();                              // level l+1 fully processed (its q values stored), levels l and l-1 prepared
             uint32_t lb = lvl[l], le = lvl[l + 1];
             if constexpr (kVirtual) { le = 2u * lb + __ldcg(&bcnt[l]); lb = 2u * lb; }      // items of the level's work list
             const uint32_t pair_off = ((l + 1u) & 1u) * 2u * kSlotB;       // block of the slots of levels l+1 and l-1
@@ -741,11 +776,11 @@ wide_engine(const WideParams p) {
             }
         }
         if (threadIdx.x == 0) { if (team_rank == 0) p.batch_status[batch] = kDone; cyc_bwd += clock64() - t_phase; }
-        cluster.sync();
+        team_sync();
     }
 
     // ---- flush counters ---------------------------------------------------------------------------------------
-    cluster.sync();                                      // rank 0's shared memory stays alive until every CTA of the team is done
+    team_sync();                                      // rank 0's shared memory stays alive until every CTA of the team is done
     if (threadIdx.x < 3) atomicAdd(&p.counters[threadIdx.x], s_cnt[threadIdx.x]);
     if (threadIdx.x == 0) {
         atomicMax(&p.counters[3], (unsigned long long)my_depth);

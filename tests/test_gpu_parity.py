@@ -18,12 +18,13 @@ ENGINES = {"auto": 0, "batched": 1, "mid": 2, "wide": 3}
 
 @pytest.fixture(params=["batched", "batched64", "batched_pull", "batched64_pull", "batched64_push", "mid",
                         "wide128", "wide64", "wide128_pull", "wide128_push", "wide64_pull", "wide128_t512", "wide64_team3",
-                        "wide256", "wide256_pull", "wide256_push", "wide256_team3"])
+                        "wide256", "wide256_pull", "wide256_push", "wide256_team3", "wide128_cluster", "wide256_cluster"])
 def engine_ctx(ctx, request, monkeypatch):
     """Runs a test once per traversal engine, batch width and forward direction (the C ABI picks by graph size,
     source count and a per-level cost model by default; NEC_BATCH_WIDTH pins the source-minor batched engine's 32 / 64
     sources per batch, NEC_WIDE_WIDTH the compact engine's 64 / 128 / 256, NEC_PULL the forward pass to push only (0) or pull
-    only (2); t512 = 512-thread CTAs, team3 = three CTAs per slot)."""
+    only (2); t512 = 512-thread CTAs, team3 = three CTAs per slot, cluster = thread-block clusters instead of the
+    default software teams)."""
     name, _, variant = request.param.partition("_")
     base = name.rstrip("0123456789")
     ctx.set_engine(ENGINES[base])
@@ -38,6 +39,8 @@ def engine_ctx(ctx, request, monkeypatch):
         monkeypatch.setenv("NEC_WIDE_THREADS", "512")
     if variant == "team3":
         monkeypatch.setenv("NEC_WIDE_TEAM", "3")
+    if variant == "cluster":                               # thread-block clusters instead of software teams
+        monkeypatch.setenv("NEC_WIDE_SOFT", "0")
     ctx.engine_name = base
     yield ctx
     ctx.set_engine(0)

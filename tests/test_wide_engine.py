@@ -32,7 +32,9 @@ def test_team_sizes_cta_shapes_and_directions_are_bitwise_identical(wide_ctx, or
         dg = ctx.upload(rp, col)
         src = np.arange(0, n, max(1, n // 700), dtype=np.uint32)        # a few batches, the last one ragged
         outs = []
-        for team, threads, pull in (("1", "1024", "1"), ("2", "1024", "1"), ("3", "512", "1"), ("8", "512", "0"), ("4", "1024", "2")):
+        for team, threads, pull, soft in (("1", "1024", "1", "1"), ("2", "1024", "1", "1"), ("3", "512", "1", "0"), ("8", "512", "0", "1"),
+                                          ("4", "1024", "2", "0"), ("5", "1024", "1", "1"), ("2", "1024", "1", "0")):
+            monkeypatch.setenv("NEC_WIDE_SOFT", soft)       # software teams (cooperative launch) or thread-block clusters
             monkeypatch.setenv("NEC_WIDE_TEAM", team)
             monkeypatch.setenv("NEC_WIDE_THREADS", threads)
             monkeypatch.setenv("NEC_PULL", pull)
