@@ -390,7 +390,7 @@ def measure_graph(name, steps, warmup, rank, world, local_rank, with_cpu_baselin
         kernel = {1: "vertex_load_engine<u8> (batched, %d sources per batch, %d-thread CTAs, %d per slot)" % (
                         st0.get("batch_width") or 32, st0.get("cta_threads") or 0, st0.get("team_size") or 1),
                   2: "mid_engine (one source per CTA)",
-                  4: "wide_engine<%d, %d> (compact batched engine, %d sources per batch, clusters of %d x %d-thread CTAs per batch)" % (
+                  4: "wide_engine<%d, %d> (compact batched engine, %d sources per batch, teams of %d x %d-thread CTAs per batch)" % (
                         st0.get("batch_width") or 0, st0.get("cta_threads") or 0, st0.get("batch_width") or 0,
                         st0.get("team_size") or 1, st0.get("cta_threads") or 0)}.get(eng, "?")
         line = {
