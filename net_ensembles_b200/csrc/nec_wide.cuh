@@ -35,6 +35,11 @@
 
 #include "nec_kernels.cuh"
 
+#ifndef NEC_WIDE_ROW_PAD
+#define NEC_WIDE_ROW_PAD 0       // bytes added to the pitch of a staged row in shared memory (A/B: 16 removes the bank conflicts of the cooking
+                                 // step but the extra shared memory shrinks L1 and the forward pass loses more: 3623 vs 3513 ms)
+#endif
+
 namespace nec {
 
 struct WideParams {
@@ -106,7 +111,7 @@ template <> struct WideTraits<256> {
 template <int kW> __host__ __device__ constexpr int wide_row_bufs() { return kW == 256 ? 1 : 2; }
 template <int kW, int kThreads>
 constexpr size_t wide_smem_bytes() {
-    return (size_t)(kThreads / 32) * wide_row_bufs<kW>() * 32 * (kW / 2) + 8 * (kW / 2) + (size_t)(kThreads / 32) * 32 * (kW / 8);
+    return (size_t)(kThreads / 32) * wide_row_bufs<kW>() * 32 * (kW / 2 + NEC_WIDE_ROW_PAD) + 8 * (kW / 2 + NEC_WIDE_ROW_PAD) + (size_t)(kThreads / 32) * 32 * (kW / 8);
 }
 
 constexpr uint32_t kWideInvalid = 0xFFFFFFFFu;
@@ -131,6 +136,8 @@ wide_engine(const WideParams p) {
     constexpr int kSlotB = kW / 4;                      // level-record slot: mask, position, tag (+ padding at B = 128)
     constexpr int kRowB = kW / 2;                       // staged row: the two slots of levels l-1 / l+1 = kWords cooked 16 B cells
     constexpr int kPieces = kRowB / 16;                 // 16 B pieces per row
+    constexpr int kRowS = kRowB + NEC_WIDE_ROW_PAD;     // row pitch in shared memory: lane r cooks row r, and at a pitch of 64 / 128 B all
+                                                        // 32 lanes would hit the same banks (16- / 32-way conflicts on every access)
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -198,8 +205,8 @@ wide_engine(const WideParams p) {
     __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
     __shared__ unsigned long long s_cnt[3];
     extern __shared__ __align__(16) unsigned char wide_smem[];
-    unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * 32 * kRowB;   // [kBufs][32][kRowB]
-    uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * 32 * kRowB + 8 * kRowB) + (size_t)warp * 32;   // [32][kWords]
+    unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * 32 * kRowS;   // [kBufs][32][kRowS]
+    uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * 32 * kRowS + 8 * kRowS) + (size_t)warp * 32;   // [32][kWords]
     uint32_t *__restrict__ bq = kVirtual ? p.bq_base + (size_t)slot * p.bq_stride : nullptr;
     uint32_t *__restrict__ bcnt = kVirtual ? p.bcnt_base + (size_t)slot * p.lvl_stride : nullptr;
 
@@ -377,29 +384,36 @@ wide_engine(const WideParams p) {
                     }
                     const bool hub = deg > kPullHubDeg;
                     if (!hub) {
-                        for (uint32_t e = 0; e < deg; e += kPullU) {
-                            uint32_t un[kPullU];
-                            Vec mm[kPullU];
+                        // the vertex's neighbour ids are read eight at a time - one pass over the L1 lines its row shares with
+                        // the rows of the neighbouring threads - and their frontier masks kPullU at a time
+                        bool more = true;
+                        for (uint32_t e = 0; e < deg && more; e += 8) {
+                            uint32_t un[8];
 #pragma unroll
-                            for (int j = 0; j < kPullU; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : kWideInvalid;
+                            for (int j = 0; j < 8; ++j) un[j] = e + j < deg ? __ldg(p.col_idx + rs + e + j) : kWideInvalid;
 #pragma unroll
-                            for (int j = 0; j < kPullU; ++j) {
-                                uint32_t z[kWords];
+                            for (int j0 = 0; j0 < 8; j0 += kPullU) {
+                                if (!more) break;
+                                Vec mm[kPullU];
 #pragma unroll
-                                for (int wd = 0; wd < kWords; ++wd) z[wd] = 0;
-                                mm[j] = un[j] != kWideInvalid ? WT::ldcg(next_of(un[j], par_c)) : WT::pack(z);
+                                for (int j = 0; j < kPullU; ++j) {
+                                    uint32_t z[kWords];
+#pragma unroll
+                                    for (int wd = 0; wd < kWords; ++wd) z[wd] = 0;
+                                    mm[j] = un[j0 + j] != kWideInvalid ? WT::ldcg(next_of(un[j0 + j], par_c)) : WT::pack(z);
+                                }
+                                uint32_t missing = 0;
+#pragma unroll
+                                for (int j = 0; j < kPullU; ++j) {
+                                    uint32_t w4[kWords];
+                                    WT::unpack(mm[j], w4);
+#pragma unroll
+                                    for (int wd = 0; wd < kWords; ++wd) acc[wd] |= w4[wd];
+                                }
+#pragma unroll
+                                for (int wd = 0; wd < kWords; ++wd) missing |= unseen[wd] & ~acc[wd];
+                                more = missing != 0 && e + j0 + kPullU < deg;      // nothing left to find for this vertex, or no neighbour left
                             }
-                            uint32_t missing = 0;
-#pragma unroll
-                            for (int j = 0; j < kPullU; ++j) {
-                                uint32_t w4[kWords];
-                                WT::unpack(mm[j], w4);
-#pragma unroll
-                                for (int wd = 0; wd < kWords; ++wd) acc[wd] |= w4[wd];
-                            }
-#pragma unroll
-                            for (int wd = 0; wd < kWords; ++wd) missing |= unseen[wd] & ~acc[wd];
-                            if (!missing) break;             // nothing left to find for this vertex
                         }
                     }
                     // hubs: the whole warp gathers one adjacency list
@@ -640,13 +654,13 @@ wide_engine(const WideParams p) {
                 auto consume = [&](auto rows_tag, auto slots_tag, const unsigned char *rows, uint32_t r, uint32_t nrows) {
                     constexpr int kRows = decltype(rows_tag)::value, kSlots = decltype(slots_tag)::value;
                     double qv[kRows][kSlots];
-                    const unsigned char *rp = rows + r * kRowB;
+                    const unsigned char *rp = rows + r * kRowS;
 #pragma unroll
                     for (int jj = 0; jj < kRows; ++jj) {
                         const bool valid = (uint32_t)jj < nrows;    // warp-uniform
 #pragma unroll
                         for (int h = 0; h < kSlots; ++h) {
-                            const uint4 cl = *reinterpret_cast<const uint4 *>(rp + jj * kRowB + cell[h]);   // {succ word, pred word, base, -}
+                            const uint4 cl = *reinterpret_cast<const uint4 *>(rp + jj * kRowS + cell[h]);   // {succ word, pred word, base, -}
                             const bool succ = valid && (cl.x & sel[h]) != 0u;
                             const uint32_t at = cl.z + __popc(cl.x & (sel[h] - 1u));
                             qv[jj][h] = succ ? __ldcg(qc_hot + at) : 0.0;
@@ -675,7 +689,7 @@ wide_engine(const WideParams p) {
                         const int part = lane % kPieces;
                         const uint32_t x = __shfl_sync(0xFFFFFFFFu, xs, r);
                         if (x != kWideInvalid) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + ((size_t)buf * 32 + r) * kRowB + part * 16);
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + ((size_t)buf * 32 + r) * kRowS + part * 16);
                             const unsigned char *src = lr + (size_t)x * 4 * kSlotB + pair_off + part * 16;
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                         }
@@ -685,7 +699,7 @@ wide_engine(const WideParams p) {
                 // lane r turns the landed block of row r into kWords cells {succ mask word, pred mask word, index of the
                 // word's first value in the neighbour's run, -}; slots with another level's tag count as empty
                 auto cook = [&](int buf, bool row_valid) {
-                    uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * 32 + lane) * kRowB);
+                    uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * 32 + lane) * kRowS);
                     uint32_t ms[kWords], mp[kWords], pos_s, ts, tp;
                     if constexpr (kW == 256) {
                         const uint4 a0 = rp[0], a1 = rp[1], a2 = rp[2], b0 = rp[4], b1 = rp[5], b2 = rp[6];
@@ -733,7 +747,7 @@ wide_engine(const WideParams p) {
                     x_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : kWideInvalid;
                     cook(buf, (uint32_t)lane < cnt);
                     __syncwarp();
-                    const unsigned char *rows = my_rows + (size_t)buf * 32 * kRowB;
+                    const unsigned char *rows = my_rows + (size_t)buf * 32 * kRowS;
                     for (uint32_t r = 0; r < cnt;) {
                         const uint32_t tt = t0 + r;
                         if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start
