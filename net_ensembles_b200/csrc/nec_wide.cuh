@@ -1,4 +1,4 @@
-// Compact batched engine ("wide" engine) for large graphs: vertex_load of B = 64 or 128 sources per batch with
+// Compact batched engine ("wide" engine) for large graphs: vertex_load of B = 64, 128 or 256 sources per batch with
 // the backward pass working on COMPACT per-entry state instead of source-minor rows.
 //
 // Same quantity as nec_kernels.cuh (reference: src/generic_graph/generic_graph.rs:1310-1385, pull form):
@@ -15,17 +15,21 @@
 //     for which x is one level deeper: successors; their rank in the mask is the index into x's run) and
 //     M_{l-1}(x) (predecessors, counted).  They live in a per-vertex LEVEL RECORD of four slots (level mod 4,
 //     each {mask, position, level tag}), arranged so that the slots of levels l-1 and l+1 share one aligned
-//     64 B (B = 128) or 32 B (B = 64) block: ONE DRAM burst per row, whatever the batch width;
+//     block of B / 2 bytes: one or two DRAM bursts per row, whatever the number of live sources;
 //   * the forward pass writes no distance rows at all (levels are recorded by the queues only), which also
 //     removes the depth limit of byte distances;
-//   * B = 128 halves the forward pass and the row traffic per source again and fills the lanes: an entry of the
-//     widest level carries ~70 of 128 sources.
-// Lanes are compact as before (lane j = j-th live source of the entry being consumed, up to B/32 per lane), one
-// lane sums one (vertex, source) value over the neighbours in adjacency order: results do not depend on the
-// mapping, on positions or on the team size, and are bit-reproducible run to run.
+//   * wide batches: the forward pass and the row traffic are per batch, so every doubling of B halves them per
+//     source, and entries of the widest level fill the lanes (~70 of 128, ~160 of 256 sources).
+// Lanes are compact (lane j = j-th live source of the entry being consumed, up to four per lane = 128 sources; at
+// B = 256 an entry with more live sources is consumed as two work items: ranks 0..127 and the rest), one lane sums
+// one (vertex, source) value over the neighbours in adjacency order: results do not depend on the mapping, on
+// positions or on the team size, and are bit-reproducible run to run.
 //
-// A slot (one batch in flight) is run by a TEAM: the CTAs of one thread-block cluster (1..8), which share the
-// queue tail, position counter and failure flag through rank 0's shared memory and meet at cluster barriers.
+// A slot (one batch in flight) is run by a TEAM of CTAs which share the queue tail, the position counter and the
+// failure flag and meet at team barriers: either consecutive CTAs of a cooperative launch with those scalars and a
+// barrier counter in global memory (kSoft, the default: any team size, every SM usable), or the CTAs of one
+// thread-block cluster with the scalars in rank 0's shared memory (clusters are placed per GPC: only 45 clusters of
+// three 1024-thread CTAs fit on 148 SMs).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
