@@ -39,9 +39,16 @@
 
 #include "nec_kernels.cuh"
 
-#ifndef NEC_WIDE_ROW_PAD
-#define NEC_WIDE_ROW_PAD 0       // bytes added to the pitch of a staged row in shared memory (A/B: 16 removes the bank conflicts of the cooking
-                                 // step but the extra shared memory shrinks L1 and the forward pass loses more: 3623 vs 3513 ms)
+// Rows (entry, neighbour) a warp stages and consumes per step, and the bytes added to a staged row's pitch in shared memory.
+// Lane r cooks row r: at a pitch of 128 B all 32 lanes hit the same banks.  At B = 256, 28 rows at a pitch of 144 B take
+// the room of 32 rows at 128 B and the conflicts drop from 32-way to 4-way: 112.7 -> 126.8 GTEPS.  (Padding WITHOUT
+// shrinking the chunk grows shared memory, shrinks L1, and the forward pass loses more than the backward pass gains;
+// at B = 128 the two staging buffers leave no such trade.)
+#ifndef NEC_WIDE_CHUNK256
+#define NEC_WIDE_CHUNK256 28
+#endif
+#ifndef NEC_WIDE_PAD256
+#define NEC_WIDE_PAD256 16
 #endif
 
 namespace nec {
@@ -113,9 +120,11 @@ template <> struct WideTraits<256> {
 // Shared-memory layout (dynamic): per warp kBufs buffers of 32 staged rows (kW / 2 bytes each; two buffers, one at 256 sources
 // per batch where two would not fit), one group of rows of read-ahead padding, then the masks of each warp's tile of entries.
 template <int kW> __host__ __device__ constexpr int wide_row_bufs() { return kW == 256 ? 1 : 2; }
+template <int kW> __host__ __device__ constexpr int wide_chunk_rows() { return kW == 256 ? NEC_WIDE_CHUNK256 : 32; }
+template <int kW> __host__ __device__ constexpr int wide_row_pitch() { return kW / 2 + (kW == 256 ? NEC_WIDE_PAD256 : 0); }
 template <int kW, int kThreads>
 constexpr size_t wide_smem_bytes() {
-    return (size_t)(kThreads / 32) * wide_row_bufs<kW>() * 32 * (kW / 2 + NEC_WIDE_ROW_PAD) + 8 * (kW / 2 + NEC_WIDE_ROW_PAD) + (size_t)(kThreads / 32) * 32 * (kW / 8);
+    return (size_t)(kThreads / 32) * wide_row_bufs<kW>() * wide_chunk_rows<kW>() * wide_row_pitch<kW>() + 8 * wide_row_pitch<kW>() + (size_t)(kThreads / 32) * 32 * (kW / 8);
 }
 
 constexpr uint32_t kWideInvalid = 0xFFFFFFFFu;
@@ -140,7 +149,8 @@ wide_engine(const WideParams p) {
     constexpr int kSlotB = kW / 4;                      // level-record slot: mask, position, tag (+ padding at B = 128)
     constexpr int kRowB = kW / 2;                       // staged row: the two slots of levels l-1 / l+1 = kWords cooked 16 B cells
     constexpr int kPieces = kRowB / 16;                 // 16 B pieces per row
-    constexpr int kRowS = kRowB + NEC_WIDE_ROW_PAD;     // row pitch in shared memory: lane r cooks row r, and at a pitch of 64 / 128 B all
+    constexpr uint32_t kChunk = wide_chunk_rows<kW>();  // rows per chunk (<= 32: lane r stages and cooks row r)
+    constexpr int kRowS = wide_row_pitch<kW>();     // row pitch in shared memory: lane r cooks row r, and at a pitch of 64 / 128 B all
                                                         // 32 lanes would hit the same banks (16- / 32-way conflicts on every access)
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31;
@@ -209,8 +219,8 @@ wide_engine(const WideParams p) {
     __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
     __shared__ unsigned long long s_cnt[3];
     extern __shared__ __align__(16) unsigned char wide_smem[];
-    unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * 32 * kRowS;   // [kBufs][32][kRowS]
-    uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * 32 * kRowS + 8 * kRowS) + (size_t)warp * 32;   // [32][kWords]
+    unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * kChunk * kRowS;   // [kBufs][kChunk][kRowS]
+    uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * kChunk * kRowS + 8 * kRowS) + (size_t)warp * 32;   // [32][kWords]
     uint32_t *__restrict__ bq = kVirtual ? p.bq_base + (size_t)slot * p.bq_stride : nullptr;
     uint32_t *__restrict__ bcnt = kVirtual ? p.bcnt_base + (size_t)slot * p.lvl_stride : nullptr;
 
@@ -679,7 +689,7 @@ wide_engine(const WideParams p) {
 
                 auto edge_of = [&](uint32_t t0) -> uint32_t {     // neighbour id of flattened entry t0 + lane
                     const uint32_t t = t0 + lane;
-                    if (t >= total) return kWideInvalid;
+                    if (t >= total || (uint32_t)lane >= kChunk) return kWideInvalid;
                     int o = 0;                                    // first entry whose rows end beyond t (zero-row entries are skipped)
 #pragma unroll
                     for (int step = 16; step >= 1; step >>= 1)
@@ -693,7 +703,7 @@ wide_engine(const WideParams p) {
                         const int part = lane % kPieces;
                         const uint32_t x = __shfl_sync(0xFFFFFFFFu, xs, r);
                         if (x != kWideInvalid) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + ((size_t)buf * 32 + r) * kRowS + part * 16);
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + ((size_t)buf * kChunk + r) * kRowS + part * 16);
                             const unsigned char *src = lr + (size_t)x * 4 * kSlotB + pair_off + part * 16;
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                         }
@@ -703,7 +713,8 @@ wide_engine(const WideParams p) {
                 // lane r turns the landed block of row r into kWords cells {succ mask word, pred mask word, index of the
                 // word's first value in the neighbour's run, -}; slots with another level's tag count as empty
                 auto cook = [&](int buf, bool row_valid) {
-                    uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * 32 + lane) * kRowS);
+                    if ((uint32_t)lane >= kChunk) return;           // (no such row: the address would belong to the next warp)
+                    uint4 *rp = reinterpret_cast<uint4 *>(my_rows + ((size_t)buf * kChunk + lane) * kRowS);
                     uint32_t ms[kWords], mp[kWords], pos_s, ts, tp;
                     if constexpr (kW == 256) {
                         const uint4 a0 = rp[0], a1 = rp[1], a2 = rp[2], b0 = rp[4], b1 = rp[5], b2 = rp[6];
@@ -735,23 +746,23 @@ wide_engine(const WideParams p) {
                 // Two row buffers: chunk sc+1's blocks are in flight while chunk sc is consumed.  One buffer (256 sources per
                 // batch: a row is 128 B): the chunk's blocks are requested and waited for in turn; the neighbour ids are
                 // loaded two chunks ahead either way.
-                const uint32_t n_chunks = (total + 31) / 32;
+                const uint32_t n_chunks = (total + kChunk - 1) / kChunk;
                 uint32_t x_cur = edge_of(0);                               // neighbour ids of chunk sc
-                uint32_t x_next = n_chunks > 1 ? edge_of(32) : kWideInvalid;   // ... and of chunk sc+1
+                uint32_t x_next = n_chunks > 1 ? edge_of(kChunk) : kWideInvalid;   // ... and of chunk sc+1
                 if constexpr (kBufs == 2) stage_rows(0, x_cur);
                 for (uint32_t sc = 0; sc < n_chunks; ++sc) {
                     const int buf = kBufs == 2 ? (int)(sc & 1) : 0;
-                    const uint32_t t0 = sc * 32;
-                    const uint32_t cnt = min(32u, total - t0);
+                    const uint32_t t0 = sc * kChunk;
+                    const uint32_t cnt = min(kChunk, total - t0);
                     if constexpr (kBufs == 1) stage_rows(0, x_cur);
                     asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's blocks have landed (this lane's copies)
                     __syncwarp();                                          // ... and every other lane's
                     if constexpr (kBufs == 2) stage_rows(buf ^ 1, x_next); // chunk sc+1 (nothing past the end); buffer drained at sc-1
                     x_cur = x_next;
-                    x_next = sc + 2 < n_chunks ? edge_of(t0 + 64) : kWideInvalid;
+                    x_next = sc + 2 < n_chunks ? edge_of(t0 + 2 * kChunk) : kWideInvalid;
                     cook(buf, (uint32_t)lane < cnt);
                     __syncwarp();
-                    const unsigned char *rows = my_rows + (size_t)buf * 32 * kRowS;
+                    const unsigned char *rows = my_rows + (size_t)buf * kChunk * kRowS;
                     for (uint32_t r = 0; r < cnt;) {
                         const uint32_t tt = t0 + r;
                         if (tt >= cur_end) {                      // warp-uniform: the next entry's rows start
