@@ -15,6 +15,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "../../include/net_ensembles_cuda.h"
@@ -667,6 +668,7 @@ template <int kW, int kThreads>
 int launch_wide_soft_t(nec_ctx *ctx, const nec::WideParams &p, uint32_t slots, uint32_t team) {
     auto kern = nec::wide_engine<kW, kThreads, true>;
     NEC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nec::wide_smem_bytes<kW, kThreads>()));   // per device
+    if (const char *env = getenv("NEC_WIDE_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env));   // A/B knob (percent)
     void *args[] = {(void *)&p};
     NEC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(slots * team), dim3(kThreads), args, nec::wide_smem_bytes<kW, kThreads>(), ctx->stream));
     return NEC_OK;
@@ -952,18 +954,33 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     double *d_bslot = d_q + q_stride * slots;
     uint32_t *d_order = (uint32_t *)(d_bslot + q_stride * slots);
     uint4 *d_pos4 = (uint4 *)(d_order + o_stride * slots);   // o_stride entries per slot; 256 B aligned since o_stride*4 is
-    memcpy(ctx->h_pin, h_sources, (size_t)n_sources * 4);
-    NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, ctx->h_pin, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const bool timing = getenv("NEC_MID_TIMING") != nullptr;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    // a run of consecutive vertex ids (every call of nec_vertex_load, whole-graph shards) needs no source list on the device
+    bool consecutive = n_sources <= 65536;
+    for (uint32_t k = 1; consecutive && k < n_sources; ++k) consecutive = h_sources[k] == h_sources[0] + k;
+    if (!consecutive) {
+        memcpy(ctx->h_pin, h_sources, (size_t)n_sources * 4);
+        NEC_CUDA(ctx, cudaMemcpyAsync(ctx->d_sources, ctx->h_pin, (size_t)n_sources * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_src_status, 0, ret_bytes, ctx->stream));
-    NEC_CUDA(ctx, cudaMemsetAsync(d_bslot, 0, q_stride * 8 * slots, ctx->stream));
+    // (the partial loads are zeroed by the CTAs that own them)
     nec::MidParams p{};
     p.n = n; p.n_pad = (n + 15) / 16 * 16; p.row_ptr = g->d_row_ptr; p.col_idx = g->d_col_idx; p.slab = g->d_slab; p.deg8 = g->d_deg8;
-    p.sources = ctx->d_sources; p.n_sources = n_sources; p.include_endpoints = include_endpoints;
+    p.sources = consecutive ? nullptr : ctx->d_sources; p.source_base = h_sources[0];
+    p.n_sources = n_sources; p.include_endpoints = include_endpoints;
     p.q_base = d_q; p.q_stride = q_stride; p.order_base = d_order; p.order_stride = o_stride;
     p.pos4_base = d_pos4;
     p.bslot_base = d_bslot; p.bslot_stride = q_stride;
     p.source_status = d_status; p.counters = d_counters;
     if (mo) { p.measure_only = 1; p.out_ecc = mo->ecc; p.out_sumdist = mo->sumdist; p.out_reached = mo->reached; }
+    if (const char *env = getenv("NEC_MID_CARVEOUT")) {          // A/B knob: preferred shared-memory carve-out in percent (what is left is L1)
+        const int pct = atoi(env);
+        cudaFuncSetAttribute(nec::mid_engine<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(nec::mid_engine<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(nec::mid_engine<8, nec::kMidThreadsSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(nec::mid_engine<16, nec::kMidThreadsSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (small_ctas) {
         if (g->slab_w == 8) nec::mid_engine<8, nec::kMidThreadsSmall><<<slots, threads, smem, ctx->stream>>>(p);
@@ -975,12 +992,22 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     NEC_CUDA(ctx, cudaGetLastError());
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     if (!mo) {
-        nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
+        // small graphs: a thread per vertex would be a handful of blocks, each thread walking all the slots
+        if ((n + 255) / 256 < 148u && slots >= 64u)
+            nec::reduce_slots_grouped_kernel<32><<<std::min<uint32_t>((n + 31) / 32, 148u * 2u), 1024, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
+        else
+            nec::reduce_slots_kernel<<<std::min<uint32_t>((n + 255) / 256, 148u * 8u), 256, 0, ctx->stream>>>(d_bslot, q_stride, slots, n, d_out);
         NEC_CUDA(ctx, cudaGetLastError());
     }
     NEC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     NEC_CUDA(ctx, cudaMemcpyAsync(h_ret, ctx->d_src_status, ret_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const auto t_host1 = std::chrono::steady_clock::now();
     NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (timing) {
+        const auto t_host2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nec] mid engine host path: issue %.1f us, wait %.1f us\n", std::chrono::duration<double, std::micro>(t_host1 - t_host0).count(),
+                std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
+    }
     unsigned long long counters[8];
     memcpy(counters, h_ret, sizeof counters);
     const uint8_t *status = h_ret + 64;

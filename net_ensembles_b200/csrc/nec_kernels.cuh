@@ -882,6 +882,39 @@ __global__ void reduce_slots_kernel(const double *__restrict__ bslot_base, size_
     }
 }
 
+// The same for SMALL n and many slots (one source per CTA on a graph of a thousand vertices: a thousand slots, four
+// blocks' worth of vertices): 32 vertices per block, warp g sums the slots g, g + G, g + 2G, ... in ascending order,
+// the G partial sums are added in group order.  The grouping depends on nothing but G: reproducible run to run.
+template <int G>
+__global__ void __launch_bounds__(32 * G) reduce_slots_grouped_kernel(const double *__restrict__ bslot_base, size_t bslot_stride,
+                                                                      uint32_t n_slots, uint32_t n, double *__restrict__ out) {
+    __shared__ double part[G][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (uint32_t v0 = blockIdx.x * 32; v0 < n; v0 += gridDim.x * 32) {
+        const uint32_t v = v0 + lane;
+        double acc = 0.0;
+        if (v < n) {
+            const double *col = bslot_base + v;
+            uint32_t s = grp;
+            for (; s + 3 * G < n_slots; s += 4 * G) {           // four loads in flight
+                const double a0 = col[(size_t)s * bslot_stride], a1 = col[(size_t)(s + G) * bslot_stride];
+                const double a2 = col[(size_t)(s + 2 * G) * bslot_stride], a3 = col[(size_t)(s + 3 * G) * bslot_stride];
+                acc += a0; acc += a1; acc += a2; acc += a3;
+            }
+            for (; s < n_slots; s += G) acc += col[(size_t)s * bslot_stride];
+        }
+        part[grp][lane] = acc;
+        __syncthreads();
+        if (grp == 0 && v < n) {
+            double t = 0.0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) t += part[g][lane];
+            out[v] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // a[v] += b[v]
 __global__ void add_into_kernel(double *__restrict__ a, const double *__restrict__ b, uint32_t n) {
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) a[v] += b[v];

@@ -66,7 +66,8 @@ struct MidParams {
     const uint32_t *__restrict__ col_idx;
     const uint4 *__restrict__ slab;           // n rows of W u32: [degree, first W-1 neighbours] (see nec_graph)
     const uint8_t *__restrict__ deg8;         // min(degree, 255) per vertex (255: look at row_ptr)
-    const uint32_t *__restrict__ sources;
+    const uint32_t *__restrict__ sources;     // nullptr: source index si is vertex source_base + si
+    uint32_t source_base;
     uint32_t n_sources;
     int include_endpoints;
     double *q_base;        size_t q_stride;
@@ -155,6 +156,10 @@ mid_engine(const MidParams p) {
     double *__restrict__ bslot = p.bslot_base + (size_t)blockIdx.x * p.bslot_stride;
 
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    if (!p.measure_only) {                        // this CTA's partial load starts at zero (ordered before the first sweep by the barriers of the first source)
+        double2 *b2 = reinterpret_cast<double2 *>(bslot);
+        for (uint32_t i = threadIdx.x; i < (n + 1) / 2; i += kT) __stcs(&b2[i], make_double2(0.0, 0.0));
+    }
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0, cyc_small = 0;
 
@@ -175,7 +180,7 @@ mid_engine(const MidParams p) {
     };
 
     for (uint32_t si = blockIdx.x; si < p.n_sources; si += gridDim.x) {
-        const uint32_t s = p.sources[si];
+        const uint32_t s = p.sources ? p.sources[si] : p.source_base + si;
         long long t_phase = clock64();
         uint32_t t_reached = 0, t_edges = 0;      // per thread, this source
         // ---- reset (shared memory only) ------------------------------------------------

@@ -40,15 +40,31 @@
 #include "nec_kernels.cuh"
 
 // Rows (entry, neighbour) a warp stages and consumes per step, and the bytes added to a staged row's pitch in shared memory.
-// Lane r cooks row r: at a pitch of 128 B all 32 lanes hit the same banks.  At B = 256, 28 rows at a pitch of 144 B take
-// the room of 32 rows at 128 B and the conflicts drop from 32-way to 4-way: 112.7 -> 126.8 GTEPS.  (Padding WITHOUT
-// shrinking the chunk grows shared memory, shrinks L1, and the forward pass loses more than the backward pass gains;
-// at B = 128 the two staging buffers leave no such trade.)
+// Lane r cooks row r: at a pitch of 128 B all 32 lanes hit the same banks; at 144 B a quarter warp is conflict-free
+// (112.7 -> 126.8 GTEPS with 28 rows per chunk in the room of 32 unpadded ones).  The chunk size also sets the L1 size, and the
+// forward pass lives on L1: 21 rows keep the CTA under 164 KB of shared memory, i.e. 92 KB of L1 instead of 60: forward pass
+// -18 %, backward pass +2.6 % (more chunks per tile), 1.5 % faster overall than 28 rows; 32 padded rows (28 KB of L1) slow
+// the forward pass down 1.6 x.  (Not the pull scan's adjacency rows: copying a warp's contiguous span of col_idx into shared
+// memory with coalesced loads left the dependence as it was and cost 1.3 %.  Not spills either: the 139 LDL/STL of this
+// kernel save batch-level values around the phases, none sits in an inner loop - scripts/sass_lines.py.)
+// (At B = 128 the two staging buffers leave no such trade.)
 #ifndef NEC_WIDE_CHUNK256
-#define NEC_WIDE_CHUNK256 28
+#define NEC_WIDE_CHUNK256 21
 #endif
 #ifndef NEC_WIDE_PAD256
 #define NEC_WIDE_PAD256 16
+#endif
+// A/B knobs (scripts/exp_r2.py --lib), both measured and left off (profiles/r2_ab_wide_engine.log):
+//  * two row buffers per warp at B = 256 (chunk sc+1 in flight while chunk sc is consumed) with chunks of half the size:
+//    10 % slower - the time goes into the q pulls of a chunk's row groups, not into waiting for its rows, and every chunk
+//    has a fixed cost;
+//  * staging a chunk with ONE bulk copy per row (cp.async.bulk, 128 B, lane r requests row r, completion counted by a
+//    per-warp mbarrier) instead of eight 16-byte cp.async pieces per row spread over the lanes: 2 % slower.
+#ifndef NEC_WIDE_BUFS256
+#define NEC_WIDE_BUFS256 1
+#endif
+#ifndef NEC_WIDE_BULK
+#define NEC_WIDE_BULK 0
 #endif
 
 namespace nec {
@@ -119,7 +135,7 @@ template <> struct WideTraits<256> {
 
 // Shared-memory layout (dynamic): per warp kBufs buffers of 32 staged rows (kW / 2 bytes each; two buffers, one at 256 sources
 // per batch where two would not fit), one group of rows of read-ahead padding, then the masks of each warp's tile of entries.
-template <int kW> __host__ __device__ constexpr int wide_row_bufs() { return kW == 256 ? 1 : 2; }
+template <int kW> __host__ __device__ constexpr int wide_row_bufs() { return kW == 256 ? NEC_WIDE_BUFS256 : 2; }
 template <int kW> __host__ __device__ constexpr int wide_chunk_rows() { return kW == 256 ? NEC_WIDE_CHUNK256 : 32; }
 template <int kW> __host__ __device__ constexpr int wide_row_pitch() { return kW / 2 + (kW == 256 ? NEC_WIDE_PAD256 : 0); }
 template <int kW, int kThreads>
@@ -218,12 +234,23 @@ wide_engine(const WideParams p) {
     __shared__ uint32_t s_tile_rs[kWarps][32], s_tile_off[kWarps][32], s_tile_end[kWarps][32];   // adjacency row start, first and past-the-end flattened row of each entry
     __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
     __shared__ unsigned long long s_cnt[3];
+    constexpr bool kBulk = NEC_WIDE_BULK != 0 && kW == 256 && wide_row_bufs<kW>() == 1;
+    __shared__ __align__(8) unsigned long long s_mbar[kBulk ? kWarps : 1];   // bulk staging: a warp's mbarrier ...
+    __shared__ uint32_t s_mphase[kBulk ? kWarps : 1];                        // ... and the parity of its next phase
     extern __shared__ __align__(16) unsigned char wide_smem[];
     unsigned char *my_rows = wide_smem + (size_t)warp * kBufs * kChunk * kRowS;   // [kBufs][kChunk][kRowS]
     uint32_t (*my_tile_m)[kWords] = reinterpret_cast<uint32_t (*)[kWords]>(wide_smem + (size_t)kWarps * kBufs * kChunk * kRowS + 8 * kRowS) + (size_t)warp * 32;   // [32][kWords]
     uint32_t *__restrict__ bq = kVirtual ? p.bq_base + (size_t)slot * p.bq_stride : nullptr;
     uint32_t *__restrict__ bcnt = kVirtual ? p.bcnt_base + (size_t)slot * p.lvl_stride : nullptr;
 
+    if constexpr (kBulk) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[warp])) : "memory");
+            s_mphase[warp] = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     uint32_t my_depth = 0;
     long long cyc_reset = 0, cyc_fwd = 0, cyc_bwd = 0;      // thread 0 only
     unsigned long long dir_levels = 0;
@@ -698,7 +725,7 @@ wide_engine(const WideParams p) {
                 };
                 auto stage_rows = [&](int buf, uint32_t xs) {     // level-record blocks of the chunk whose neighbour ids are `xs` (lane r: row r)
 #pragma unroll
-                    for (int it = 0; it < kPieces; ++it) {
+                    for (int it = 0; it < ((int)kChunk * kPieces + 31) / 32; ++it) {      // 32 / kPieces rows per step
                         const int r = it * (32 / kPieces) + lane / kPieces;
                         const int part = lane % kPieces;
                         const uint32_t x = __shfl_sync(0xFFFFFFFFu, xs, r);
@@ -709,6 +736,29 @@ wide_engine(const WideParams p) {
                         }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                // bulk form: lane r requests row r as one 128 B copy; the warp's mbarrier counts the bytes
+                auto stage_rows_bulk = [&](uint32_t xs, uint32_t cnt) {
+                    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
+                    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * (uint32_t)kRowB) : "memory");
+                    __syncwarp();
+                    if (xs != kWideInvalid) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(my_rows + (size_t)lane * kRowS);
+                        const unsigned char *src = lr + (size_t)xs * 4 * kSlotB + pair_off;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst), "l"(src), "r"((uint32_t)kRowB), "r"(bar) : "memory");
+                    }
+                };
+                auto wait_rows_bulk = [&]() {
+                    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
+                    const uint32_t phase = s_mphase[warp];
+                    uint32_t done;
+                    do {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+                    } while (!done);
+                    __syncwarp();                                   // every lane has read the parity
+                    if (lane == 0) s_mphase[warp] = phase ^ 1u;
                 };
                 // lane r turns the landed block of row r into kWords cells {succ mask word, pred mask word, index of the
                 // word's first value in the neighbour's run, -}; slots with another level's tag count as empty
@@ -754,8 +804,11 @@ wide_engine(const WideParams p) {
                     const int buf = kBufs == 2 ? (int)(sc & 1) : 0;
                     const uint32_t t0 = sc * kChunk;
                     const uint32_t cnt = min(kChunk, total - t0);
-                    if constexpr (kBufs == 1) stage_rows(0, x_cur);
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's blocks have landed (this lane's copies)
+                    if constexpr (kBulk) { stage_rows_bulk(x_cur, cnt); wait_rows_bulk(); }
+                    else {
+                        if constexpr (kBufs == 1) stage_rows(0, x_cur);
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");   // chunk sc's blocks have landed (this lane's copies)
+                    }
                     __syncwarp();                                          // ... and every other lane's
                     if constexpr (kBufs == 2) stage_rows(buf ^ 1, x_next); // chunk sc+1 (nothing past the end); buffer drained at sc-1
                     x_cur = x_next;
@@ -793,6 +846,7 @@ wide_engine(const WideParams p) {
                         }
                     }
                     __syncwarp();                                 // buffer `buf` may be refilled next iteration
+                    if constexpr (kBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cooked (generic) writes before the next bulk copies
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 if (cur >= 0) finish_entry();
