@@ -41,15 +41,18 @@
 
 // Rows (entry, neighbour) a warp stages and consumes per step, and the bytes added to a staged row's pitch in shared memory.
 // Lane r cooks row r: at a pitch of 128 B all 32 lanes hit the same banks; at 144 B a quarter warp is conflict-free
-// (112.7 -> 126.8 GTEPS with 28 rows per chunk in the room of 32 unpadded ones).  The chunk size also sets the L1 size, and the
-// forward pass lives on L1: 21 rows keep the CTA under 164 KB of shared memory, i.e. 92 KB of L1 instead of 60: forward pass
-// -18 %, backward pass +2.6 % (more chunks per tile), 1.5 % faster overall than 28 rows; 32 padded rows (28 KB of L1) slow
-// the forward pass down 1.6 x.  (Not the pull scan's adjacency rows: copying a warp's contiguous span of col_idx into shared
-// memory with coalesced loads left the dependence as it was and cost 1.3 %.  Not spills either: the 139 LDL/STL of this
-// kernel save batch-level values around the phases, none sits in an inner loop - scripts/sass_lines.py.)
+// (112.7 -> 126.8 GTEPS with 28 rows per chunk in the room of 32 unpadded ones).  The chunk size also sets the L1 size, and both
+// passes live on L1 (it bounds the misses an SM keeps in flight): a CTA under 164 KB of shared memory leaves 92 KB of L1 instead
+// of 60, which makes the forward pass 18 % and the backward pass 7 % faster at equal chunk size, while every row taken from
+// the chunk costs the backward pass ~0.4 % (more chunks per tile).  25 rows is the most that fits under 164 KB after the
+// kernel's static shared memory was cut from 33 to 17 KB: 1270 -> 1249 ms per 37 888 sources against 21 rows with the old
+// layout, 1291 ms at 26 rows (over the step: 60 KB of L1).  32 padded rows (28 KB of L1) slow the forward pass down 1.6 x.
+// (What in the forward pass needs the L1 is not the pull scan's adjacency rows: copying a warp's contiguous span of col_idx
+// into shared memory with coalesced loads left the dependence as it was and cost 1.3 %.  Not spills either: the 139 LDL/STL
+// of this kernel save batch-level values around the phases, none sits in an inner loop - scripts/sass_lines.py.)
 // (At B = 128 the two staging buffers leave no such trade.)
 #ifndef NEC_WIDE_CHUNK256
-#define NEC_WIDE_CHUNK256 21
+#define NEC_WIDE_CHUNK256 25
 #endif
 #ifndef NEC_WIDE_PAD256
 #define NEC_WIDE_PAD256 16
@@ -229,10 +232,11 @@ wide_engine(const WideParams p) {
         } else
             cg::this_cluster().sync();
     };
-    __shared__ unsigned char s_klist[kWarps][kW];        // backward: the live sources of the entry a warp is consuming
+    // Static shared memory is kept small on purpose: together with the staging buffers it decides how much L1 the SM keeps.
+    __shared__ unsigned char s_klist[kWarps][kW > 128 ? 128 : kW];   // backward: the live sources of the work item a warp is consuming (at most 128)
     __shared__ uint32_t s_tile_p[kWarps][32];             // backward: run positions of the warp's tile of entries (masks: dynamic, below)
-    __shared__ uint32_t s_tile_rs[kWarps][32], s_tile_off[kWarps][32], s_tile_end[kWarps][32];   // adjacency row start, first and past-the-end flattened row of each entry
-    __shared__ double s_tile_t[kWarps][32];               // the entries' contributions to the partial load
+    __shared__ uint32_t s_tile_base[kWarps][32], s_tile_end[kWarps][32];   // per entry: adjacency row start minus its first flattened row, and its past-the-end flattened row
+    // (an entry's contribution to the partial load is written over its mask in my_tile_m once the entry has been begun)
     __shared__ unsigned long long s_cnt[3];
     constexpr bool kBulk = NEC_WIDE_BULK != 0 && kW == 256 && wide_row_bufs<kW>() == 1;
     __shared__ __align__(8) unsigned long long s_mbar[kBulk ? kWarps : 1];   // bulk staging: a warp's mbarrier ...
@@ -635,10 +639,8 @@ wide_engine(const WideParams p) {
                     count_tile(counted ? c : 0u, deg, counted);
                     const uint32_t incl = warp_inclusive_scan(deg, lane);
                     total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                    s_tile_rs[warp][lane] = rs;
-                    s_tile_off[warp][lane] = incl - deg;
+                    s_tile_base[warp][lane] = rs - (incl - deg);
                     s_tile_end[warp][lane] = incl;
-                    s_tile_t[warp][lane] = 0.0;
                 }
                 __syncwarp();
                 // per-entry state of this lane: up to kWords sources (ranks lane, lane + 32, ...)
@@ -688,7 +690,7 @@ wide_engine(const WideParams p) {
                         }
                     }
                     const double tot = warp_sum(contrib);
-                    if (lane == 0) s_tile_t[warp][cur] = tot;
+                    if (lane == 0) *reinterpret_cast<double *>(&my_tile_m[cur][0]) = tot;      // the mask was consumed by begin_entry
                 };
                 // kRows rows of the current entry starting at row r of the cooked chunk in `rows`, kSlots sources per
                 // lane.  Straight-line: every q load of the group is issued (predicated) before the first is consumed.
@@ -721,7 +723,7 @@ wide_engine(const WideParams p) {
 #pragma unroll
                     for (int step = 16; step >= 1; step >>= 1)
                         if (s_tile_end[warp][o + step - 1] <= t) o += step;
-                    return __ldg(p.col_idx + s_tile_rs[warp][o] + (t - s_tile_off[warp][o]));
+                    return __ldg(p.col_idx + (uint32_t)(s_tile_base[warp][o] + t));     // (32-bit wrap-around: the base may be 'negative')
                 };
                 auto stage_rows = [&](int buf, uint32_t xs) {     // level-record blocks of the chunk whose neighbour ids are `xs` (lane r: row r)
 #pragma unroll
@@ -854,7 +856,9 @@ wide_engine(const WideParams p) {
                 if (idx < le) {                                     // one writer per vertex, level and half
                     double *b = bslot;
                     if constexpr (kVirtual) { if (my_qi >> 31) b = bslot + p.bslot_hi_off; }
-                    b[queue_v[my_qi & 0x7FFFFFFFu]] += s_tile_t[warp][lane];
+                    // (an entry of level >= 1 has at least its predecessor's row; one without rows was never begun and still holds its mask)
+                    if (s_tile_end[warp][lane] != (lane ? s_tile_end[warp][lane - 1] : 0u))
+                        b[queue_v[my_qi & 0x7FFFFFFFu]] += *reinterpret_cast<const double *>(&my_tile_m[lane][0]);
                 }
             }
         }
