@@ -817,3 +817,24 @@ def test_mid_engine_cta_shapes_agree(ctx, oracle, monkeypatch):
         monkeypatch.delenv("NEC_MID_SMALL_N")
         assert close(small, big, 1e-12) and close(small, oracle.vertex_load(rp, col, False, threads=0), REL)
         dg.free()
+
+
+def test_mid_engine_consecutive_sources_need_no_list_and_small_graphs_reduce_in_groups(ctx, oracle):
+    """A run of consecutive source ids is passed to the kernel as (first id, count) instead of a device list, and on small
+    graphs the slots' partial loads are summed by slot groups (many slots, few vertices): same values as the list path
+    and the oracle, whatever the first id, and bitwise reproducible."""
+    for e in (ne.ErEnsembleC(1000, 4.0, 5), ne.SwEnsemble(3000, 0.1, 9)):
+        rp, col = e.export_csr()
+        n = len(rp) - 1
+        dg = ctx.upload(rp, col)
+        ctx.set_engine(2)
+        for lo, hi in ((0, n), (n // 3, n // 3 + 257), (n - 40, n), (17, 18)):
+            run = np.arange(lo, hi, dtype=np.uint32)
+            got = dg.vertex_load_sources(run, True)
+            assert ctx.stats()["engine"] == 2 and ctx.stats()["n_sources"] == hi - lo
+            assert dg.vertex_load_sources(run, True).tobytes() == got.tobytes()
+            rev = dg.vertex_load_sources(run[::-1].copy(), True)             # same sources, not a run: the list path
+            assert close(got, rev, 1e-12)
+            assert close(got, oracle.vertex_load(rp, col, True, sources=run, threads=0), REL), (lo, hi)
+        ctx.set_engine(0)
+        dg.free()

@@ -135,3 +135,61 @@ def test_differential_fuzz_against_the_oracle(wide_ctx, oracle, monkeypatch):
         incl = bool(trial & 4)
         assert close(dg.vertex_load(incl), oracle.vertex_load(rp, col, incl), REL), trial
         dg.free()
+
+
+def _csr_from_edges(n, a, b):
+    """Undirected edge arrays -> CSR with rows in edge order (numpy only: these graphs have a few 10^5 vertices)."""
+    src = np.concatenate([a, b]).astype(np.int64)
+    dst = np.concatenate([b, a]).astype(np.uint32)
+    order = np.argsort(src, kind="stable")
+    rp = np.zeros(n + 1, np.uint64)
+    rp[1:] = np.cumsum(np.bincount(src, minlength=n))
+    return rp, dst[order]
+
+
+def test_default_plan_on_a_giant_hub_with_a_tail_and_isolated_vertices(ctx, oracle):
+    """Beyond the mid engine's size (default plan, no knobs): one hub with 200 000 leaves (a row of 200 000 entries: the pull
+    scan's whole-warp gather, a backward tile of 200 000 rows), a path of 1500 vertices hanging off a leaf (1500 levels:
+    32-bit level tags, one team barrier set per level), a second small component and isolated vertices."""
+    hub, leaves, path, extra = 0, 200_000, 1500, 300
+    n = 1 + leaves + path + extra + 50                       # the last 50 vertices are isolated
+    a = [np.zeros(leaves, np.int64)]
+    b = [np.arange(1, leaves + 1, dtype=np.int64)]
+    p0 = 1 + leaves
+    a.append(np.concatenate([[leaves], np.arange(p0, p0 + path - 1)]))          # last leaf -> path
+    b.append(np.arange(p0, p0 + path))
+    e0 = p0 + path
+    a.append(np.arange(e0, e0 + extra - 1)); b.append(np.arange(e0 + 1, e0 + extra))   # second component: a short path ...
+    a.append(np.arange(e0, e0 + extra - 2)); b.append(np.arange(e0 + 2, e0 + extra))   # ... with chords
+    rp, col = _csr_from_edges(n, np.concatenate(a), np.concatenate(b))
+    dg = ctx.upload(rp, col)
+    src = np.concatenate([[hub, 1, 2, leaves, p0, p0 + path - 1, e0, e0 + extra - 1, n - 1],
+                          np.arange(7, n, 9973)]).astype(np.uint32)
+    for incl in (True, False):
+        got = dg.vertex_load_sources(src, incl)
+        st = ctx.stats()
+        assert st["engine"] & 15 == 4 and st["max_depth"] >= path
+        want = oracle.vertex_load(rp, col, incl, sources=src, threads=0)
+        assert close(got, want, REL), incl
+        assert st["reached_pairs"] == oracle.last_stats["reached_pairs"] and st["edge_pairs"] == oracle.last_stats["edge_pairs"]
+    assert got[n - 1] == 0.0 and got[hub] > 1e5
+    dg.free()
+
+
+def test_default_plan_hands_a_lattice_back_and_the_deep_path_finishes_it(ctx, oracle):
+    """A 450 x 450 grid through the default plan: a vertex sits on far more than a dozen distinct levels within a batch, so the
+    batch overflows its slot's queue, is handed to the source-minor engine, and - 898 levels deep - to that engine's
+    32-bit distance rows.  Nothing is approximated on the way."""
+    side = 450
+    n = side * side
+    idx = np.arange(n, dtype=np.int64).reshape(side, side)
+    a = np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()])
+    b = np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()])
+    rp, col = _csr_from_edges(n, a, b)
+    dg = ctx.upload(rp, col)
+    src = np.concatenate([[0, side - 1, n - 1, n // 2 + side // 2], np.arange(11, n, 3001)]).astype(np.uint32)
+    got = dg.vertex_load_sources(src, True)
+    st = ctx.stats()
+    assert st["engine"] & 15 == 4 and st["requeued_batches"] >= 1 and st["max_depth"] == 2 * (side - 1)
+    assert close(got, oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
+    dg.free()
