@@ -78,11 +78,14 @@ int nec_set_stream(nec_ctx *ctx, void *cuda_stream);
  * 0 restores the default (80 % of free device memory at first use). */
 int nec_set_workspace_limit(nec_ctx *ctx, uint64_t bytes);
 
-/* Engine selection (tests and profiling; the default 0 chooses by graph size):
+/* Engine selection (tests and profiling; the default 0 chooses by graph size and structure):
  *   NEC_ENGINE_AUTO    0  n in [64, 180000]: one source per CTA, per-source state in shared
- *                         memory; n > 180000: the compact batched engine (64 or 128 sources per
- *                         batch, a thread-block cluster per batch); n < 64: the source-minor
- *                         batched engine (32 or 64 sources per CTA)
+ *                         memory - unless n >= 8192, the call has >= 512 sources and a one-off
+ *                         probe of the graph (kept with the nec_graph) finds that a vertex sits on
+ *                         few distinct BFS levels within a batch (random, scale-free graphs): then,
+ *                         and for n > 180000, the compact batched engine (64, 128 or 256 sources per
+ *                         batch, a team of CTAs per batch); n < 64: the source-minor batched engine
+ *                         (32 or 64 sources per CTA)
  *   NEC_ENGINE_BATCHED 1  always the source-minor batched engine
  *   NEC_ENGINE_MID     2  the one-source-per-CTA engine whenever n <= 180000
  *   NEC_ENGINE_WIDE    3  the compact batched engine whatever n */

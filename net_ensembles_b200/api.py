@@ -59,8 +59,9 @@ class Context:
         self._check(self._lib.nec_set_workspace_limit(self._h, int(nbytes)))
 
     def set_engine(self, engine):
-        """0 auto, 1 source-minor batched (32 or 64 sources per CTA), 2 mid (one source per CTA, default for 64 <= n <= 180000),
-        3 compact batched (64 or 128 sources per thread-block cluster, default for n > 180000)."""
+        """0 auto, 1 source-minor batched (32 or 64 sources per CTA), 2 mid (one source per CTA, default for 64 <= n <= 180000
+        unless a one-off structural probe of the graph prefers 3), 3 compact batched (64 / 128 / 256 sources per team of CTAs,
+        default for n > 180000)."""
         self._check(self._lib.nec_set_engine(self._h, int(engine)))
 
     def stats(self):

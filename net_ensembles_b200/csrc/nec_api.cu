@@ -71,6 +71,10 @@ struct nec_graph {
     uint8_t *d_deg8 = nullptr;       // min(degree, 255) per vertex (mid engine)
     int slab_w = 0;
     std::vector<nec_graph *> replicas;   // multi-device context: the same CSR on devices 1..
+    // Which engine runs large calls on a graph that fits the mid engine (engine_hint below): 0 not probed yet, 2 mid, 4 wide;
+    // and the probe's finding, queue entries per vertex of one 256-source batch
+    mutable int engine_hint = 0;
+    mutable float probe_entries = 0.f;
 };
 
 struct nec_ctx {
@@ -102,6 +106,7 @@ struct nec_ctx {
     uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;      // pinned host staging of a call's small transfers (source list in, verdicts + counters out)
     struct { uint32_t n = 0; int slab_w = 0, threads = 0, occ = 0; } mid_occ;   // occupancy of the last mid-engine shape asked for
     int force_engine = 0;                             // 0 auto, 1 batched only, 2 mid whenever it fits
+    bool probe_mode = false;                          // engine_hint: a probe batch is running (its hand-backs are not re-run)
     double *dbg_sigma = nullptr;                      // nec_bfs_debug: plane for the path counts of the debug instantiation
     uint32_t pull_mode = 1;                           // batched forward pass: 0 push only, 1 per-level cost model, 2 pull only (NEC_PULL, tests)
     bool wide_ctas = false;                           // batched engine: 1024-thread CTAs, one per SM (set per call)
@@ -701,7 +706,8 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
     WidePlan best{};
     double best_cost = 1e300;
     for (uint32_t kw : {256u, 128u, 64u}) {
-        if (const char *env = getenv("NEC_WIDE_WIDTH")) { if ((uint32_t)atoi(env) != kw) continue; }
+        if (ctx->probe_mode) { if (kw != 64u) continue; }               // engine_hint's probe: four 64-source batches, whatever the knobs say
+        else if (const char *env = getenv("NEC_WIDE_WIDTH")) { if ((uint32_t)atoi(env) != kw) continue; }
         if ((uint64_t)n * kw + kw >= 0xFFFFFFFFull) continue;           // 32-bit positions and queue indices
         const size_t qcap = std::min((size_t)n * kw + kw, (size_t)n * per_vertex + kw);
         const size_t ps = wide_per_slot_bytes(n, kw, qcap, max_levels);
@@ -862,7 +868,7 @@ int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources
         for (uint32_t k = b * kw; k < std::min<uint64_t>((uint64_t)(b + 1) * kw, n_sources); ++k) redo.push_back(h_sources[k]);
         st.requeued_batches++;
     }
-    if (!redo.empty()) {
+    if (!redo.empty() && !ctx->probe_mode) {            // (a probe only wants to know that the batch did not fit)
         if ((rc = grow(ctx, ctx->d_tmp, ctx->d_tmp_cap, n)) != NEC_OK) return rc;
         rc = run_sources_batched(ctx, g, redo.data(), (uint32_t)redo.size(), include_endpoints, ctx->d_tmp, false, nullptr, nullptr, nullptr);
         if (rc != NEC_OK) return rc;
@@ -1041,8 +1047,58 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
     return NEC_OK;
 }
 
-// Engine choice: graphs whose distance vector fits in shared memory take the one-source-per-CTA
-// engine; everything else (and whatever that engine hands back) takes the batched engine.
+// Which of the two engines suits a graph that FITS the mid engine is a property of its structure, not of its size: what the compact
+// batched engine pays per source is proportional to the number of distinct BFS levels a vertex sits on within a batch (queue
+// entries per vertex: ~4 on random and scale-free graphs, where it is 1.3-5 x faster than one source per CTA from n = 8192 up;
+// 9 and more on small-world rings and lattices, where it is slower: scripts/exp_engine_choice.py, profiles/r2_engine_choice.log).
+// So the first large call on such a graph runs a probe (vertex ids 0..255 as four 64-source batches, result discarded, ~1-7 ms) and the finding is
+// kept with the graph: a pure function of the graph, hence the same engine - and bitwise the same result - call after call.
+constexpr uint32_t kProbeMinN = 8192;            // below: the mid engine's small CTAs win whatever the structure
+constexpr uint32_t kProbeMinSources = 512;       // below: not worth a probe; one wave of the mid engine
+constexpr float kProbeMaxEntries = 7.5f;         // queue entries per vertex of a 64-source batch; measured break-even: 7.0 -> 1.5 x for wide, 7.8 -> 1.0, 8.4 -> 0.97, 8.8 -> 0.77
+int engine_hint(nec_ctx *ctx, const nec_graph *g, int *hint) {
+    if (g->engine_hint == 0) {
+        const uint32_t cnt = std::min<uint32_t>(g->n, 256u);
+        std::vector<uint32_t> probe(cnt);
+        for (uint32_t k = 0; k < cnt; ++k) probe[k] = k;
+        int rc = grow(ctx, ctx->d_tmp, ctx->d_tmp_cap, g->n);
+        if (rc != NEC_OK) return rc;
+        ctx->probe_mode = true;
+        rc = run_sources_wide(ctx, g, probe.data(), cnt, 1, ctx->d_tmp);
+        ctx->probe_mode = false;
+        if (rc == NEC_ENOMEM) { g->engine_hint = 2; g->probe_entries = -1.f; }          // no room for a slot: the mid engine it is
+        else if (rc != NEC_OK) return rc;
+        else {
+            const nec_stats &st = ctx->stats;
+            g->probe_entries = st.requeued_batches ? 1e9f : (float)((double)st.vertex_visits / ((double)std::max<uint64_t>(st.n_batches, 1) * (double)std::max<uint32_t>(g->n, 1u)));
+            g->engine_hint = g->probe_entries <= kProbeMaxEntries ? 4 : 2;
+        }
+        if (getenv("NEC_PROBE_VERBOSE")) fprintf(stderr, "[nec] probe: n=%u, %.2f queue entries per vertex in one batch -> %s engine\n", g->n, g->probe_entries, g->engine_hint == 4 ? "compact batched" : "mid");
+        if (g->engine_hint == 2 && ctx->wide.base) {       // the probe's slot is of no further use
+            NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->wide.base);
+            ctx->wide = WideArena{};
+        }
+    }
+    *hint = g->engine_hint;
+    return NEC_OK;
+}
+// does a call of n_sources sources on this (mid-capable) graph go to the compact batched engine instead?
+int prefers_wide(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources, bool *wide) {
+    *wide = false;
+    if (ctx->force_engine != 0 || g->n < kProbeMinN || n_sources < kProbeMinSources || (uint64_t)g->n * 256 + 256 >= 0xFFFFFFFFull) return NEC_OK;
+    if (const char *env = getenv("NEC_WIDE")) { if (atoi(env) == 0) return NEC_OK; }
+    if (const char *env = getenv("NEC_PROBE")) { if (atoi(env) == 0) return NEC_OK; }     // A/B knob: size threshold only
+    int hint = 2;
+    const int rc = engine_hint(ctx, g, &hint);
+    if (rc != NEC_OK) return rc;
+    *wide = hint == 4;
+    return NEC_OK;
+}
+
+// Engine choice: graphs whose distance vector fits in shared memory take the one-source-per-CTA engine unless their structure
+// suits the compact batched engine (engine_hint); larger ones take the compact batched engine; tiny ones, debug planes and
+// whatever the others hand back take the source-minor batched engine.
 int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uint32_t n_sources,
                 int include_endpoints, double *d_out, bool debug, uint32_t *dbg_npred, double *dbg_bk) {
     if (const char *env = getenv("NEC_L2_FETCH")) {       // A/B knob: L2 fetch granularity hint (32 / 64 / 128 B)
@@ -1058,6 +1114,12 @@ int run_sources(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources, uin
                    (uint64_t)g->n * 64 + 64 < 0xFFFFFFFFull;
     if (const char *env = getenv("NEC_WIDE")) { if (atoi(env) == 0 && ctx->force_engine != 3) wide_ok = false; }
     if (wide_ok) return run_sources_wide(ctx, g, h_sources, n_sources, include_endpoints, d_out);
+    if (mid_ok) {
+        bool wide = false;
+        const int rcp = prefers_wide(ctx, g, n_sources, &wide);
+        if (rcp != NEC_OK) return rcp;
+        if (wide) return run_sources_wide(ctx, g, h_sources, n_sources, include_endpoints, d_out);
+    }
     if (!mid_ok) return run_sources_batched(ctx, g, h_sources, n_sources, include_endpoints, d_out, debug, dbg_npred, dbg_bk);
     std::vector<uint32_t> fallback;
     int rc = run_sources_mid(ctx, g, h_sources, n_sources, include_endpoints, d_out, fallback);
@@ -1897,7 +1959,12 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     const uint32_t ns = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, n_sources_total / n_devices_of(ctx)), 0xFFFFFFFFull);   // per device
     const bool mid_ok = g->d_slab && g->n <= nec::kMidMaxN && nec::mid_smem_bytes(g->n, g->slab_w) <= 227u * 1024u - 4096u &&
                         ctx->force_engine != 1 && ctx->force_engine != 3 && (g->n >= nec::kMidMinN || ctx->force_engine == 2);
-    if (mid_ok) {       // one source per CTA, two CTAs per SM
+    bool mid_prefers_wide = false;
+    if (mid_ok) {
+        const int rcp = prefers_wide(ctx, g, ns, &mid_prefers_wide);
+        if (rcp != NEC_OK) return rcp;
+    }
+    if (mid_ok && !mid_prefers_wide) {       // one source per CTA, two CTAs per SM
         uint32_t small_n = 16384;
         if (const char *env = getenv("NEC_MID_SMALL_N")) small_n = (uint32_t)atol(env);
         const uint64_t per_sm = g->n <= small_n ? 8ull : 2ull;      // CTAs (= sources in flight) per SM, see run_sources_mid
@@ -1906,7 +1973,7 @@ int nec_wave_size(nec_ctx *ctx, const nec_graph *g, uint64_t n_sources_total, ui
     }
     bool wide_ok = (ctx->force_engine == 3 || (ctx->force_engine == 0 && g->n > nec::kMidMaxN)) && (uint64_t)g->n * 64 + 64 < 0xFFFFFFFFull;
     if (const char *env = getenv("NEC_WIDE")) { if (atoi(env) == 0 && ctx->force_engine != 3) wide_ok = false; }
-    if (wide_ok) {
+    if (wide_ok || mid_prefers_wide) {
         WidePlan wp{};
         const int rcw = plan_wide(ctx, g->n, ns, wp);
         if (rcw != NEC_OK) return rcw;

@@ -838,3 +838,40 @@ def test_mid_engine_consecutive_sources_need_no_list_and_small_graphs_reduce_in_
             assert close(got, oracle.vertex_load(rp, col, True, sources=run, threads=0), REL), (lo, hi)
         ctx.set_engine(0)
         dg.free()
+
+
+def test_engine_is_chosen_by_structure_for_graphs_that_fit_the_mid_engine(ctx, oracle, monkeypatch):
+    """From n = 8192 up a large call on a graph that fits the mid engine first probes one batch with the compact batched engine
+    (queue entries per vertex: how many distinct levels a vertex sits on within a batch) and keeps the finding with the
+    graph: random / scale-free graphs go to the compact engine, small-world rings stay with one source per CTA.  The
+    choice is a function of the graph alone: repeated calls are bitwise equal, small calls never probe, a forced
+    engine is obeyed, and all of them agree with the oracle."""
+    cases = [(ne.gnm_scalable(20000, 80000, 3), 4), (ne.ba_scalable(12000, 3, 4, 7), 4), (ne.SwEnsemble(12000, 0.05, 9), 2)]
+    for e, want in cases:
+        rp, col = e.export_csr()
+        n = len(rp) - 1
+        dg = ctx.upload(rp, col)
+        few = np.arange(0, n, n // 100, dtype=np.uint32)                  # a small call: no probe, mid engine
+        got_few = dg.vertex_load_sources(few, True)
+        assert ctx.stats()["engine"] == 2
+        assert close(got_few, oracle.vertex_load(rp, col, True, sources=few, threads=0), REL)
+        src = np.arange(0, n, 4, dtype=np.uint32)                         # a large call
+        got = dg.vertex_load_sources(src, True)
+        assert ctx.stats()["engine"] & 15 == want, (n, want, ctx.stats())
+        assert dg.vertex_load_sources(src, True).tobytes() == got.tobytes()
+        wave = dg.wave_size(len(src))
+        if want == 2:
+            assert wave in (min(len(src), 296), min(len(src), 1184))
+        else:
+            assert wave == min(len(src), ctx.stats()["n_slots"] * ctx.stats()["batch_width"])
+        want_load = oracle.vertex_load(rp, col, True, sources=src, threads=0)
+        assert close(got, want_load, REL)
+        ctx.set_engine(2)
+        forced = dg.vertex_load_sources(src, True)
+        assert ctx.stats()["engine"] == 2 and close(forced, want_load, REL) and close(forced, got, 1e-12)
+        ctx.set_engine(0)
+        monkeypatch.setenv("NEC_PROBE", "0")                                # size threshold only
+        dg.vertex_load_sources(src, True)
+        assert ctx.stats()["engine"] == 2
+        monkeypatch.delenv("NEC_PROBE")
+        dg.free()
