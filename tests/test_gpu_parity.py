@@ -875,3 +875,9 @@ def test_engine_is_chosen_by_structure_for_graphs_that_fit_the_mid_engine(ctx, o
         assert ctx.stats()["engine"] == 2
         monkeypatch.delenv("NEC_PROBE")
         dg.free()
+
+
+def test_smoke_entry_point_runs():
+    """The driver's smoke(): kept under test so that a change of defaults cannot break it unnoticed."""
+    import __graft_entry__
+    __graft_entry__.smoke()
