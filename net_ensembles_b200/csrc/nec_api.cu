@@ -816,6 +816,7 @@ int run_sources_wide(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources
     p.bq_base = a.bq; p.bq_stride = a.bq_stride; p.bcnt_base = a.bcnt; p.bslot_hi_off = a.bslot_stride / 2;
     p.batch_status = ctx->d_status; p.counters = ctx->d_counters;
     p.team_size = pl.team; p.team_base = nullptr;
+    p.forward_only = ctx->probe_mode ? 1 : 0;
     if (pl.soft) {                                   // the teams' shared scalars and barrier counters (8 u32 per slot)
         if ((rc = grow(ctx, ctx->d_worklist, ctx->d_worklist_cap, (size_t)slots * 8)) != NEC_OK) return rc;
         NEC_CUDA(ctx, cudaMemsetAsync(ctx->d_worklist, 0, (size_t)slots * 8 * sizeof(uint32_t), ctx->stream));
@@ -1051,7 +1052,7 @@ int run_sources_mid(nec_ctx *ctx, const nec_graph *g, const uint32_t *h_sources,
 // batched engine pays per source is proportional to the number of distinct BFS levels a vertex sits on within a batch (queue
 // entries per vertex: ~4 on random and scale-free graphs, where it is 1.3-5 x faster than one source per CTA from n = 8192 up;
 // 9 and more on small-world rings and lattices, where it is slower: scripts/exp_engine_choice.py, profiles/r2_engine_choice.log).
-// So the first large call on such a graph runs a probe (vertex ids 0..255 as four 64-source batches, result discarded, ~1-7 ms) and the finding is
+// So the first large call on such a graph runs a probe (the forward pass of vertex ids 0..255 as four 64-source batches, < 1 ms) and the finding is
 // kept with the graph: a pure function of the graph, hence the same engine - and bitwise the same result - call after call.
 constexpr uint32_t kProbeMinN = 8192;            // below: the mid engine's small CTAs win whatever the structure
 constexpr uint32_t kProbeMinSources = 512;       // below: not worth a probe; one wave of the mid engine
@@ -1074,7 +1075,7 @@ int engine_hint(nec_ctx *ctx, const nec_graph *g, int *hint) {
             g->engine_hint = g->probe_entries <= kProbeMaxEntries ? 4 : 2;
         }
         if (getenv("NEC_PROBE_VERBOSE")) fprintf(stderr, "[nec] probe: n=%u, %.2f queue entries per vertex in one batch -> %s engine\n", g->n, g->probe_entries, g->engine_hint == 4 ? "compact batched" : "mid");
-        if (g->engine_hint == 2 && ctx->wide.base) {       // the probe's slot is of no further use
+        if (g->engine_hint == 2 && ctx->wide.base && ctx->wide.bytes > (1ull << 30)) {       // the probe's slots are of no further use (small ones stay for the next graph's probe)
             NEC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->wide.base);
             ctx->wide = WideArena{};

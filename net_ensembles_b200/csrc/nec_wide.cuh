@@ -106,6 +106,9 @@ struct WideParams {
     // scalars and barrier counter live in global memory (8 u32 per slot: tail, fail, open, pos, barrier, -, -, -)
     uint32_t team_size;
     uint32_t *team_base;
+    // != 0: stop after the forward pass and only count the queue entries (counters[2]): the planner's probe of how many distinct
+    // levels a vertex sits on within a batch (nec_api.cu, engine_hint); nothing is added to the partial loads
+    int forward_only;
 };
 
 struct alignas(16) WideVec256 { uint4 a, b; };
@@ -518,6 +521,11 @@ wide_engine(const WideParams p) {
         const uint32_t depth = level - 1;
         if (threadIdx.x == 0) { const long long t = clock64(); cyc_fwd += t - t_phase; t_phase = t; }
         if (depth > my_depth) my_depth = depth;
+        if (p.forward_only) {
+            if (tid_t == 0) { atomicAdd(&s_cnt[2], (unsigned long long)qend); p.batch_status[batch] = kDone; }
+            team_sync();
+            continue;
+        }
 
         // ---- backward: levels depth .. 1 ----------------------------------------------------------------------
         // prepare(L): every entry of level L gets the position of its run in qc (prefix sums per warp, one atomic on
