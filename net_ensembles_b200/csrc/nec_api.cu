@@ -701,11 +701,17 @@ int plan_wide(nec_ctx *ctx, uint32_t n, uint32_t n_sources, WidePlan &out) {
     const uint32_t max_levels = n;
     // queue entries per vertex the slot has room for: a vertex sits on a handful of distinct levels within one batch
     // on the graphs this engine is meant for; batches that need more are handed to the source-minor engine
-    size_t per_vertex = 12;
-    if (const char *env = getenv("NEC_WIDE_QUEUE")) per_vertex = (size_t)std::max(1, atoi(env));
+    // A dozen suffices on random graphs (5 at 256 per batch); small-world graphs need ~14 (half the batches of the N=2^16 config overflow a
+    // queue of 12: 28 against 53 GTEPS).  Room for 24 is planned wherever it costs no speed (with software teams fewer, larger teams run
+    // as fast as many small ones), 12 where memory is so short that it would.
+    size_t per_vertex_opts[2] = {24, 12};
+    int n_opts = 2;
+    if (const char *env = getenv("NEC_WIDE_QUEUE")) { per_vertex_opts[0] = (size_t)std::max(1, atoi(env)); n_opts = 1; }
     WidePlan best{};
     double best_cost = 1e300;
+    for (int opt = 0; opt < n_opts; ++opt)
     for (uint32_t kw : {256u, 128u, 64u}) {
+        const size_t per_vertex = per_vertex_opts[opt];
         if (ctx->probe_mode) { if (kw != 64u) continue; }               // engine_hint's probe: four 64-source batches, whatever the knobs say
         else if (const char *env = getenv("NEC_WIDE_WIDTH")) { if ((uint32_t)atoi(env) != kw) continue; }
         if ((uint64_t)n * kw + kw >= 0xFFFFFFFFull) continue;           // 32-bit positions and queue indices
