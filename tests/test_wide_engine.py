@@ -193,3 +193,28 @@ def test_default_plan_hands_a_lattice_back_and_the_deep_path_finishes_it(ctx, or
     assert st["engine"] & 15 == 4 and st["requeued_batches"] >= 1 and st["max_depth"] == 2 * (side - 1)
     assert close(got, oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
     dg.free()
+
+
+def test_planner_queue_room_follows_the_memory_it_is_given(ctx, oracle):
+    """Room for 24 queue entries per vertex where it costs no speed, a dozen where the workspace is short - and either way
+    the same loads (per-batch values do not depend on the queue's size), equal to the oracle's."""
+    g = ne.gnm_scalable(30000, 120000, 9)
+    rp, col = g.export_csr()
+    n = len(rp) - 1
+    dg = ctx.upload(rp, col)
+    ctx.set_engine(3)
+    src = np.arange(0, n, 5, dtype=np.uint32)                      # 6000 sources = 24 batches of 256
+    roomy = dg.vertex_load_sources(src, True)
+    st_roomy = ctx.stats()
+    per_slot_roomy = st_roomy["workspace_bytes"] / st_roomy["n_slots"]
+    limit = int(st_roomy["workspace_bytes"] * 0.3)                 # 7 slots with the long queue, 8 with the short one: one wave fewer
+    ctx.set_workspace_limit(limit)
+    tight = dg.vertex_load_sources(src, True)
+    st_tight = ctx.stats()
+    assert st_tight["engine"] == 4 and st_tight["requeued_batches"] == 0 and st_tight["n_slots"] < st_roomy["n_slots"]
+    assert st_tight["workspace_bytes"] <= limit
+    assert st_tight["workspace_bytes"] / st_tight["n_slots"] < per_slot_roomy          # the dozen
+    assert close(tight, roomy, 1e-12) and close(roomy, oracle.vertex_load(rp, col, True, sources=src, threads=0), REL)
+    ctx.set_workspace_limit(0)
+    ctx.set_engine(0)
+    dg.free()
