@@ -1070,9 +1070,10 @@ int engine_hint(nec_ctx *ctx, const nec_graph *g, int *hint) {
         for (uint32_t k = 0; k < cnt; ++k) probe[k] = k;
         int rc = grow(ctx, ctx->d_tmp, ctx->d_tmp_cap, g->n);
         if (rc != NEC_OK) return rc;
-        ctx->probe_mode = true;
-        rc = run_sources_wide(ctx, g, probe.data(), cnt, 1, ctx->d_tmp);
-        ctx->probe_mode = false;
+        {
+            struct ProbeMode { nec_ctx *c; explicit ProbeMode(nec_ctx *x) : c(x) { c->probe_mode = true; } ~ProbeMode() { c->probe_mode = false; } } guard(ctx);
+            rc = run_sources_wide(ctx, g, probe.data(), cnt, 1, ctx->d_tmp);
+        }
         if (rc == NEC_ENOMEM) { g->engine_hint = 2; g->probe_entries = -1.f; }          // no room for a slot: the mid engine it is
         else if (rc != NEC_OK) return rc;
         else {
