@@ -503,7 +503,7 @@ def secondary_lines(local_rank):
     measured value, e2e, roofline and parity figure for every config, not only the headline one."""
     import net_ensembles_b200 as ne
     out = {}
-    for name, (k, w) in (("erc1000", (20, 5)), ("sw65536", (3, 2)), ("ba2p22", (1, 1))):
+    for name, (k, w) in (("erc1000", (20, 5)), ("sw65536", (3, 2)), ("ba2p22", (2, 1))):
         try:
             ln = measure_graph(name, k, w, 0, 1, local_rank, with_cpu_baseline=(name != "ba2p22"), e2e_steps=3)
             out[name] = {key: ln.get(key) for key in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "details",
