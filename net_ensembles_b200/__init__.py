@@ -6,7 +6,9 @@ operator interface for this path (`Graph`, `SwGraph`-backed `SwEnsemble`, `ErEns
 `ErEnsembleM`, `BAensemble`, each with `vertex_load(include_endpoints)`).
 """
 from .api import (BAensemble, ChainBatch, Context, DeviceGraph, ErEnsembleC, ErEnsembleM, Graph, NecError,  # noqa: F401
-                  SwEnsemble, chains_step_and_load, default_context, gnm_scalable, ba_scalable, vertex_load_batch)
+                  SavedState, SwEnsemble, chains_step_and_load, default_context, dump_serde_json, gnm_scalable, ba_scalable,
+                  graph_from_adjacency, load_serde_json, vertex_load_batch)
 
 __all__ = ["Context", "DeviceGraph", "Graph", "ErEnsembleC", "ErEnsembleM", "SwEnsemble", "BAensemble",
-           "NecError", "ChainBatch", "chains_step_and_load", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch"]
+           "NecError", "ChainBatch", "chains_step_and_load", "default_context", "gnm_scalable", "ba_scalable", "vertex_load_batch",
+           "SavedState", "load_serde_json", "dump_serde_json", "graph_from_adjacency"]

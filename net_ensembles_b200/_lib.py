@@ -57,6 +57,7 @@ NEC_SYMBOLS = {
 NECH_SYMBOLS = {
     "nech_last_error": (ctypes.c_char_p, []),
     "nech_graph_new": (c_vp, [c_u64]),
+    "nech_graph_from_adjacency": (c_vp, [c_u64, c_vp, c_vp]),
     "nech_erc_new": (c_vp, [c_u64, c_dbl, c_u64]),
     "nech_erm_new": (c_vp, [c_u64, c_u64, c_u64]),
     "nech_sw_new": (c_vp, [c_u64, c_dbl, c_u64, c_u64]),

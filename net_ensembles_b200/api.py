@@ -405,6 +405,7 @@ class ErEnsembleC(_Ensemble):
 
     def __init__(self, n, c_target, seed):
         super().__init__(_lib.load_host().nech_erc_new(n, c_target, seed))
+        self._params = {"prob": float(c_target) / (n - 1) if n > 1 else 0.0, "c_target": float(c_target)}   # er_c.rs: prob = c_target / (n - 1)
 
     def randomize_cuda(self, ctx=None):
         """`randomize()` (src/er_c.rs:128-143) drawn ON THE DEVICE with Pcg64 jump-ahead: same graph, same adjacency
@@ -421,6 +422,7 @@ class ErEnsembleM(_Ensemble):
 
     def __init__(self, n, m, seed):
         super().__init__(_lib.load_host().nech_erm_new(n, m, seed))
+        self._params = {"m": int(m)}
 
 
 class SwEnsemble(_Ensemble):
@@ -428,6 +430,7 @@ class SwEnsemble(_Ensemble):
 
     def __init__(self, n, r_prob, seed, ring_distance=2):
         super().__init__(_lib.load_host().nech_sw_new(n, r_prob, seed, ring_distance))
+        self._params = {"r_prob": float(r_prob)}
 
     def root_targets(self):
         out = np.empty(int(self._lib.nech_nnz(self._h)), np.uint32)
@@ -450,3 +453,120 @@ def gnm_scalable(n, m, seed):
 def ba_scalable(n, m, source_n, seed):
     """Barabasi-Albert for sizes the crate's BAensemble cannot reach; not seed-identical."""
     return Graph(n, _handle=_lib.load_host().nech_ba_scalable(n, m, source_n, seed))
+
+
+# ------------------------------------------------------------------------------------------------
+# The crate's serde save-states (`serde_support`, e.g. generic_graph.rs:31-32, er_c.rs:71-80; lib.rs:147-180 shows the
+# save / resume idiom; TestData/unchaning_*.json are such dumps).  The format on the INPUT side of the path: a topology
+# stored by the crate goes to the GPU with its adjacency order intact.
+# ------------------------------------------------------------------------------------------------
+class SavedState:
+    """What a serde_json dump of a Graph / ErEnsembleC / ErEnsembleM / SwEnsemble holds for this path.
+
+    kind         "graph" | "erc" | "erm" | "sw"
+    graph        host `Graph` with exactly the stored adjacency lists (order preserved); `.vertex_load(...)`, `.to_device(ctx)`
+    params       the ensemble's parameters as stored (prob / c_target, m, r_prob)
+    rng          (state, increment) of the Pcg64 as Python ints, or None
+    root_targets small-world only: per adjacency entry the `originally_to` of a root edge, -1 for a loose entry (CSR order)
+    """
+
+    def __init__(self, kind, graph, params, rng, root_targets):
+        self.kind, self.graph, self.params, self.rng, self.root_targets = kind, graph, params, rng, root_targets
+
+    def vertex_load(self, include_endpoints, ctx=None):
+        return self.graph.vertex_load(include_endpoints, ctx)
+
+
+def graph_from_adjacency(adjacency):
+    """Host `Graph` whose adjacency lists are exactly `adjacency` (list of lists of neighbour ids), in that order.
+    Raises ValueError on ids out of range, self-loops, repeated entries or entries without a counterpart."""
+    n = len(adjacency)
+    row_ptr = np.zeros(n + 1, np.uint64)
+    row_ptr[1:] = np.cumsum([len(a) for a in adjacency], dtype=np.uint64)
+    flat = [x for a in adjacency for x in a]
+    if any((not isinstance(x, (int, np.integer))) or x < 0 or x >= max(n, 1) for x in flat):
+        raise ValueError("graph_from_adjacency: neighbour id out of range")
+    col = np.asarray(flat, dtype=np.uint32) if flat else np.zeros(0, np.uint32)
+    lib = _lib.load_host()
+    handle = lib.nech_graph_from_adjacency(n, _ptr(row_ptr), _ptr(col))
+    if not handle:
+        raise ValueError(lib.nech_last_error().decode())
+    return Graph(n, _handle=handle)
+
+
+def load_serde_json(src):
+    """Parses a serde_json dump of the crate (`src`: path, open file, JSON text or the parsed dict) into a SavedState.
+    Layout: {"graph": {"next_id", "edge_count", "vertices": [{"id", "adj": [...], "node": ...}], "phantom"},
+    <parameters>, "rng": {"state", "increment"}}; a bare Graph is the inner object alone; small-world adjacency entries are
+    {"to": k, "originally_to": null | k0}.  Unknown keys (ErM's edge lists, node payloads) are ignored."""
+    import json
+    if isinstance(src, dict):
+        doc = src
+    elif hasattr(src, "read"):
+        doc = json.load(src)
+    elif isinstance(src, str) and src.lstrip().startswith("{"):
+        doc = json.loads(src)
+    else:
+        with open(src) as fh:
+            doc = json.load(fh)
+    inner = doc["graph"] if "graph" in doc else doc
+    if "vertices" not in inner:
+        raise ValueError("load_serde_json: no `vertices` array (not a net_ensembles graph dump)")
+    verts = inner["vertices"]
+    n = len(verts)
+    if "next_id" in inner and int(inner["next_id"]) != n:
+        raise ValueError("load_serde_json: next_id %s does not match %d vertices" % (inner["next_id"], n))
+    adjacency, roots, is_sw = [], [], False
+    for i, v in enumerate(verts):
+        if int(v.get("id", i)) != i:
+            raise ValueError("load_serde_json: vertex %d carries id %s" % (i, v.get("id")))
+        row = []
+        for e in v["adj"]:
+            if isinstance(e, dict):
+                is_sw = True
+                row.append(int(e["to"]))
+                roots.append(-1 if e.get("originally_to") is None else int(e["originally_to"]))
+            else:
+                row.append(int(e))
+                roots.append(-1)
+        adjacency.append(row)
+    g = graph_from_adjacency(adjacency)
+    if "edge_count" in inner and int(inner["edge_count"]) != g.edge_count():
+        raise ValueError("load_serde_json: edge_count %s does not match the %d edges of the lists" % (inner["edge_count"], g.edge_count()))
+    kind = "graph"
+    if "graph" in doc:
+        kind = "erc" if "c_target" in doc else "erm" if "m" in doc else "sw" if ("r_prob" in doc or is_sw) else "graph"
+    params = {k: doc[k] for k in ("prob", "c_target", "m", "r_prob") if k in doc}
+    rng = None
+    if isinstance(doc.get("rng"), dict) and "state" in doc["rng"]:
+        rng = (int(doc["rng"]["state"]), int(doc["rng"]["increment"]))
+    return SavedState(kind, g, params, rng, np.asarray(roots, dtype=np.int64) if is_sw else None)
+
+
+def dump_serde_json(ensemble, path=None):
+    """The inverse for this package's ensembles (ErEnsembleC / ErEnsembleM / SwEnsemble / Graph): a dict in the crate's
+    layout holding what this path produces and needs - topology in storage order, parameters passed in, generator state.
+    (ErM's private edge lists are not written: the crate cannot resume an ErEnsembleM from it; the others it can.)"""
+    import json
+    adj = ensemble.adjacency()
+    roots = ensemble.root_targets() if isinstance(ensemble, SwEnsemble) else None
+    verts, at = [], 0
+    for i, row in enumerate(adj):
+        if roots is None:
+            entries = [int(x) for x in row]
+        else:
+            entries = [{"to": int(x), "originally_to": (None if int(roots[at + k]) < 0 or int(roots[at + k]) == 0xFFFFFFFF else int(roots[at + k]))} for k, x in enumerate(row)]
+        at += len(row)
+        verts.append({"id": i, "adj": entries, "node": {}})
+    inner = {"next_id": len(adj), "edge_count": ensemble.edge_count(), "vertices": verts, "phantom": None}
+    if isinstance(ensemble, _Ensemble):
+        doc = {"graph": inner}
+        doc.update(getattr(ensemble, "_params", {}))
+        state, inc = ensemble.rng_state()
+        doc["rng"] = {"state": state, "increment": inc}
+    else:
+        doc = inner
+    if path is not None:
+        with open(path, "w") as fh:
+            json.dump(doc, fh)
+    return doc

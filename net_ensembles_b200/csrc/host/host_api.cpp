@@ -60,6 +60,35 @@ void *nech_gnm_scalable(uint64_t n, uint64_t m, uint64_t seed) {
 void *nech_ba_scalable(uint64_t n, uint64_t m, uint64_t source_n, uint64_t seed) {
     return guarded([&]() -> void * { auto h = new Handle{Kind::Plain}; h->plain.reset(new Graph(ba_scalable(n, m, source_n, Pcg64::seed_from_u64(seed)))); return h; }, nullptr);
 }
+// A plain graph with EXACTLY these adjacency lists, in this order (the order defines the rounding of vertex_load and is
+// what the crate's serde save-states store: graph.vertices[i].adj).  Validated: ids < n, no self-loops, no repeated entry
+// within a list, every entry (v, x) matched by an entry (x, v).
+void *nech_graph_from_adjacency(uint64_t n, const uint64_t *row_ptr, const uint32_t *col_idx) {
+    return guarded([&]() -> void * {
+        if (n > 0 && (!row_ptr || row_ptr[0] != 0)) throw std::runtime_error("nech_graph_from_adjacency: row_ptr must start at 0");
+        std::unique_ptr<Graph> g(new Graph(n));
+        for (uint64_t v = 0; v < n; ++v) {
+            if (row_ptr[v + 1] < row_ptr[v]) throw std::runtime_error("nech_graph_from_adjacency: row_ptr not monotone");
+            auto &adj = g->vertices[v].adj;
+            adj.reserve(row_ptr[v + 1] - row_ptr[v]);
+            for (uint64_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+                const uint32_t x = col_idx[e];
+                if (x >= n) throw std::runtime_error("nech_graph_from_adjacency: neighbour id out of range (vertex " + std::to_string(v) + ")");
+                if (x == v) throw std::runtime_error("nech_graph_from_adjacency: self-loop at vertex " + std::to_string(v));
+                if (g->vertices[v].is_adjacent(x)) throw std::runtime_error("nech_graph_from_adjacency: repeated entry in the list of vertex " + std::to_string(v));
+                adj.push_back(PlainEdge{x});
+            }
+        }
+        for (uint64_t v = 0; v < n; ++v)
+            for (const auto &e : g->vertices[v].adj)
+                if (!g->vertices[e.to].is_adjacent((uint32_t)v))
+                    throw std::runtime_error("nech_graph_from_adjacency: entry (" + std::to_string(v) + ", " + std::to_string(e.to) + ") has no counterpart");
+        g->edge_count = (n ? row_ptr[n] : 0) / 2;
+        auto h = new Handle{Kind::Plain};
+        h->plain = std::move(g);
+        return h;
+    }, nullptr);
+}
 void nech_free(void *p) { delete static_cast<Handle *>(p); }
 
 uint64_t nech_vertex_count(const void *p) {
