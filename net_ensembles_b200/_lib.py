@@ -58,6 +58,9 @@ NECH_SYMBOLS = {
     "nech_last_error": (ctypes.c_char_p, []),
     "nech_graph_new": (c_vp, [c_u64]),
     "nech_graph_from_adjacency": (c_vp, [c_u64, c_vp, c_vp]),
+    "nech_restore": (c_vp, [c_int, c_u64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_u64, c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, c_u64]),
+    "nech_erm_list_size": (c_u64, [c_vp, c_int]),
+    "nech_erm_list": (c_int, [c_vp, c_int, c_vp]),
     "nech_erc_new": (c_vp, [c_u64, c_dbl, c_u64]),
     "nech_erm_new": (c_vp, [c_u64, c_u64, c_u64]),
     "nech_sw_new": (c_vp, [c_u64, c_dbl, c_u64, c_u64]),

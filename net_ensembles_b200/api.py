@@ -470,11 +470,45 @@ class SavedState:
     root_targets small-world only: per adjacency entry the `originally_to` of a root edge, -1 for a loose entry (CSR order)
     """
 
-    def __init__(self, kind, graph, params, rng, root_targets):
+    def __init__(self, kind, graph, params, rng, root_targets, erm_lists=None):
         self.kind, self.graph, self.params, self.rng, self.root_targets = kind, graph, params, rng, root_targets
+        self.erm_lists = erm_lists          # ErEnsembleM: (all_edges, possible_edges, current_edges) as (k, 2) uint32 arrays, or None
 
     def vertex_load(self, include_endpoints, ctx=None):
         return self.graph.vertex_load(include_endpoints, ctx)
+
+    def resume(self):
+        """A live ensemble of this package in exactly the saved state - lists, parameters, generator, ErM's edge lists, Sw's root
+        edges - so that `m_steps` / `randomize` continue as the crate's own would (lib.rs:147-180, the resume idiom).  Nothing
+        is drawn on the way."""
+        if self.kind not in ("erc", "erm", "sw") or self.rng is None:
+            raise ValueError("resume: the save-state holds no ensemble with a generator (kind %r)" % self.kind)
+        rp, col = self.graph.export_csr()
+        n = len(rp) - 1
+        mask = (1 << 64) - 1
+        rng4 = np.array([self.rng[0] & mask, self.rng[0] >> 64, self.rng[1] & mask, self.rng[1] >> 64], dtype=np.uint64)
+        lib = _lib.load_host()
+        none = None
+        if self.kind == "erc":
+            cls, params = ErEnsembleC, {"prob": float(self.params["prob"]), "c_target": float(self.params["c_target"])}
+            h = lib.nech_restore(1, n, _ptr(rp), _ptr(col), none, params["c_target"], params["prob"], 0, _ptr(rng4), none, 0, none, 0, none, 0)
+        elif self.kind == "erm":
+            if self.erm_lists is None:
+                raise ValueError("resume: an ErEnsembleM needs its all_edges / possible_edges / current_edges lists")
+            cls, params = ErEnsembleM, {"m": int(self.params["m"])}
+            al, po, cu = (np.ascontiguousarray(x, dtype=np.uint32).reshape(-1, 2) for x in self.erm_lists)
+            h = lib.nech_restore(2, n, _ptr(rp), _ptr(col), none, 0.0, 0.0, params["m"], _ptr(rng4),
+                                 _ptr(al), len(al), _ptr(po), len(po), _ptr(cu), len(cu))
+        else:
+            cls, params = SwEnsemble, {"r_prob": float(self.params["r_prob"])}
+            roots = np.where(self.root_targets < 0, 0xFFFFFFFF, self.root_targets).astype(np.uint32)
+            h = lib.nech_restore(3, n, _ptr(rp), _ptr(col), _ptr(roots), params["r_prob"], 0.0, 0, _ptr(rng4), none, 0, none, 0, none, 0)
+        if not h:
+            raise ValueError(lib.nech_last_error().decode())
+        e = cls.__new__(cls)
+        _HostGraph.__init__(e, h)
+        e._params = params
+        return e
 
 
 def graph_from_adjacency(adjacency):
@@ -540,13 +574,16 @@ def load_serde_json(src):
     rng = None
     if isinstance(doc.get("rng"), dict) and "state" in doc["rng"]:
         rng = (int(doc["rng"]["state"]), int(doc["rng"]["increment"]))
-    return SavedState(kind, g, params, rng, np.asarray(roots, dtype=np.int64) if is_sw else None)
+    erm_lists = None
+    if kind == "erm" and all(k in doc for k in ("all_edges", "possible_edges", "current_edges")):
+        erm_lists = tuple(np.asarray(doc[k], dtype=np.uint32).reshape(-1, 2) for k in ("all_edges", "possible_edges", "current_edges"))
+    return SavedState(kind, g, params, rng, np.asarray(roots, dtype=np.int64) if is_sw else None, erm_lists)
 
 
 def dump_serde_json(ensemble, path=None):
     """The inverse for this package's ensembles (ErEnsembleC / ErEnsembleM / SwEnsemble / Graph): a dict in the crate's
-    layout holding what this path produces and needs - topology in storage order, parameters passed in, generator state.
-    (ErM's private edge lists are not written: the crate cannot resume an ErEnsembleM from it; the others it can.)"""
+    layout - topology in storage order, parameters, generator state, ErEnsembleM's three edge lists - i.e. everything the
+    crate's Deserialize needs to resume the ensemble."""
     import json
     adj = ensemble.adjacency()
     roots = ensemble.root_targets() if isinstance(ensemble, SwEnsemble) else None
@@ -564,6 +601,12 @@ def dump_serde_json(ensemble, path=None):
         doc.update(getattr(ensemble, "_params", {}))
         state, inc = ensemble.rng_state()
         doc["rng"] = {"state": state, "increment": inc}
+        if isinstance(ensemble, ErEnsembleM):
+            for which, key in enumerate(("all_edges", "possible_edges", "current_edges")):
+                pairs = np.empty((int(ensemble._lib.nech_erm_list_size(ensemble._h, which)), 2), np.uint32)
+                if ensemble._lib.nech_erm_list(ensemble._h, which, _ptr(pairs)) != 0:
+                    raise ValueError(ensemble._lib.nech_last_error().decode())
+                doc[key] = pairs.tolist()
     else:
         doc = inner
     if path is not None:

@@ -208,6 +208,8 @@ struct ErEnsembleC {
     double c_target, prob;
     Pcg64 rng;
     ErEnsembleC(size_t n, double c, Pcg64 r) : graph(n), c_target(c), prob(c / (double)(n - 1)), rng(r) { randomize(); }
+    // resume from a save-state (serde dump of the crate: graph, prob, c_target, rng): nothing is drawn
+    ErEnsembleC(Graph &&g, double c, double p, Pcg64 r) : graph(std::move(g)), c_target(c), prob(p), rng(r) {}
     void randomize() {  // one uniform draw per unordered pair, lexicographic
         graph.clear_edges();
         const size_t n = graph.vertex_count();
@@ -245,6 +247,16 @@ struct ErEnsembleM {
             for (size_t j = i + 1; j < n; ++j) all_edges.emplace_back((uint32_t)i, (uint32_t)j);
         randomize();
     }
+    // resume from a save-state (graph, m, rng and the three pair lists, er_m.rs:157-170)
+    ErEnsembleM(Graph &&g, size_t m_, Pcg64 r, std::vector<Pair> all, std::vector<Pair> possible, std::vector<Pair> current)
+        : graph(std::move(g)), m(m_), rng(r), all_edges(std::move(all)), possible_edges(std::move(possible)), current_edges(std::move(current)) {
+        const size_t n = graph.vertex_count(), total = n * (n - 1) / 2;
+        if (all_edges.size() != total || possible_edges.size() + current_edges.size() != total || current_edges.size() != m || graph.edge_count != m)
+            throw std::invalid_argument("ErEnsembleM: the save-state's edge lists do not fit n and m");
+        for (auto &e : current_edges)
+            if (e.first >= n || e.second >= n || !graph.vertices[e.first].is_adjacent(e.second))
+                throw std::invalid_argument("ErEnsembleM: current_edges names an edge the graph does not have");
+    }
     void randomize() {
         graph.clear_edges();
         shuffle(all_edges, rng);
@@ -272,6 +284,14 @@ struct SwEnsemble {
     SwEnsemble(size_t n, double p, Pcg64 r, size_t ring_distance = 2) : graph(n), r_prob(p), rng(r) {
         graph.init_ring(ring_distance);
         randomize();
+    }
+    // resume from a save-state (graph with its root edges, r_prob, rng); the Markov step assumes two root edges per vertex
+    SwEnsemble(SwGraph &&g, double p, Pcg64 r) : graph(std::move(g)), r_prob(p), rng(r) {
+        for (size_t v = 0; v < graph.vertex_count(); ++v) {
+            size_t roots = 0;
+            for (auto &e : graph.vertices[v].adj) roots += e.is_root() ? 1 : 0;
+            if (roots != 2) throw std::invalid_argument("SwEnsemble: a vertex of the save-state does not have two root edges");
+        }
     }
     SwChange randomize_edge(uint32_t i0, uint32_t i1) {
         if (rng.gen_f64() <= r_prob) {

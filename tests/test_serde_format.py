@@ -98,3 +98,70 @@ def test_loaded_topology_gives_bitwise_the_load_of_its_ensemble(ctx, oracle, tmp
         rp, col = e.export_csr()
         want = oracle.vertex_load(rp, col, True)
         assert float(np.max(np.abs(mine - want) / np.maximum(np.abs(want), 1.0))) <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["erc_1", "erm_1", "sw_1", "sw_2", "sw_4"])
+def test_resumed_ensemble_continues_like_the_one_it_was_saved_from(built, golden, name, tmp_path):
+    """dump -> load -> resume, then both copies take the same Markov steps and the same randomize(): lists (order included),
+    small-world root targets, ErM's edge lists and the generator stay identical."""
+    g = golden["graphs"][name]
+    original = MAKERS[g["kind"]](g)
+    original.m_steps(37)
+    copy = ne.load_serde_json(ne.dump_serde_json(original, str(tmp_path / "s.json"))).resume()
+    assert type(copy) is type(original) and copy.rng_state() == original.rng_state() and copy.adjacency() == original.adjacency()
+    for action in (lambda e: e.m_steps(500), lambda e: e.randomize(), lambda e: e.m_steps(123)):
+        action(original), action(copy)
+        assert copy.adjacency() == original.adjacency() and copy.rng_state() == original.rng_state()
+        if g["kind"] == "sw":
+            assert copy.root_targets().tolist() == original.root_targets().tolist()
+    assert ne.dump_serde_json(copy) == ne.dump_serde_json(original)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TestData"), reason="the reference checkout exists in the build container only")
+@pytest.mark.parametrize("name", ["erc_1", "erc_2", "erm_1", "erm_2", "sw_1", "sw_2", "sw_3", "sw_4"])
+def test_reference_dumps_resume_into_the_state_the_seeded_constructor_gives(built, golden, name):
+    """The reference's TestData dumps are the state right after construction: resuming one must give an ensemble that
+    is indistinguishable from ours built from the same seed - including ErM's private edge lists - now and after steps."""
+    g = golden["graphs"][name]
+    with open("/root/reference/TestData/unchaning_%s.json" % name) as fh:
+        raw = json.load(fh)
+    resumed, built_here = ne.load_serde_json(raw).resume(), MAKERS[g["kind"]](g)
+    mine = ne.dump_serde_json(built_here)
+    for key in ("all_edges", "possible_edges", "current_edges", "rng", "m", "r_prob", "c_target", "prob"):
+        assert mine.get(key) == raw.get(key), key
+    assert [v["adj"] for v in mine["graph"]["vertices"]] == [v["adj"] for v in raw["graph"]["vertices"]]
+    for e in (resumed, built_here):
+        e.m_steps(300)
+    assert resumed.adjacency() == built_here.adjacency() and resumed.rng_state() == built_here.rng_state()
+
+
+def test_resume_rejects_states_that_do_not_fit(built):
+    e = ne.SwEnsemble(30, 0.3, 3)
+    doc = ne.dump_serde_json(e)
+    broken = json.loads(json.dumps(doc))
+    for entry in broken["graph"]["vertices"][0]["adj"]:
+        entry["originally_to"] = None                              # vertex 0 loses its root edges
+    with pytest.raises(ValueError, match="root"):
+        ne.load_serde_json(broken).resume()
+    m = ne.dump_serde_json(ne.ErEnsembleM(12, 20, 5))
+    m["current_edges"] = m["current_edges"][:-1]
+    with pytest.raises(ValueError, match="edge lists"):
+        ne.load_serde_json(m).resume()
+    with pytest.raises(ValueError, match="no ensemble"):
+        ne.load_serde_json(ne.dump_serde_json(ne.Graph(4))).resume()
+
+
+@pytest.mark.gpu
+def test_resumed_chains_run_device_resident_like_their_originals(ctx, tmp_path):
+    """Checkpoint / resume around the batched Markov-chain path: chains saved, resumed and put into a ChainBatch give
+    bitwise the loads of the chains they were saved from, step after step."""
+    originals = [ne.ErEnsembleC(96, 4.0, 500 + g) for g in range(40)]
+    for e in originals:
+        e.m_steps(10)
+    copies = [ne.load_serde_json(ne.dump_serde_json(e)).resume() for e in originals]
+    a, b = ne.ChainBatch(originals), ne.ChainBatch(copies)
+    for _ in range(3):
+        ra, rb = a.step_and_load(ctx, 5, True), b.step_and_load(ctx, 5, True)
+        assert ra.tobytes() == rb.tobytes()
+    assert [e.adjacency() for e in originals] == [e.adjacency() for e in copies]
+    a.close(), b.close()
